@@ -1,0 +1,147 @@
+/* rslam.h -- C ABI of the B200-native 1-point-RANSAC EKF measurement-update path.
+ *
+ * This is the drop-in boundary for plumewind/ransac_slam's hot path.  The reference has no plugin/FFI layer: the
+ * boundary there is the set of C++ methods that System::TrackRunning calls (src/System.cpp:111-129) plus the public
+ * members of ExtendKF (include/ransac_slam/ExtendKF.h:154-169).  Each entry point below names the reference method it
+ * replaces; the C++ classes in ransac_slam_b200/host/ (same names and signatures as the reference's ExtendKF / Tracking /
+ * Map) are thin callers of this ABI.  Plain C types only; no Eigen / OpenCV / STL / torch types cross the boundary.
+ *
+ * Conventions
+ *   - every function returns RSLAM_OK (0) or a negative rslam_status; rslam_last_error() gives the text.
+ *   - a handle owns `batch` independent filters that are stepped together (batch == 1 for the reference's single
+ *     filter; batch == 4096 for the batched-filter configuration).  Per-filter transfers take the filter index `b`.
+ *   - all device work of a handle is issued on the handle's own CUDA stream and is asynchronous; rslam_sync() or any
+ *     download waits for it.  Calls on one handle are not re-entrant; different handles are independent.
+ *   - state layout: x = [r(3) q(4: w,x,y,z) v(3) w(3) | y_1 ... y_N], inverse-depth y = (x,y,z,theta,phi,rho) (6) or
+ *     cartesian y = (X,Y,Z) (3) (src/ExtendKF.cpp:137-152).  P is column-major n x n with leading dimension ldp, i.e.
+ *     exactly Eigen's MatrixXd::data() of the reference's p_k_k.
+ *   - pointer arguments documented "host or device" may point to either (unified virtual addressing decides).
+ *   - the library keeps ONE covariance per filter, updated in place: after rslam_ekf_prediction it is p_k_km1, after
+ *     rslam_update_li / rslam_update_hi it is p_k_k (the reference keeps both as separate Eigen members).
+ *   - there is no CPU fallback: every entry point fails with RSLAM_ERR_CUDA if no sm_100 device is usable.
+ */
+#ifndef RSLAM_H
+#define RSLAM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rslam_filter rslam_filter; /* opaque */
+
+typedef enum {
+    RSLAM_OK = 0,
+    RSLAM_ERR_INVALID = -1,   /* bad argument */
+    RSLAM_ERR_CUDA = -2,      /* CUDA runtime error / no device */
+    RSLAM_ERR_CAPACITY = -3,  /* exceeds max_features / workspace limits given at create */
+    RSLAM_ERR_REFERENCE_UB = -4 /* input on which the reference itself is undefined: cartesian matches in RANSAC */
+} rslam_status;
+
+/* include/ransac_slam/System.h:69-82 (CamParam), filled from initialize_param.yaml at src/System.cpp:34-58 */
+typedef struct {
+    double k1, k2;
+    int nRows, nCols;
+    double Cx, Cy, f, dx, dy;
+} rslam_camera;
+
+/* reference behaviours that change results; set bit = behave like the reference */
+#define RSLAM_Q1_ANGLES_FROM_POSITIONS 0x1u /* src/Tracking.cpp:448 */
+#define RSLAM_Q4_JNORM_INT_EXPONENT 0x2u    /* src/ExtendKF.cpp:627 */
+#define RSLAM_Q6_RESCUE_WITHOUT_R 0x4u      /* src/Tracking.cpp:589 */
+#define RSLAM_Q_ALL 0x7u
+
+typedef struct {
+    double std_a, std_alpha, std_z; /* Sigma.a / Sigma.alpha / Sigma.noise (src/ExtendKF.cpp:16-18) */
+    double chi2_095_2;              /* 5.9915 (src/Tracking.cpp:283,576) */
+    double corr_threshold;          /* 0.80   (src/Tracking.cpp:281) */
+    double p_spurious_free;         /* 0.99   (src/Tracking.cpp:354) */
+    int n_hyp_initial;              /* 1000   (src/Tracking.cpp:357) */
+    double max_ellipse_eig;         /* 100    (src/Tracking.cpp:303) */
+    unsigned quirks;                /* RSLAM_Q_* mask, default RSLAM_Q_ALL */
+    int dedupe_hypotheses;          /* 1: score each distinct 1-point hypothesis once (identical results) */
+} rslam_params;
+
+typedef struct {
+    int status;        /* 0 ok, 1 no individually-compatible matches (Q9), 3 uniform draws exhausted before termination */
+    int hyp_run;       /* hypotheses evaluated by the reference's sequential loop */
+    int best_support;  /* inlier count of the winning hypothesis */
+    int n_hyp;         /* final adaptive hypothesis budget (src/Tracking.cpp:532) */
+    int num_ic;        /* individually compatible matches */
+    int winner;        /* index (into the uniform sequence) of the winning hypothesis, -1 if none */
+} rslam_ransac_result;
+
+void rslam_default_params(rslam_params* p);
+const char* rslam_last_error(void);
+const char* rslam_version(void);
+
+/* lifecycle.  max_features bounds N per filter; device = CUDA ordinal. */
+int rslam_create(const rslam_camera* cam, const rslam_params* par, int max_features, int batch, int device, rslam_filter** out);
+int rslam_destroy(rslam_filter* f);
+int rslam_sync(rslam_filter* f);
+/* cudaStream_t of the handle (as void*), so callers can record events on the launching stream */
+void* rslam_stream(rslam_filter* f);
+/* number of kernel launches issued by this handle since creation (bench.py's gpu_launches) */
+long long rslam_launch_count(rslam_filter* f);
+int rslam_num_features(rslam_filter* f, int b);
+int rslam_state_dim(rslam_filter* f, int b);
+
+/* state transfer.  Replaces direct access to ExtendKF::x_k_k / p_k_k / features_info (ExtendKF.h:154-169).
+ * feat_types[N]: 0 inverse depth, 1 cartesian.  x, P: host or device.  which: 0 -> x_k_k, 1 -> x_k_km1. */
+int rslam_upload_state(rslam_filter* f, int b, int which, const double* x, const double* P, int n, int ldp, const int* feat_types, int N);
+int rslam_download_state(rslam_filter* f, int b, int which, double* x, double* P, int ldp);
+/* predicted appearance patch_when_matching (13x13 row-major per feature, values must be float-exact) */
+int rslam_upload_patches(rslam_filter* f, int b, const double* patches, int N);
+/* per-feature outputs (any pointer may be NULL): h[2N], S[4N] row-major 2x2, z[2N], flags[4N] = {has_h, individually_compatible,
+ * low_innovation_inlier, high_innovation_inlier}, counters[2N] = {times_predicted, times_measured} */
+int rslam_download_features(rslam_filter* f, int b, double* h, double* S, double* z, uint8_t* flags, int* counters);
+/* structurally non-zero part of H_i: Hc[14N] = d h / d (r,q) (2x7 row-major), Hf[12N] = d h / d y_i (2x6 row-major; 2x3 used for cartesian) */
+int rslam_download_H(rslam_filter* f, int b, double* Hc, double* Hf);
+/* inject matches directly (z[2N], ic[N]) instead of running the active search */
+int rslam_set_matches(rslam_filter* f, int b, const double* z, const uint8_t* ic);
+/* grayscale frame for filter b (host or device).  With share != 0 the same image is used by every filter of the batch. */
+int rslam_set_image(rslam_filter* f, int b, const uint8_t* gray, int rows, int cols, int stride, int share);
+
+/* --- the per-frame path (src/System.cpp:111-129) ------------------------------------------------------------- */
+/* Map::map_management step 2 (src/Map.cpp:34-55): update times_predicted/times_measured, clear per-frame flags */
+int rslam_begin_frame(rslam_filter* f);
+/* ExtendKF::ekf_prediction (src/ExtendKF.cpp:333-388), constant-velocity model */
+int rslam_ekf_prediction(rslam_filter* f);
+/* Tracking::search_IC_matches (src/Tracking.cpp:32-70): h_i, H_i, S_i at x_k_km1, then ZNCC active search on the
+ * image set by rslam_set_image (skipped when no image is set: only h/H/S are produced). */
+int rslam_search_ic_matches(rslam_filter* f);
+/* Tracking::ransac_hypotheses (src/Tracking.cpp:352-539).  u01: batch x n_u01 uniform draws in [0,1) (host or device),
+ * replacing ExtendKF::rand (src/ExtendKF.cpp:220-235). */
+int rslam_ransac_hypotheses(rslam_filter* f, const double* u01, int n_u01);
+int rslam_ransac_result_get(rslam_filter* f, int b, rslam_ransac_result* out);
+/* ExtendKF::ekf_update_li_inliers (src/ExtendKF.cpp:559-596) -> update (:597-639) */
+int rslam_update_li(rslam_filter* f);
+/* Tracking::rescue_hi_inliers (src/Tracking.cpp:574-597) */
+int rslam_rescue_hi(rslam_filter* f);
+/* ExtendKF::ekf_update_hi_inliers (src/ExtendKF.cpp:640-678) -> update */
+int rslam_update_hi(rslam_filter* f);
+/* all of the above in order for one frame.  flags: bit0 = run begin_frame + ekf_prediction first.
+ * images: batch images (or one shared, see rslam_set_image) host or device, may be NULL to keep the current one. */
+int rslam_frame(rslam_filter* f, const uint8_t* images, int rows, int cols, int stride, int share, const double* u01, int n_u01,
+                int flags);
+/* camera pose of filter b after the frame: x_k_k[0..6] plus the 13-state head (13 doubles) */
+int rslam_download_pose(rslam_filter* f, int b, double* x13);
+
+/* --- support-scoring sweep (compute_hypothesis_support_fast, src/Tracking.cpp:424-503; Tracking.h:42) ---------- */
+/* Scores hypotheses [hyp_begin, hyp_end) of the list hyp_match_idx[n_hyp] (each entry: index into the filter's list of
+ * individually compatible matches; host or device) against all matches of filter 0 at (x_k_km1, P).  Writes
+ *   *best_key = (support << 32) | (0xFFFFFFFF - hypothesis id)   (max over the range; 0 if the range is empty)
+ * to best_key (host or device; device lets the caller all-reduce it with NCCL ncclMax without a host round trip), and,
+ * if best_mask != NULL (host), the winner's inlier bit per matched feature (ceil(m/8) bytes, feature order).
+ * n_pairs_scored (host, optional): number of (hypothesis, match) pairs actually evaluated on the device. */
+int rslam_support_sweep(rslam_filter* f, const int* hyp_match_idx, int n_hyp, int hyp_begin, int hyp_end, uint64_t* best_key,
+                        uint8_t* best_mask, long long* n_pairs_scored);
+/* inlier mask of one hypothesis id after a sweep that covered it (for the rank that owns the all-reduced winner) */
+int rslam_sweep_mask(rslam_filter* f, int match_idx, uint8_t* mask);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RSLAM_H */

@@ -1,0 +1,848 @@
+// kernels_track.cuh -- prediction, measurement prediction + Jacobians + S_i, ZNCC active search, 1-point RANSAC.
+// Every kernel takes the array of per-filter descriptors and uses blockIdx.y as the filter index.
+#pragma once
+#include "common.cuh"
+
+namespace rslam {
+
+// ---------------------------------------------------------------------------------------------------------------
+// Map::map_management step 2 (src/Map.cpp:34-55): counters + per-frame flag reset.  One thread per feature.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void k_begin_frame(DevFilter* Fs) {
+    DevFilter& F = Fs[blockIdx.y];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= F.N) return;
+    if (F.has_h[i]) F.times_predicted[i] += 1;
+    if (F.li[i] || F.hi[i]) F.times_measured[i] += 1;
+    F.ic[i] = 0;
+    F.li[i] = 0;
+    F.hi[i] = 0;
+    F.has_h[i] = 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// ExtendKF::ekf_prediction (src/ExtendKF.cpp:333-388), constant velocity, dt = 1.
+//   x_k_km1 = [fv(x_v); y],  P_cc <- F P_cc F^T + Q,  P_cf <- F P_cf,  P_fc <- P_fc F^T,  P_ff untouched (in place).
+// Every CTA recomputes the 13x13 F (cheap); CTA 0 also does the camera block.  Thread j >= 13 owns column/row j.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ void v2q_dev(const double* v, double* q) {  // src/ExtendKF.cpp:428-443 (Q14: zero quaternion below eps)
+    const double theta = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    if (theta < 2.220446049250313e-16) {
+        q[0] = q[1] = q[2] = q[3] = 0.0;
+    } else {
+        const double vn0 = v[0] / theta, vn1 = v[1] / theta, vn2 = v[2] / theta;
+        const double vnn = sqrt(vn0 * vn0 + vn1 * vn1 + vn2 * vn2);
+        const double s = sin(theta / 2.0);
+        q[0] = cos(theta / 2.0);
+        q[1] = s * (vn0 / vnn);
+        q[2] = s * (vn1 / vnn);
+        q[3] = s * (vn2 / vnn);
+    }
+}
+
+__device__ void build_F_Q(const double* x, const ParDev& par, double* Fm /*13x13 row-major*/, double* Q /*13x13*/, double* xv_new /*13*/) {
+    const double dt = 1.0;
+    for (int i = 0; i < 169; i++) {
+        Fm[i] = 0.0;
+        Q[i] = 0.0;
+    }
+    for (int i = 0; i < 13; i++) Fm[i * 13 + i] = 1.0;
+    double wdt[3] = {x[10] * dt, x[11] * dt, x[12] * dt}, qwt[4];
+    v2q_dev(wdt, qwt);
+    // qprod (src/ExtendKF.cpp:416-427)
+    const double* q = x + 3;
+    const double cr0 = q[2] * qwt[3] - q[3] * qwt[2], cr1 = q[3] * qwt[1] - q[1] * qwt[3], cr2 = q[1] * qwt[2] - q[2] * qwt[1];
+    for (int i = 0; i < 3; i++) xv_new[i] = x[i] + x[7 + i] * dt;
+    xv_new[3] = q[0] * qwt[0] - (q[1] * qwt[1] + q[2] * qwt[2] + q[3] * qwt[3]);
+    xv_new[4] = (q[0] * qwt[1] + qwt[0] * q[1]) + cr0;
+    xv_new[5] = (q[0] * qwt[2] + qwt[0] * q[2]) + cr1;
+    xv_new[6] = (q[0] * qwt[3] + qwt[0] * q[3]) + cr2;
+    for (int i = 7; i < 13; i++) xv_new[i] = x[i];
+    // dfv_by_dxv (src/ExtendKF.cpp:444-481)
+    const double qd[16] = {qwt[0], -qwt[1], -qwt[2], -qwt[3], qwt[1], qwt[0], qwt[3], -qwt[2],
+                           qwt[2], -qwt[3], qwt[0], qwt[1], qwt[3], qwt[2], -qwt[1], qwt[0]};
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++) Fm[(3 + i) * 13 + 3 + j] = qd[4 * i + j];
+    for (int i = 0; i < 3; i++) Fm[i * 13 + 7 + i] = dt;
+    // dq3_by_dq1(qOld) * dqomegadt_by_domega(omegaOld, dt)   (src/ExtendKF.cpp:482-529)
+    const double a[16] = {q[0], -q[1], -q[2], -q[3], q[1], q[0], -q[3], q[2], q[2], q[3], q[0], -q[1], q[3], -q[2], q[1], q[0]};
+    const double* w = x + 10;
+    const double om = sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+    double b[12];
+    const double sh = sin(om * dt / 2.0), ch = cos(om * dt / 2.0);
+    for (int j = 0; j < 3; j++) b[j] = (-dt / 2.0) * (w[j] / om) * sh;
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            if (i == j)
+                b[(i + 1) * 3 + j] = (dt / 2.0) * w[i] * w[i] / (om * om) * ch + (1.0 / om) * (1.0 - w[i] * w[i] / (om * om)) * sh;
+            else
+                b[(i + 1) * 3 + j] = (w[i] * w[j] / (om * om)) * ((dt / 2.0) * ch - (1.0 / om) * sh);
+        }
+    double ab[12];
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 3; j++) {
+            double s = 0;
+            for (int k = 0; k < 4; k++) s += a[4 * i + k] * b[3 * k + j];
+            ab[3 * i + j] = s;
+            Fm[(3 + i) * 13 + 10 + j] = s;
+        }
+    // Q = G Pn G^T with G(7:10,0:3)=I, G(10:13,3:6)=I, G(0:3,0:3)=I*dt, G(3:7,3:6)=ab  (src/ExtendKF.cpp:347-376)
+    double G[13 * 6];
+    for (int i = 0; i < 78; i++) G[i] = 0.0;
+    for (int i = 0; i < 3; i++) {
+        G[(7 + i) * 6 + i] = 1.0;
+        G[(10 + i) * 6 + 3 + i] = 1.0;
+        G[i * 6 + i] = dt;
+    }
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 3; j++) G[(3 + i) * 6 + 3 + j] = ab[3 * i + j];
+    for (int i = 0; i < 13; i++)
+        for (int j = 0; j < 13; j++) {
+            double s = 0;
+            for (int k = 0; k < 6; k++) s += (G[i * 6 + k] * (k < 3 ? par.la : par.aa)) * G[j * 6 + k];
+            Q[i * 13 + j] = s;
+        }
+}
+
+__global__ void __launch_bounds__(128) k_ekf_prediction(DevFilter* Fs, ParDev par) {
+    DevFilter& F = Fs[blockIdx.y];
+    __shared__ double sF[169], sQ[169], sX[13], sP[169], sT[169];
+    const int n = F.n;
+    if (blockIdx.x * blockDim.x >= (unsigned)n && blockIdx.x != 0) return;
+    if (threadIdx.x == 0) build_F_Q(F.x_kk, par, sF, sQ, sX);
+    __syncthreads();
+    const int ld = F.ldp;
+    if (blockIdx.x == 0) {
+        // camera block: F Pcc F^T + Q  (left to right)
+        for (int e = threadIdx.x; e < 169; e += blockDim.x) sP[e] = F.P[(e / 13) + (size_t)(e % 13) * ld];
+        __syncthreads();
+        for (int e = threadIdx.x; e < 169; e += blockDim.x) {
+            const int i = e / 13, j = e % 13;
+            double s = 0;
+            for (int k = 0; k < 13; k++) s += sF[i * 13 + k] * sP[k * 13 + j];
+            sT[e] = s;
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < 169; e += blockDim.x) {
+            const int i = e / 13, j = e % 13;
+            double s = 0;
+            for (int k = 0; k < 13; k++) s += sT[i * 13 + k] * sF[j * 13 + k];
+            F.P[i + (size_t)j * ld] = s + sQ[e];
+        }
+        if (threadIdx.x < 13) F.x_km1[threadIdx.x] = sX[threadIdx.x];
+    }
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= 13 && j < n) {
+        F.x_km1[j] = F.x_kk[j];
+        double v[13], o[13];
+#pragma unroll
+        for (int c = 0; c < 13; c++) v[c] = F.P[j + (size_t)c * ld];  // row j (== column j by symmetry), coalesced
+#pragma unroll
+        for (int i = 0; i < 13; i++) {
+            double s = 0;
+#pragma unroll
+            for (int k = 0; k < 13; k++) s += sF[i * 13 + k] * v[k];
+            o[i] = s;
+        }
+#pragma unroll
+        for (int c = 0; c < 13; c++) {
+            F.P[j + (size_t)c * ld] = o[c];
+            F.P[c + (size_t)j * ld] = o[c];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// (a) measurement prediction h_i, sparse Jacobian H_i and S_i = H_i P H_i^T + R_i.  One thread per feature.
+//   mode 0 : Tracking::search_IC_matches first half (src/Tracking.cpp:35-44) at x_k_km1
+//   mode 1 : Tracking::rescue_hi_inliers (src/Tracking.cpp:574-597) at x_k_k: refresh h/H where visible, then chi2 gate
+// References: ExtendKF::predict_camera_measurements / hi_cartesian / hu / distort_fm (src/ExtendKF.cpp:56-204),
+// Tracking::calculate_Hi_inverse_depth / calculate_Hi_cartesian (src/Tracking.cpp:71-163).
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mul_2x2_2x3(const double* a1, const double* a2, double* o) {
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) o[i * 3 + j] = a1[i * 2] * a2[j] + a1[i * 2 + 1] * a2[3 + j];
+}
+
+__global__ void __launch_bounds__(128) k_predict(DevFilter* Fs, CamDev cam, ParDev par, int mode) {
+    DevFilter& F = Fs[blockIdx.y];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ double sPcc[49];
+    const int ld = F.ldp;
+    if (threadIdx.x < 49) sPcc[threadIdx.x] = F.P[(threadIdx.x / 7) + (size_t)(threadIdx.x % 7) * ld];
+    __syncthreads();
+    if (i >= F.N) return;
+    const double* x = mode == 0 ? F.x_km1 : F.x_kk;
+    const int off = F.foff[i];
+    const int type = F.ftype[i];
+    const int fs = type == 0 ? 6 : 3;
+    double t[3] = {x[0], x[1], x[2]};
+    double q[4] = {x[3], x[4], x[5], x[6]};
+    double R[9];
+    q2r_dev(q, R);
+    double Rrw[9];
+    inv3_dev(R, Rrw);
+    double y[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) y[k] = (k < fs) ? x[off + k] : 0.0;
+    double d[3], rho = 1.0, mi[3] = {0, 0, 0}, sth = 0, cth = 0, sph = 0, cph = 0;
+    if (type == 0) {
+        sincos(y[3], &sth, &cth);
+        sincos(y[4], &sph, &cph);
+        rho = y[5];
+        mi[0] = cph * sth;
+        mi[1] = -sph;
+        mi[2] = cph * cth;
+#pragma unroll
+        for (int k = 0; k < 3; k++) d[k] = (y[k] - t[k]) * rho + mi[k];
+    } else {
+#pragma unroll
+        for (int k = 0; k < 3; k++) d[k] = y[k] - t[k];
+    }
+    // predict_camera_measurements: hrl = R^T d (inverse depth, :75) / R^-1 d (cartesian, :83)
+    double hrl[3];
+    if (type == 0) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) hrl[k] = R[k] * d[0] + R[3 + k] * d[1] + R[6 + k] * d[2];
+    } else {
+#pragma unroll
+        for (int k = 0; k < 3; k++) hrl[k] = Rrw[3 * k] * d[0] + Rrw[3 * k + 1] * d[1] + Rrw[3 * k + 2] * d[2];
+    }
+    bool vis = true;
+    {
+        const double ax = atan2(hrl[0], hrl[2]) * 180 / M_PI, ay = atan2(hrl[1], hrl[2]) * 180 / M_PI;
+        if (ax < -60 || ax > 60 || ay < -60 || ay > 60) vis = false;
+    }
+    double hd[2] = {0, 0};
+    if (vis) {
+        const double uu = cam.Cx + (hrl[0] / hrl[2]) * cam.f * (1.0 / cam.dx);
+        const double vu = cam.Cy + (hrl[1] / hrl[2]) * cam.f * (1.0 / cam.dy);
+        distort_dev(cam, uu, vu, hd[0], hd[1]);
+        vis = (hd[0] > 0) && (hd[0] < cam.nCols) && (hd[1] > 0) && (hd[1] < cam.nRows);
+    }
+    double Hc[14], Hf[12];
+    if (vis) {
+        // Jacobian at zi = h
+        double Ju[4];
+        jacob_undistort_dev(cam, hd[0], hd[1], Ju);
+        const double idet = 1.0 / (Ju[0] * Ju[3] - Ju[2] * Ju[1]);
+        const double a1[4] = {Ju[3] * idet, -Ju[1] * idet, -Ju[2] * idet, Ju[0] * idet};
+        double hc[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) hc[k] = Rrw[3 * k] * d[0] + Rrw[3 * k + 1] * d[1] + Rrw[3 * k + 2] * d[2];
+        const double fku = cam.f * (1.0 / cam.dx), fkv = cam.f * (1.0 / cam.dy);
+        const double a2[6] = {fku / hc[2], 0, -hc[0] * fku / (hc[2] * hc[2]), 0, fkv / hc[2], -hc[1] * fkv / (hc[2] * hc[2])};
+        double A[6];
+        mul_2x2_2x3(a1, a2, A);
+        // d h / d r = A * (-Rrw) [* rho]
+#pragma unroll
+        for (int a = 0; a < 2; a++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                double s = A[a * 3] * (-Rrw[c]) + A[a * 3 + 1] * (-Rrw[3 + c]) + A[a * 3 + 2] * (-Rrw[6 + c]);
+                Hc[a * 7 + c] = (type == 0) ? s * rho : s;
+            }
+        // d h / d q = A * dRq_times_a_by_dq(qconj, d) * diag(1,-1,-1,-1)
+        const double qb[4] = {q[0], -q[1], -q[2], -q[3]};
+        double dR[12];
+        dRq_times_a_by_dq_dev(qb, d, dR);
+#pragma unroll
+        for (int a = 0; a < 2; a++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const double sg = (c == 0) ? 1.0 : -1.0;
+                Hc[a * 7 + 3 + c] = A[a * 3] * (dR[c] * sg) + A[a * 3 + 1] * (dR[4 + c] * sg) + A[a * 3 + 2] * (dR[8 + c] * sg);
+            }
+        // d h / d y
+        double c0[18];  // 3 x 6 row-major
+        if (type == 0) {
+            const double c2[3] = {cph * cth, 0.0, -cph * sth};
+            const double c3[3] = {-sph * sth, -cph, -sph * cth};
+            const double dr[3] = {y[0] - t[0], y[1] - t[1], y[2] - t[2]};
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+                c0[r * 6 + 0] = rho * Rrw[3 * r];
+                c0[r * 6 + 1] = rho * Rrw[3 * r + 1];
+                c0[r * 6 + 2] = rho * Rrw[3 * r + 2];
+                c0[r * 6 + 3] = Rrw[3 * r] * c2[0] + Rrw[3 * r + 1] * c2[1] + Rrw[3 * r + 2] * c2[2];
+                c0[r * 6 + 4] = Rrw[3 * r] * c3[0] + Rrw[3 * r + 1] * c3[1] + Rrw[3 * r + 2] * c3[2];
+                c0[r * 6 + 5] = Rrw[3 * r] * dr[0] + Rrw[3 * r + 1] * dr[1] + Rrw[3 * r + 2] * dr[2];
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+                c0[r * 6 + 0] = Rrw[3 * r];
+                c0[r * 6 + 1] = Rrw[3 * r + 1];
+                c0[r * 6 + 2] = Rrw[3 * r + 2];
+                c0[r * 6 + 3] = c0[r * 6 + 4] = c0[r * 6 + 5] = 0.0;
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < 2; a++)
+#pragma unroll
+            for (int c = 0; c < 6; c++) Hf[a * 6 + c] = A[a * 3] * c0[c] + A[a * 3 + 1] * c0[6 + c] + A[a * 3 + 2] * c0[12 + c];
+        F.has_h[i] = 1;
+        F.h[2 * i] = hd[0];
+        F.h[2 * i + 1] = hd[1];
+#pragma unroll
+        for (int e = 0; e < 14; e++) F.Hc[14 * i + e] = Hc[e];
+#pragma unroll
+        for (int e = 0; e < 12; e++) F.Hf[12 * i + e] = Hf[e];
+    }
+    bool need_S;
+    if (mode == 0) {
+        need_S = vis;
+    } else {
+        need_S = F.ic[i] && !F.li[i];
+        if (need_S && !vis) {  // stale linearisation from x_k_km1 stays in force (src/ExtendKF.cpp:77-78)
+#pragma unroll
+            for (int e = 0; e < 14; e++) Hc[e] = F.Hc[14 * i + e];
+#pragma unroll
+            for (int e = 0; e < 12; e++) Hf[e] = F.Hf[12 * i + e];
+            hd[0] = F.h[2 * i];
+            hd[1] = F.h[2 * i + 1];
+        }
+    }
+    if (!need_S) return;
+    // S = H P H^T over the 7 + fs structurally non-zero columns; T = H * P first (left to right)
+    const double* P = F.P;
+    double T[2][13];
+#pragma unroll
+    for (int j = 0; j < 7; j++) {
+        double s0 = 0, s1 = 0;
+#pragma unroll
+        for (int k = 0; k < 7; k++) {
+            const double p = sPcc[k * 7 + j];
+            s0 += Hc[k] * p;
+            s1 += Hc[7 + k] * p;
+        }
+        for (int k = 0; k < fs; k++) {
+            const double p = P[(off + k) + (size_t)j * ld];
+            s0 += Hf[k] * p;
+            s1 += Hf[6 + k] * p;
+        }
+        T[0][j] = s0;
+        T[1][j] = s1;
+    }
+    for (int j = 0; j < fs; j++) {
+        double s0 = 0, s1 = 0;
+        const double* pc = P + (size_t)(off + j) * ld;
+#pragma unroll
+        for (int k = 0; k < 7; k++) {
+            const double p = pc[k];
+            s0 += Hc[k] * p;
+            s1 += Hc[7 + k] * p;
+        }
+        for (int k = 0; k < fs; k++) {
+            const double p = pc[off + k];
+            s0 += Hf[k] * p;
+            s1 += Hf[6 + k] * p;
+        }
+        T[0][7 + j] = s0;
+        T[1][7 + j] = s1;
+    }
+    double S[4];
+#pragma unroll
+    for (int a = 0; a < 2; a++)
+#pragma unroll
+        for (int b = 0; b < 2; b++) {
+            double s = 0;
+#pragma unroll
+            for (int j = 0; j < 7; j++) s += T[a][j] * Hc[b * 7 + j];
+            for (int j = 0; j < fs; j++) s += T[a][7 + j] * Hf[b * 6 + j];
+            S[a * 2 + b] = s;
+        }
+    if (mode == 0) {
+        S[0] += 1.0;  // R_i = I_2 (src/Map.cpp:310), not scaled by std_z (Q5)
+        S[3] += 1.0;
+#pragma unroll
+        for (int e = 0; e < 4; e++) F.S[4 * i + e] = S[e];
+    } else {
+        if (!(par.quirks & RSLAM_Q6_RESCUE_WITHOUT_R)) {
+            S[0] += 1.0;
+            S[3] += 1.0;
+        }
+        const double nu0 = F.z[2 * i] - hd[0], nu1 = F.z[2 * i + 1] - hd[1];
+        const double idet = 1.0 / (S[0] * S[3] - S[1] * S[2]);
+        const double i00 = S[3] * idet, i01 = -S[1] * idet, i10 = -S[2] * idet, i11 = S[0] * idet;
+        const double t0 = nu0 * i00 + nu1 * i10, t1 = nu0 * i01 + nu1 * i11;
+        const double chi = t0 * nu0 + t1 * nu1;
+        F.hi[i] = (chi < par.chi2) ? 1 : 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// (b) active search: Tracking::matching (src/Tracking.cpp:279-351) + Converter::corrcoef_opencv (src/Converter.cpp:188-209).
+// One CTA per feature.  The search window and the predicted 13x13 patch are staged in shared memory; each thread scores
+// candidates with one-pass sums (sum b, sum b^2 exact in integers; sum a*b in fp64); block arg-max keeps the FIRST maximum in
+// the reference's (x outer, y inner) visiting order; a NaN score on the first visited candidate is sticky (Eigen maxCoeff).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kMaxHalfSearch = 20;                           // ceil(2*sqrt(S_ii)) with S_ii < 100
+constexpr int kWinMax = 2 * kMaxHalfSearch + 1 + 2 * kHalfPatch;  // 53
+
+__global__ void __launch_bounds__(128) k_search(DevFilter* Fs, CamDev cam, ParDev par) {
+    DevFilter& F = Fs[blockIdx.y];
+    const int i = blockIdx.x;
+    if (i >= F.N) return;
+    if (!F.has_h[i] || F.image == nullptr) return;
+    __shared__ unsigned char win[kWinMax * kWinMax + 8];
+    __shared__ double pa[kPatchPix];  // predicted patch minus its mean
+    __shared__ double red_c[4], red_firstc[4];
+    __shared__ int red_i[4], red_first[4];
+    __shared__ double s_stats[2];
+    const double h0 = F.h[2 * i], h1 = F.h[2 * i + 1];
+    const double S00 = F.S[4 * i], S01 = F.S[4 * i + 1], S10 = F.S[4 * i + 2], S11 = F.S[4 * i + 3];
+    // largest eigenvalue of the symmetric 2x2 (lower triangle, as SelfAdjointEigenSolver)
+    const double lmax = 0.5 * (S00 + S11) + sqrt(0.25 * (S00 - S11) * (S00 - S11) + S10 * S10);
+    if (!(lmax < par.max_eig)) return;
+    // predicted patch is zero when h is within half a patch of the border (src/Tracking.cpp:174-175,275) -> NaN scores -> no match
+    if (!((h0 > kHalfPatch) && (h0 < (cam.nCols - kHalfPatch)) && (h1 > kHalfPatch) && (h1 < (cam.nRows - kHalfPatch)))) return;
+    const int hsx = (int)ceil(2 * sqrt(S00)), hsy = (int)ceil(2 * sqrt(S11));
+    if (hsx > kMaxHalfSearch || hsy > kMaxHalfSearch) return;  // cannot happen while lmax < 100
+    const int cx = (int)round(h0), cy = (int)round(h1);
+    const int x_lo = cx - hsx, y_lo = cy - hsy;
+    const int ww = 2 * hsx + 1 + 2 * kHalfPatch, wh = 2 * hsy + 1 + 2 * kHalfPatch;
+    const int wx0 = x_lo - kHalfPatch, wy0 = y_lo - kHalfPatch;
+    for (int e = threadIdx.x; e < ww * wh; e += blockDim.x) {
+        const int wy = e / ww, wx = e % ww;
+        const int gx = wx0 + wx, gy = wy0 + wy;
+        unsigned char v = 0;
+        if (gx >= 0 && gx < F.img_cols && gy >= 0 && gy < F.img_rows) v = F.image[(size_t)gy * F.img_stride + gx];
+        win[e] = v;
+    }
+    for (int e = threadIdx.x; e < kPatchPix; e += blockDim.x) pa[e] = (double)F.patch[(size_t)i * kPatchPix + e];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double sa = 0;
+        for (int e = 0; e < kPatchPix; e++) sa += pa[e];
+        s_stats[0] = sa * (1.0 / kPatchPix);
+    }
+    __syncthreads();
+    const double mean_a = s_stats[0];
+    for (int e = threadIdx.x; e < kPatchPix; e += blockDim.x) pa[e] -= mean_a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double va = 0;
+        for (int e = 0; e < kPatchPix; e++) va += pa[e] * pa[e];
+        s_stats[1] = va;  // sum (a - mean)^2, exactly 0 for a constant (e.g. zeroed) patch
+    }
+    __syncthreads();
+    const double var_a = s_stats[1];
+    const double idet = 1.0 / (S00 * S11 - S01 * S10);
+    const double i00 = S11 * idet, i01 = -S01 * idet, i10 = -S10 * idet, i11 = S00 * idet;
+    const int ncx = 2 * hsx + 1, ncy = 2 * hsy + 1;
+    double best_c = -INFINITY;   // best finite score seen by this thread
+    int best_idx = 0x7fffffff;   // its visiting-order index jx*ncy + iy
+    int first_idx = 0x7fffffff;  // first accepted candidate seen by this thread
+    double first_c = 0.0;
+    for (int cand = threadIdx.x; cand < ncx * ncy; cand += blockDim.x) {
+        const int jx = cand / ncy, iy = cand % ncy;  // reference visiting order: x outer, y inner
+        const int j = x_lo + jx, ii = y_lo + iy;
+        const double nu0 = j - h0, nu1 = ii - h1;
+        const double t0 = nu0 * i00 + nu1 * i10, t1 = nu0 * i01 + nu1 * i11;
+        if (!((t0 * nu0 + t1 * nu1) < par.chi2)) continue;
+        if (!((j > kHalfPatch) && (j < (cam.nCols - kHalfPatch)) && (ii > kHalfPatch) && (ii < (cam.nRows - kHalfPatch)))) continue;
+        int sb = 0, sbb = 0;
+        double sab = 0;
+        const unsigned char* wp = &win[iy * ww + jx];
+#pragma unroll 1
+        for (int r = 0; r < kPatch; r++) {
+#pragma unroll
+            for (int c = 0; c < kPatch; c++) {
+                const int b = wp[r * ww + c];
+                sb += b;
+                sbb += b * b;
+                sab = fma(pa[r * kPatch + c], (double)b, sab);  // sum (a - mean_a) * b == sum (a - mean_a)(b - mean_b)
+            }
+        }
+        const double var_b = (double)((long long)kPatchPix * sbb - (long long)sb * sb) / kPatchPix;
+        const double corr = sab / sqrt(var_a * var_b);
+        if (cand < first_idx) {
+            first_idx = cand;
+            first_c = corr;
+        }
+        if (corr == corr && (corr > best_c)) {  // NaN never wins; strict '>' keeps the earlier index (cand increases per thread)
+            best_c = corr;
+            best_idx = cand;
+        }
+    }
+    // block reduce: maximum finite corr, ties -> smaller visiting index ; and the globally first accepted candidate
+    const unsigned fm = 0xffffffffu;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double oc = __shfl_xor_sync(fm, best_c, o);
+        const int oi = __shfl_xor_sync(fm, best_idx, o);
+        if (oc > best_c || (oc == best_c && oi < best_idx)) {
+            best_c = oc;
+            best_idx = oi;
+        }
+        const int of = __shfl_xor_sync(fm, first_idx, o);
+        const double ofc = __shfl_xor_sync(fm, first_c, o);
+        if (of < first_idx) {
+            first_idx = of;
+            first_c = ofc;
+        }
+    }
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) {
+        red_c[w] = best_c;
+        red_i[w] = best_idx;
+        red_first[w] = first_idx;
+        red_firstc[w] = first_c;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < 4; k++) {
+            if (red_c[k] > best_c || (red_c[k] == best_c && red_i[k] < best_idx)) {
+                best_c = red_c[k];
+                best_idx = red_i[k];
+            }
+            if (red_first[k] < first_idx) {
+                first_idx = red_first[k];
+                first_c = red_firstc[k];
+            }
+        }
+        if (first_idx == 0x7fffffff) return;  // no candidate pixel (Q10: reference divides by zero here)
+        if (first_c != first_c) return;        // NaN in slot 0 is sticky in Eigen's maxCoeff -> unmatched (Q10)
+        if (best_c > par.corr_thr) {
+            F.ic[i] = 1;
+            const int jx = best_idx / ncy, iy = best_idx % ncy;
+            F.z[2 * i] = (double)(x_lo + jx);
+            F.z[2 * i + 1] = (double)(y_lo + iy);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// (c) 1-point RANSAC (src/Tracking.cpp:352-539)
+// ---------------------------------------------------------------------------------------------------------------
+// c.1 ordered compaction of the individually-compatible list and the matched inverse-depth list (z_id columns, :361-397)
+__global__ void __launch_bounds__(256) k_ransac_compact(DevFilter* Fs) {
+    DevFilter& F = Fs[blockIdx.y];
+    __shared__ int s_scan[2][256];
+    __shared__ int s_base[3];
+    if (threadIdx.x == 0) s_base[0] = s_base[1] = s_base[2] = 0;
+    __syncthreads();
+    for (int base = 0; base < F.N; base += 256) {
+        const int i = base + threadIdx.x;
+        int a = 0, b = 0, c = 0;
+        if (i < F.N) {
+            a = F.ic[i] ? 1 : 0;
+            b = (a && F.ftype[i] == 0) ? 1 : 0;
+            c = (a && F.ftype[i] != 0) ? 1 : 0;
+        }
+        s_scan[0][threadIdx.x] = a;
+        s_scan[1][threadIdx.x] = b;
+        __syncthreads();
+        // Hillis-Steele inclusive scan over 256 entries (two arrays at once)
+        for (int o = 1; o < 256; o <<= 1) {
+            int va = 0, vb = 0;
+            if (threadIdx.x >= o) {
+                va = s_scan[0][threadIdx.x - o];
+                vb = s_scan[1][threadIdx.x - o];
+            }
+            __syncthreads();
+            s_scan[0][threadIdx.x] += va;
+            s_scan[1][threadIdx.x] += vb;
+            __syncthreads();
+        }
+        const int pa = s_base[0] + s_scan[0][threadIdx.x] - a;
+        const int pb = s_base[1] + s_scan[1][threadIdx.x] - b;
+        if (i < F.N) {
+            if (a) F.ic_list[pa] = i;
+            if (b) {
+                F.id_list[pb] = i;
+                F.id_pos[i] = pb;
+            } else {
+                F.id_pos[i] = -1;
+            }
+        }
+        const int csum = __syncthreads_count(c);
+        __syncthreads();
+        if (threadIdx.x == 255) {
+            s_base[0] += s_scan[0][255];
+            s_base[1] += s_scan[1][255];
+            s_base[2] += csum;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        F.ctl[CTL_NIC] = s_base[0];
+        F.ctl[CTL_MID] = s_base[1];
+        F.ctl[CTL_NCART] = s_base[2];
+    }
+}
+
+// c.2 one thread per distinct 1-point hypothesis t (match p = ic_list[t]): partial EKF state update restricted to the camera
+//     (src/Tracking.cpp:419-422):  g = S_p^-1 (z_p - h_p);  a = Hc_p^T g;  b = Hf_p^T g;  x_i[0..6] = x[0..6] + P[0..6,nz] [a;b]
+__global__ void __launch_bounds__(128) k_ransac_hyp(DevFilter* Fs) {
+    DevFilter& F = Fs[blockIdx.y];
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= F.ctl[CTL_NIC]) return;
+    const int p = F.ic_list[t];
+    const int off = F.foff[p];
+    const int fs = F.ftype[p] == 0 ? 6 : 3;
+    const double S0 = F.S[4 * p], S1 = F.S[4 * p + 1], S2 = F.S[4 * p + 2], S3 = F.S[4 * p + 3];
+    const double idet = 1.0 / (S0 * S3 - S1 * S2);
+    const double nu0 = F.z[2 * p] - F.h[2 * p], nu1 = F.z[2 * p + 1] - F.h[2 * p + 1];
+    const double g0 = (S3 * nu0 - S1 * nu1) * idet, g1 = (-S2 * nu0 + S0 * nu1) * idet;
+    double ab[13];
+#pragma unroll
+    for (int c = 0; c < 7; c++) ab[c] = F.Hc[14 * p + c] * g0 + F.Hc[14 * p + 7 + c] * g1;
+#pragma unroll
+    for (int c = 0; c < 6; c++) ab[7 + c] = (c < fs) ? (F.Hf[12 * p + c] * g0 + F.Hf[12 * p + 6 + c] * g1) : 0.0;
+#pragma unroll
+    for (int c = 0; c < 13; c++) F.hyp_ab[(size_t)t * 13 + c] = ab[c];
+    const int ld = F.ldp;
+    for (int r = 0; r < 7; r++) {
+        double s = 0;
+#pragma unroll
+        for (int c = 0; c < 7; c++) s += F.P[r + (size_t)c * ld] * ab[c];
+        for (int c = 0; c < fs; c++) s += F.P[r + (size_t)(off + c) * ld] * ab[7 + c];
+        F.hyp_xcam[(size_t)t * 7 + r] = F.x_km1[r] + s;
+    }
+}
+
+// c.3 support scoring (compute_hypothesis_support_fast, inlined at src/Tracking.cpp:424-503): one CTA per distinct hypothesis.
+//     For every matched inverse-depth feature j the hypothesised feature rows are formed on the fly,
+//         x_i[y_j] = x[y_j] + P[y_j, 0..6] a + P[y_j, y_p] b,
+//     so K (n x 2) is never materialised; the only pair-unique HBM traffic is the 6x6 block P[y_j, y_p] (288 B).
+//     Quirk Q1 (reference): the angles of match jj are read from the stacked POSITION vector, entries (2jj, 2jj+1); the
+//     positions/rho of all matches are therefore staged in shared memory first (4*m doubles).
+__global__ void __launch_bounds__(256) k_ransac_support(DevFilter* Fs, CamDev cam, ParDev par, const int* t_indirect, int t_begin,
+                                                        const int* used, unsigned long long* pair_counter) {
+    DevFilter& F = Fs[blockIdx.y];
+    extern __shared__ double smem[];
+    int t = t_begin + blockIdx.x;
+    if (t_indirect) t = t_indirect[t];
+    if (t < 0 || t >= F.ctl[CTL_NIC]) return;
+    if (used && !used[t]) return;
+    const int m = F.ctl[CTL_MID];
+    if (pair_counter && threadIdx.x == 0) atomicAdd(pair_counter, (unsigned long long)m);
+    const bool q1 = (par.quirks & RSLAM_Q1_ANGLES_FROM_POSITIONS) != 0;
+    double* s_ri = smem;           // 3m (only with Q1)
+    double* s_rho = smem + 3 * m;  // m
+    __shared__ double s_ab[13], s_xc[7], s_R[9];
+    __shared__ int s_cnt[8];
+    const int p = F.ic_list[t];
+    const int offp = F.foff[p];
+    const int fsp = F.ftype[p] == 0 ? 6 : 3;
+    if (threadIdx.x < 13) s_ab[threadIdx.x] = F.hyp_ab[(size_t)t * 13 + threadIdx.x];
+    if (threadIdx.x < 7) s_xc[threadIdx.x] = F.hyp_xcam[(size_t)t * 7 + threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0) q2r_dev(&s_xc[3], s_R);
+    const int ld = F.ldp;
+    const double* P = F.P;
+    const double* x = F.x_km1;
+    const double* pcol = P + (size_t)offp * ld;
+    if (q1) {
+        for (int jj = threadIdx.x; jj < m; jj += blockDim.x) {
+            const int oj = F.foff[F.id_list[jj]];
+            const int rows[4] = {oj, oj + 1, oj + 2, oj + 5};
+            double v[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const int r = rows[e];
+                double s = 0;
+#pragma unroll
+                for (int c = 0; c < 7; c++) s += P[r + (size_t)c * ld] * s_ab[c];
+                for (int c = 0; c < fsp; c++) s += pcol[r + (size_t)c * ld] * s_ab[7 + c];
+                v[e] = x[r] + s;
+            }
+            s_ri[3 * jj] = v[0];
+            s_ri[3 * jj + 1] = v[1];
+            s_ri[3 * jj + 2] = v[2];
+            s_rho[jj] = v[3];
+        }
+    }
+    __syncthreads();
+    int cnt = 0;
+    const int mpad = (m + 31) & ~31;
+    for (int jj = threadIdx.x; jj < mpad; jj += blockDim.x) {
+        bool inl = false;
+        if (jj < m) {
+            const int fj = F.id_list[jj];
+            double r3[3], a0, a1, rho;
+            if (q1) {
+                r3[0] = s_ri[3 * jj];
+                r3[1] = s_ri[3 * jj + 1];
+                r3[2] = s_ri[3 * jj + 2];
+                rho = s_rho[jj];
+                a0 = s_ri[2 * jj];
+                a1 = s_ri[2 * jj + 1];
+            } else {
+                const int oj = F.foff[fj];
+                double v[6];
+#pragma unroll
+                for (int e = 0; e < 6; e++) {
+                    const int r = oj + e;
+                    double s = 0;
+#pragma unroll
+                    for (int c = 0; c < 7; c++) s += P[r + (size_t)c * ld] * s_ab[c];
+                    for (int c = 0; c < fsp; c++) s += pcol[r + (size_t)c * ld] * s_ab[7 + c];
+                    v[e] = x[r] + s;
+                }
+                r3[0] = v[0];
+                r3[1] = v[1];
+                r3[2] = v[2];
+                a0 = v[3];
+                a1 = v[4];
+                rho = v[5];
+            }
+            double s0, c0, s1, c1;
+            sincos(a0, &s0, &c0);
+            sincos(a1, &s1, &c1);
+            const double mi[3] = {c1 * s0, -s1, c1 * c0};
+            double v3[3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) v3[k] = (r3[k] - s_xc[k]) * rho + mi[k];
+            double hc[3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) hc[k] = s_R[k] * v3[0] + s_R[3 + k] * v3[1] + s_R[6 + k] * v3[2];  // R^T v
+            const double fku = cam.f * (1.0 / cam.dx);
+            const double u = fku * (hc[0] / hc[2]) + cam.Cx;
+            const double v = fku * (hc[1] / hc[2]) + cam.Cy;  // ku for both rows (src/Tracking.cpp:471)
+            double ud, vd;
+            distort_dev(cam, u, v, ud, vd);
+            const double n0 = F.z[2 * fj] - ud, n1 = F.z[2 * fj + 1] - vd;
+            const double res = sqrt(n0 * n0 + n1 * n1);
+            inl = res < par.std_z;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, inl);
+        if ((threadIdx.x & 31) == 0) F.masks[(size_t)t * F.mwords + (jj >> 5)] = bal;
+        cnt += inl ? 1 : 0;
+    }
+    cnt = warp_sum_int(cnt);
+    if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int s = 0;
+        for (int k = 0; k < (int)(blockDim.x >> 5); k++) s += s_cnt[k];
+        F.support[t] = s;
+    }
+}
+
+// c.4 replay of the reference's sequential, adaptive control flow (src/Tracking.cpp:403-415, 506-537) over the uniform draws,
+//     then write-back of the winner's low_innovation_inlier flags.  One CTA per filter.
+__global__ void __launch_bounds__(256) k_ransac_select(DevFilter* Fs, ParDev par) {
+    DevFilter& F = Fs[blockIdx.y];
+    __shared__ int s_sup[1024];
+    __shared__ int s_state[8];  // 0 done, 1 max, 2 n_hyp, 3 winner i, 4 winner t, 5 hyp_run, 6 status
+    const int nIC = F.ctl[CTL_NIC];
+    if (threadIdx.x == 0) {
+        s_state[0] = 0;
+        s_state[1] = 0;
+        s_state[2] = par.n_hyp0;
+        s_state[3] = -1;
+        s_state[4] = -1;
+        s_state[5] = 0;
+        s_state[6] = 0;
+        if (nIC == 0) {
+            s_state[0] = 1;
+            s_state[6] = 1;  // Q9
+        }
+    }
+    __syncthreads();
+    for (int base = 0; !s_state[0]; base += 1024) {
+        for (int e = threadIdx.x; e < 1024; e += blockDim.x) {
+            const int i = base + e;
+            int s = -1;
+            if (i < F.n_u01) {
+                const int pos = (int)floor(F.u01[i] * (double)nIC);
+                s = F.support[pos < nIC ? pos : nIC - 1];
+            }
+            s_sup[e] = s;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int mx = s_state[1], n_hyp = s_state[2], win = s_state[3], run = s_state[5], status = 0, done = 0;
+            for (int e = 0; e < 1024; e++) {
+                const int i = base + e;
+                if (!(i < n_hyp)) {
+                    done = 1;
+                    break;
+                }
+                const int s = s_sup[e];
+                if (s < 0) {
+                    done = 1;
+                    status = 3;  // uniform draws exhausted
+                    break;
+                }
+                run = i + 1;
+                if (s > mx) {
+                    mx = s;
+                    win = i;
+                    const double epsilon = 1 - ((double)s / (double)nIC);
+                    n_hyp = (int)ceil(log(1 - par.p_free) / log(1 - (1 - epsilon)));
+                    if (n_hyp == 0) {
+                        done = 1;
+                        break;
+                    }
+                }
+                if (i > n_hyp) {
+                    done = 1;
+                    break;
+                }
+            }
+            s_state[0] = done;
+            s_state[1] = mx;
+            s_state[2] = n_hyp;
+            s_state[3] = win;
+            s_state[5] = run;
+            if (status) s_state[6] = status;
+        }
+        __syncthreads();
+    }
+    const int win = s_state[3];
+    int wt = -1;
+    if (win >= 0) {
+        const int pos = (int)floor(F.u01[win] * (double)nIC);
+        wt = pos < nIC ? pos : nIC - 1;
+        const int m = F.ctl[CTL_MID];
+        for (int jj = threadIdx.x; jj < m; jj += blockDim.x) {
+            const unsigned wbits = F.masks[(size_t)wt * F.mwords + (jj >> 5)];
+            F.li[F.id_list[jj]] = (wbits >> (jj & 31)) & 1u;
+        }
+    }
+    if (threadIdx.x == 0) {
+        F.ctl[CTL_STATUS] = s_state[6];
+        F.ctl[CTL_HYPRUN] = s_state[5];
+        F.ctl[CTL_BEST] = s_state[1];
+        F.ctl[CTL_NHYP] = s_state[2];
+        F.ctl[CTL_WINNER] = win;
+        F.ctl[CTL_WINNER_T] = wt;
+    }
+}
+
+// sweep (config C4): reduce key = (support << 32) | (0xFFFFFFFF - hypothesis id) over hypotheses [h0, h1)
+__global__ void __launch_bounds__(256) k_sweep_reduce(DevFilter* Fs, const int* hyp_idx, int h0, int h1, unsigned long long* out_key) {
+    DevFilter& F = Fs[0];
+    unsigned long long best = 0ull;
+    const int nIC = F.ctl[CTL_NIC];
+    for (int i = h0 + blockIdx.x * blockDim.x + threadIdx.x; i < h1; i += gridDim.x * blockDim.x) {
+        const int t = hyp_idx[i];
+        if (t < 0 || t >= nIC) continue;
+        const unsigned long long key = ((unsigned long long)(unsigned)F.support[t] << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
+        best = key > best ? key : best;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long ob = __shfl_xor_sync(0xffffffffu, best, o);
+        best = ob > best ? ob : best;
+    }
+    if ((threadIdx.x & 31) == 0 && best) atomicMax(out_key, best);
+}
+
+// mark which distinct hypotheses are referenced by hyp_idx[h0, h1) (dedupe), then compact them
+__global__ void k_sweep_mark(DevFilter* Fs, const int* hyp_idx, int h0, int h1, int* used) {
+    DevFilter& F = Fs[0];
+    const int nIC = F.ctl[CTL_NIC];
+    for (int i = h0 + blockIdx.x * blockDim.x + threadIdx.x; i < h1; i += gridDim.x * blockDim.x) {
+        const int t = hyp_idx[i];
+        if (t >= 0 && t < nIC) used[t] = 1;
+    }
+}
+
+}  // namespace rslam

@@ -1,0 +1,704 @@
+// rslam_api.cu -- host side of the C ABI declared in include/rslam.h: handle lifecycle, state transfer and the launch
+// sequences of the per-frame path.  No CPU fallback: every entry point needs a CUDA device.
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels_track.cuh"
+#include "kernels_update.cuh"
+
+using namespace rslam;
+
+namespace {
+thread_local std::string g_err;
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CK(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t e__ = (call);                                                                             \
+        if (e__ != cudaSuccess) return fail(RSLAM_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+}  // namespace
+
+struct rslam_filter {
+    int device = 0, B = 1, Nmax = 0, nmax = 0, ldp = 0, ldw = 0, lds = 0, kmax = 0, mwords = 0;
+    rslam_camera cam{};
+    rslam_params par{};
+    CamDev camd{};
+    ParDev pard{};
+    cudaStream_t stream = nullptr;
+    long long launches = 0;
+    std::vector<DevFilter> hF;  // host mirror of the device descriptors
+    DevFilter* dF = nullptr;
+    std::vector<void*> allocs;
+    // shared buffers
+    unsigned char* d_images = nullptr;
+    size_t image_cap = 0;
+    double* d_u01 = nullptr;
+    size_t u01_cap = 0;
+    int* d_hyp_idx = nullptr;
+    size_t hyp_cap = 0;
+    int* d_used = nullptr;
+    unsigned long long* d_key = nullptr;  // [0] key, [1] pair counter
+    bool have_image = false;
+    bool upd_ws = false;
+    int hN = 0, hn = 0;  // max over filters of the uploaded N / n
+    bool descr_dirty = false;
+};
+
+namespace {
+
+template <typename T>
+int dev_alloc(rslam_filter* f, T** p, size_t count, bool zero = true) {
+    void* q = nullptr;
+    size_t bytes = count * sizeof(T);
+    if (bytes == 0) bytes = 16;
+    CK(cudaMalloc(&q, bytes));
+    if (zero) CK(cudaMemsetAsync(q, 0, bytes, f->stream));
+    f->allocs.push_back(q);
+    *p = (T*)q;
+    return 0;
+}
+
+int push_descr(rslam_filter* f) {
+    CK(cudaMemcpyAsync(f->dF, f->hF.data(), sizeof(DevFilter) * f->B, cudaMemcpyHostToDevice, f->stream));
+    // hF is pageable: the copy is staged before the call returns, so later host edits are safe
+    f->descr_dirty = false;
+    return 0;
+}
+
+int ensure_update_ws(rslam_filter* f) {
+    if (f->upd_ws) return 0;
+    const size_t wsz = (size_t)f->ldw * f->kmax, ssz = (size_t)f->lds * f->kmax;
+    double *W = nullptr, *S = nullptr;
+    int rc;
+    if ((rc = dev_alloc(f, &W, wsz * f->B))) return rc;
+    if ((rc = dev_alloc(f, &S, ssz * f->B))) return rc;
+    for (int b = 0; b < f->B; b++) {
+        f->hF[b].W = W + wsz * b;
+        f->hF[b].Sm = S + ssz * b;
+    }
+    f->upd_ws = true;
+    return push_descr(f);
+}
+
+bool is_device_ptr(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+__global__ void k_set_inputs(DevFilter* Fs, int B, const unsigned char* img, long long img_stride_per_filter, int rows, int cols, int stride,
+                             int set_img, const double* u01, int n_u01, int set_u01) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    if (set_img) {
+        Fs[b].image = img ? img + img_stride_per_filter * b : nullptr;
+        Fs[b].img_rows = rows;
+        Fs[b].img_cols = cols;
+        Fs[b].img_stride = stride;
+    }
+    if (set_u01) {
+        Fs[b].u01 = u01 + (size_t)n_u01 * b;
+        Fs[b].n_u01 = n_u01;
+    }
+}
+
+#define LAUNCH(f, kern, grid, block, smem, ...)                   \
+    do {                                                          \
+        kern<<<grid, block, smem, (f)->stream>>>(__VA_ARGS__);    \
+        (f)->launches++;                                          \
+    } while (0)
+
+int check_launch() {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(RSLAM_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+int run_update(rslam_filter* f, int which) {
+    int rc = ensure_update_ws(f);
+    if (rc) return rc;
+    const int B = f->B, N = f->hN, n = f->hn;
+    if (N == 0) return 0;
+    const int kmax = 2 * N;
+    const int nsteps = cdiv(kmax, kNB);
+    LAUNCH(f, k_upd_gather, dim3(1, B), 256, 0, f->dF, which);
+    LAUNCH(f, k_upd_W, dim3(cdiv(n, 256), cdiv(N, kWChunk), B), 256, 0, f->dF);
+    LAUNCH(f, k_upd_S, dim3(cdiv(N, 16), cdiv(N, 16), B), 256, 0, f->dF);
+    for (int s = 0; s < nsteps; s++) {
+        LAUNCH(f, k_chol_panel, dim3(nsteps - s, B), 128, 0, f->dF, s);
+        const int rem = kmax - kNB * (s + 1);
+        if (rem > 0) {
+            const int tm = cdiv(rem, GBM);
+            LAUNCH(f, k_gemm_dmma, dim3(tm * (tm + 1) / 2, 1, B), 256, kGemmSmemBytes, f->dF, (int)GEMM_CHOL_TRAIL, s);
+        }
+    }
+    for (int s = 0; s < nsteps; s++) {
+        LAUNCH(f, k_trsm_panel, dim3(cdiv(n + 1, 128), B), 128, 0, f->dF, s);
+        const int rem = kmax - kNB * (s + 1);
+        if (rem > 0) {
+            const int tm = cdiv(n + 1, GBM), tn = cdiv(rem, GBN);
+            LAUNCH(f, k_gemm_dmma, dim3(tm * tn, 1, B), 256, kGemmSmemBytes, f->dF, (int)GEMM_TRSM_TRAIL, s);
+        }
+    }
+    LAUNCH(f, k_upd_x, dim3(cdiv(n, 128), B), 128, 0, f->dF, which);
+    {
+        const int tm = cdiv(n, GBM);
+        LAUNCH(f, k_gemm_dmma, dim3(tm * (tm + 1) / 2, 1, B), 256, kGemmSmemBytes, f->dF, (int)GEMM_SYRK_P, 0);
+    }
+    LAUNCH(f, k_upd_jnorm, dim3(1, B), 256, 0, f->dF, f->pard);
+    return check_launch();
+}
+
+int run_ransac_core(rslam_filter* f, bool select) {
+    const int B = f->B, N = f->hN;
+    if (N == 0) return 0;
+    LAUNCH(f, k_ransac_compact, dim3(1, B), 256, 0, f->dF);
+    LAUNCH(f, k_ransac_hyp, dim3(cdiv(N, 128), B), 128, 0, f->dF);
+    if (select) {
+        const size_t smem = (f->pard.quirks & RSLAM_Q1_ANGLES_FROM_POSITIONS) ? (size_t)4 * N * sizeof(double) : 0;
+        LAUNCH(f, k_ransac_support, dim3(N, B), 256, smem, f->dF, f->camd, f->pard, (const int*)nullptr, 0, (const int*)nullptr,
+               (unsigned long long*)nullptr);
+        LAUNCH(f, k_ransac_select, dim3(1, B), 256, 0, f->dF, f->pard);
+    }
+    return check_launch();
+}
+
+}  // namespace
+
+extern "C" {
+
+void rslam_default_params(rslam_params* p) {
+    p->std_a = 0.007;
+    p->std_alpha = 0.007;
+    p->std_z = 1.0;
+    p->chi2_095_2 = 5.9915;
+    p->corr_threshold = 0.80;
+    p->p_spurious_free = 0.99;
+    p->n_hyp_initial = 1000;
+    p->max_ellipse_eig = 100.0;
+    p->quirks = RSLAM_Q_ALL;
+    p->dedupe_hypotheses = 1;
+}
+
+const char* rslam_last_error(void) { return g_err.c_str(); }
+const char* rslam_version(void) { return "rslam-b200 0.1 (sm_100a)"; }
+
+int rslam_create(const rslam_camera* cam, const rslam_params* par, int max_features, int batch, int device, rslam_filter** out) {
+    if (!cam || !out || max_features < 1 || batch < 1) return fail(RSLAM_ERR_INVALID, "rslam_create: bad arguments");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(RSLAM_ERR_CUDA, "rslam_create: no CUDA device (this library has no CPU fallback)");
+    }
+    if (device < 0 || device >= ndev) return fail(RSLAM_ERR_INVALID, "rslam_create: device %d out of range (%d devices)", device, ndev);
+    CK(cudaSetDevice(device));
+    rslam_filter* f = new rslam_filter();
+    f->device = device;
+    f->B = batch;
+    f->Nmax = max_features;
+    f->nmax = 13 + 6 * max_features;
+    f->ldp = round_up(f->nmax, 16);
+    f->ldw = round_up(f->nmax + 1, 16);
+    f->kmax = 2 * max_features;
+    f->lds = round_up(f->kmax, 16);
+    f->mwords = cdiv(max_features, 32);
+    f->cam = *cam;
+    if (par)
+        f->par = *par;
+    else
+        rslam_default_params(&f->par);
+    f->camd = CamDev{cam->k1, cam->k2, cam->Cx, cam->Cy, cam->f, cam->dx, cam->dy, cam->f * (1.0 / cam->dx), cam->f * (1.0 / cam->dy), cam->nRows, cam->nCols};
+    f->pard = ParDev{f->par.std_z, f->par.chi2_095_2, f->par.corr_threshold, f->par.p_spurious_free, f->par.max_ellipse_eig,
+                     (f->par.std_a * 1.0) * (f->par.std_a * 1.0), (f->par.std_alpha * 1.0) * (f->par.std_alpha * 1.0), f->par.n_hyp_initial, f->par.quirks};
+    CK(cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking));
+    const size_t smem_support = (size_t)4 * max_features * sizeof(double);
+    if ((f->pard.quirks & RSLAM_Q1_ANGLES_FROM_POSITIONS) && smem_support > 220 * 1024) {
+        delete f;
+        return fail(RSLAM_ERR_CAPACITY, "rslam_create: max_features %d exceeds the shared-memory staging limit of the Q1 support kernel (7040)", max_features);
+    }
+    CK(cudaFuncSetAttribute(k_gemm_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
+    if (smem_support > 48 * 1024) CK(cudaFuncSetAttribute(k_ransac_support, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_support));
+
+    const int B = batch, N = max_features, n = f->nmax;
+    f->hF.assign(B, DevFilter{});
+    int rc = 0;
+    double *P, *xkk, *xkm1, *h, *Hc, *Hf, *S, *z, *hyp_ab, *hyp_xcam, *Jn;
+    int *ftype, *foff, *tp, *tm, *ic_list, *id_list, *id_pos, *support, *ctl, *upd_list;
+    unsigned char *has_h, *ic, *li, *hi;
+    float* patch;
+    unsigned* masks;
+    const size_t psz = (size_t)f->ldp * n;
+#define A(ptr, cnt)                                       \
+    if ((rc = dev_alloc(f, &ptr, (size_t)(cnt)*B))) {    \
+        rslam_destroy(f);                                 \
+        return rc;                                        \
+    }
+    A(P, psz) A(xkk, n) A(xkm1, n) A(h, 2 * N) A(Hc, 14 * N) A(Hf, 12 * N) A(S, 4 * N) A(z, 2 * N) A(hyp_ab, 13 * N) A(hyp_xcam, 7 * N) A(Jn, 32)
+    A(ftype, N) A(foff, N) A(tp, N) A(tm, N) A(ic_list, N) A(id_list, N) A(id_pos, N) A(support, N) A(ctl, CTL_SIZE) A(upd_list, N)
+    A(has_h, N) A(ic, N) A(li, N) A(hi, N) A(patch, (size_t)N * kPatchPix) A(masks, (size_t)N * f->mwords)
+#undef A
+    if ((rc = dev_alloc(f, &f->dF, (size_t)B))) {
+        rslam_destroy(f);
+        return rc;
+    }
+    if ((rc = dev_alloc(f, &f->d_used, (size_t)N)) || (rc = dev_alloc(f, &f->d_key, (size_t)2))) {
+        rslam_destroy(f);
+        return rc;
+    }
+    for (int b = 0; b < B; b++) {
+        DevFilter& D = f->hF[b];
+        D.n = 13;
+        D.N = 0;
+        D.ldp = f->ldp;
+        D.ldw = f->ldw;
+        D.lds = f->lds;
+        D.kmax = f->kmax;
+        D.mwords = f->mwords;
+        D.P = P + psz * b;
+        D.x_kk = xkk + (size_t)n * b;
+        D.x_km1 = xkm1 + (size_t)n * b;
+        D.ftype = ftype + (size_t)N * b;
+        D.foff = foff + (size_t)N * b;
+        D.h = h + (size_t)2 * N * b;
+        D.Hc = Hc + (size_t)14 * N * b;
+        D.Hf = Hf + (size_t)12 * N * b;
+        D.S = S + (size_t)4 * N * b;
+        D.z = z + (size_t)2 * N * b;
+        D.has_h = has_h + (size_t)N * b;
+        D.ic = ic + (size_t)N * b;
+        D.li = li + (size_t)N * b;
+        D.hi = hi + (size_t)N * b;
+        D.times_predicted = tp + (size_t)N * b;
+        D.times_measured = tm + (size_t)N * b;
+        D.patch = patch + (size_t)N * kPatchPix * b;
+        D.image = nullptr;
+        D.ic_list = ic_list + (size_t)N * b;
+        D.id_list = id_list + (size_t)N * b;
+        D.id_pos = id_pos + (size_t)N * b;
+        D.hyp_ab = hyp_ab + (size_t)13 * N * b;
+        D.hyp_xcam = hyp_xcam + (size_t)7 * N * b;
+        D.support = support + (size_t)N * b;
+        D.masks = masks + (size_t)N * f->mwords * b;
+        D.u01 = nullptr;
+        D.n_u01 = 0;
+        D.ctl = ctl + (size_t)CTL_SIZE * b;
+        D.upd_list = upd_list + (size_t)N * b;
+        D.W = nullptr;
+        D.Sm = nullptr;
+        D.Jn = Jn + (size_t)32 * b;
+    }
+    if ((rc = push_descr(f))) {
+        rslam_destroy(f);
+        return rc;
+    }
+    CK(cudaStreamSynchronize(f->stream));
+    *out = f;
+    return RSLAM_OK;
+}
+
+int rslam_destroy(rslam_filter* f) {
+    if (!f) return RSLAM_OK;
+    cudaSetDevice(f->device);
+    if (f->stream) cudaStreamSynchronize(f->stream);
+    for (void* p : f->allocs) cudaFree(p);
+    if (f->d_images) cudaFree(f->d_images);
+    if (f->d_u01) cudaFree(f->d_u01);
+    if (f->d_hyp_idx) cudaFree(f->d_hyp_idx);
+    if (f->stream) cudaStreamDestroy(f->stream);
+    delete f;
+    return RSLAM_OK;
+}
+
+int rslam_sync(rslam_filter* f) {
+    if (!f) return fail(RSLAM_ERR_INVALID, "null handle");
+    CK(cudaStreamSynchronize(f->stream));
+    return RSLAM_OK;
+}
+void* rslam_stream(rslam_filter* f) { return f ? (void*)f->stream : nullptr; }
+long long rslam_launch_count(rslam_filter* f) { return f ? f->launches : 0; }
+int rslam_num_features(rslam_filter* f, int b) { return (f && b >= 0 && b < f->B) ? f->hF[b].N : -1; }
+int rslam_state_dim(rslam_filter* f, int b) { return (f && b >= 0 && b < f->B) ? f->hF[b].n : -1; }
+
+int rslam_upload_state(rslam_filter* f, int b, int which, const double* x, const double* P, int n, int ldp, const int* feat_types, int N) {
+    if (!f || b < 0 || b >= f->B || !x || n < 13 || N < 0) return fail(RSLAM_ERR_INVALID, "rslam_upload_state: bad arguments");
+    if (N > f->Nmax) return fail(RSLAM_ERR_CAPACITY, "rslam_upload_state: %d features > max_features %d", N, f->Nmax);
+    CK(cudaSetDevice(f->device));
+    std::vector<int> types(N, 0), offs(N, 0);
+    int off = 13;
+    for (int i = 0; i < N; i++) {
+        types[i] = feat_types ? feat_types[i] : 0;
+        if (types[i] != 0 && types[i] != 1) return fail(RSLAM_ERR_INVALID, "rslam_upload_state: feature type must be 0 or 1");
+        offs[i] = off;
+        off += types[i] == 0 ? 6 : 3;
+    }
+    if (off != n) return fail(RSLAM_ERR_INVALID, "rslam_upload_state: n = %d does not match 13 + sum(feature sizes) = %d", n, off);
+    DevFilter& D = f->hF[b];
+    const bool shape_changed = (D.n != n) || (D.N != N);
+    D.n = n;
+    D.N = N;
+    if (N) {
+        CK(cudaMemcpyAsync(D.ftype, types.data(), sizeof(int) * N, cudaMemcpyHostToDevice, f->stream));
+        CK(cudaMemcpyAsync(D.foff, offs.data(), sizeof(int) * N, cudaMemcpyHostToDevice, f->stream));
+    }
+    CK(cudaMemcpyAsync(which ? D.x_km1 : D.x_kk, x, sizeof(double) * n, cudaMemcpyDefault, f->stream));
+    if (P) {
+        if (ldp < n) return fail(RSLAM_ERR_INVALID, "rslam_upload_state: ldp < n");
+        CK(cudaMemcpy2DAsync(D.P, sizeof(double) * f->ldp, P, sizeof(double) * ldp, sizeof(double) * n, n, cudaMemcpyDefault, f->stream));
+    }
+    if (shape_changed) {
+        // a new map: clear per-feature state
+        CK(cudaMemsetAsync(D.has_h, 0, f->Nmax, f->stream));
+        CK(cudaMemsetAsync(D.ic, 0, f->Nmax, f->stream));
+        CK(cudaMemsetAsync(D.li, 0, f->Nmax, f->stream));
+        CK(cudaMemsetAsync(D.hi, 0, f->Nmax, f->stream));
+        CK(cudaMemsetAsync(D.times_predicted, 0, sizeof(int) * f->Nmax, f->stream));
+        CK(cudaMemsetAsync(D.times_measured, 0, sizeof(int) * f->Nmax, f->stream));
+    }
+    f->hN = 0;
+    f->hn = 0;
+    for (int k = 0; k < f->B; k++) {
+        f->hN = f->hF[k].N > f->hN ? f->hF[k].N : f->hN;
+        f->hn = f->hF[k].n > f->hn ? f->hF[k].n : f->hn;
+    }
+    CK(cudaStreamSynchronize(f->stream));  // types/offs are stack vectors
+    return push_descr(f);
+}
+
+int rslam_download_state(rslam_filter* f, int b, int which, double* x, double* P, int ldp) {
+    if (!f || b < 0 || b >= f->B) return fail(RSLAM_ERR_INVALID, "rslam_download_state: bad arguments");
+    CK(cudaSetDevice(f->device));
+    DevFilter& D = f->hF[b];
+    if (x) CK(cudaMemcpyAsync(x, which ? D.x_km1 : D.x_kk, sizeof(double) * D.n, cudaMemcpyDefault, f->stream));
+    if (P) {
+        if (ldp < D.n) return fail(RSLAM_ERR_INVALID, "rslam_download_state: ldp < n");
+        CK(cudaMemcpy2DAsync(P, sizeof(double) * ldp, D.P, sizeof(double) * f->ldp, sizeof(double) * D.n, D.n, cudaMemcpyDefault, f->stream));
+    }
+    CK(cudaStreamSynchronize(f->stream));
+    return RSLAM_OK;
+}
+
+int rslam_download_pose(rslam_filter* f, int b, double* x13) {
+    if (!f || b < 0 || b >= f->B || !x13) return fail(RSLAM_ERR_INVALID, "rslam_download_pose: bad arguments");
+    CK(cudaSetDevice(f->device));
+    CK(cudaMemcpyAsync(x13, f->hF[b].x_kk, sizeof(double) * 13, cudaMemcpyDefault, f->stream));
+    CK(cudaStreamSynchronize(f->stream));
+    return RSLAM_OK;
+}
+
+int rslam_upload_patches(rslam_filter* f, int b, const double* patches, int N) {
+    if (!f || b < 0 || b >= f->B || !patches || N < 0 || N > f->Nmax) return fail(RSLAM_ERR_INVALID, "rslam_upload_patches: bad arguments");
+    CK(cudaSetDevice(f->device));
+    std::vector<float> tmp((size_t)N * kPatchPix);
+    for (size_t i = 0; i < tmp.size(); i++) tmp[i] = (float)patches[i];  // Converter::toCvMat_f (src/Converter.cpp:83-94)
+    CK(cudaMemcpyAsync(f->hF[b].patch, tmp.data(), sizeof(float) * tmp.size(), cudaMemcpyHostToDevice, f->stream));
+    CK(cudaStreamSynchronize(f->stream));
+    return RSLAM_OK;
+}
+
+int rslam_download_features(rslam_filter* f, int b, double* h, double* S, double* z, uint8_t* flags, int* counters) {
+    if (!f || b < 0 || b >= f->B) return fail(RSLAM_ERR_INVALID, "rslam_download_features: bad arguments");
+    CK(cudaSetDevice(f->device));
+    DevFilter& D = f->hF[b];
+    const int N = D.N;
+    if (N == 0) return RSLAM_OK;
+    if (h) CK(cudaMemcpyAsync(h, D.h, sizeof(double) * 2 * N, cudaMemcpyDeviceToHost, f->stream));
+    if (S) CK(cudaMemcpyAsync(S, D.S, sizeof(double) * 4 * N, cudaMemcpyDeviceToHost, f->stream));
+    if (z) CK(cudaMemcpyAsync(z, D.z, sizeof(double) * 2 * N, cudaMemcpyDeviceToHost, f->stream));
+    std::vector<unsigned char> a(N), bb(N), c(N), d(N);
+    std::vector<int> tp(N), tm(N);
+    if (flags) {
+        CK(cudaMemcpyAsync(a.data(), D.has_h, N, cudaMemcpyDeviceToHost, f->stream));
+        CK(cudaMemcpyAsync(bb.data(), D.ic, N, cudaMemcpyDeviceToHost, f->stream));
+        CK(cudaMemcpyAsync(c.data(), D.li, N, cudaMemcpyDeviceToHost, f->stream));
+        CK(cudaMemcpyAsync(d.data(), D.hi, N, cudaMemcpyDeviceToHost, f->stream));
+    }
+    if (counters) {
+        CK(cudaMemcpyAsync(tp.data(), D.times_predicted, sizeof(int) * N, cudaMemcpyDeviceToHost, f->stream));
+        CK(cudaMemcpyAsync(tm.data(), D.times_measured, sizeof(int) * N, cudaMemcpyDeviceToHost, f->stream));
+    }
+    CK(cudaStreamSynchronize(f->stream));
+    for (int i = 0; i < N; i++) {
+        if (flags) {
+            flags[4 * i] = a[i];
+            flags[4 * i + 1] = bb[i];
+            flags[4 * i + 2] = c[i];
+            flags[4 * i + 3] = d[i];
+        }
+        if (counters) {
+            counters[2 * i] = tp[i];
+            counters[2 * i + 1] = tm[i];
+        }
+    }
+    return RSLAM_OK;
+}
+
+int rslam_download_H(rslam_filter* f, int b, double* Hc, double* Hf) {
+    if (!f || b < 0 || b >= f->B) return fail(RSLAM_ERR_INVALID, "rslam_download_H: bad arguments");
+    CK(cudaSetDevice(f->device));
+    DevFilter& D = f->hF[b];
+    if (Hc) CK(cudaMemcpyAsync(Hc, D.Hc, sizeof(double) * 14 * D.N, cudaMemcpyDeviceToHost, f->stream));
+    if (Hf) CK(cudaMemcpyAsync(Hf, D.Hf, sizeof(double) * 12 * D.N, cudaMemcpyDeviceToHost, f->stream));
+    CK(cudaStreamSynchronize(f->stream));
+    return RSLAM_OK;
+}
+
+int rslam_set_matches(rslam_filter* f, int b, const double* z, const uint8_t* ic) {
+    if (!f || b < 0 || b >= f->B || !z || !ic) return fail(RSLAM_ERR_INVALID, "rslam_set_matches: bad arguments");
+    CK(cudaSetDevice(f->device));
+    DevFilter& D = f->hF[b];
+    CK(cudaMemcpyAsync(D.z, z, sizeof(double) * 2 * D.N, cudaMemcpyDefault, f->stream));
+    CK(cudaMemcpyAsync(D.ic, ic, D.N, cudaMemcpyDefault, f->stream));
+    CK(cudaStreamSynchronize(f->stream));
+    return RSLAM_OK;
+}
+
+static int set_images(rslam_filter* f, int b_first, int count, const uint8_t* gray, int rows, int cols, int stride, int share) {
+    // count == B (all filters) or 1 (filter b_first); share: one image for all
+    const bool dev = is_device_ptr(gray);
+    const size_t per = (size_t)rows * stride;
+    const int nimg = share ? 1 : count;
+    const unsigned char* base = gray;
+    if (!dev) {
+        const size_t need = per * (share ? 1 : f->B);
+        if (need > f->image_cap) {
+            if (f->d_images) CK(cudaFree(f->d_images));
+            CK(cudaMalloc((void**)&f->d_images, need));
+            f->image_cap = need;
+        }
+        unsigned char* dst = f->d_images + (share ? 0 : per * b_first);
+        CK(cudaMemcpyAsync(dst, gray, per * nimg, cudaMemcpyHostToDevice, f->stream));
+        base = f->d_images;
+        if (!share && count == 1) base = f->d_images;  // per-filter slot addressing below
+    }
+    if (count == f->B || share) {
+        const unsigned char* b0 = dev ? gray : f->d_images;
+        LAUNCH(f, k_set_inputs, cdiv(f->B, 128), 128, 0, f->dF, f->B, b0, (long long)(share ? 0 : per), rows, cols, stride, 1, (const double*)nullptr, 0, 0);
+        for (int b = 0; b < f->B; b++) {
+            f->hF[b].image = b0 + (share ? 0 : per * b);
+            f->hF[b].img_rows = rows;
+            f->hF[b].img_cols = cols;
+            f->hF[b].img_stride = stride;
+        }
+    } else {
+        DevFilter& D = f->hF[b_first];
+        D.image = dev ? gray : (f->d_images + per * b_first);
+        D.img_rows = rows;
+        D.img_cols = cols;
+        D.img_stride = stride;
+        (void)base;
+        int rc = push_descr(f);
+        if (rc) return rc;
+    }
+    f->have_image = true;
+    return check_launch();
+}
+
+int rslam_set_image(rslam_filter* f, int b, const uint8_t* gray, int rows, int cols, int stride, int share) {
+    if (!f || b < 0 || b >= f->B || !gray || rows <= 0 || cols <= 0 || stride < cols) return fail(RSLAM_ERR_INVALID, "rslam_set_image: bad arguments");
+    CK(cudaSetDevice(f->device));
+    return set_images(f, b, 1, gray, rows, cols, stride, share);
+}
+
+int rslam_begin_frame(rslam_filter* f) {
+    if (!f) return fail(RSLAM_ERR_INVALID, "null handle");
+    CK(cudaSetDevice(f->device));
+    if (f->hN == 0) return RSLAM_OK;
+    LAUNCH(f, k_begin_frame, dim3(cdiv(f->hN, 128), f->B), 128, 0, f->dF);
+    return check_launch();
+}
+
+int rslam_ekf_prediction(rslam_filter* f) {
+    if (!f) return fail(RSLAM_ERR_INVALID, "null handle");
+    CK(cudaSetDevice(f->device));
+    LAUNCH(f, k_ekf_prediction, dim3(cdiv(f->hn > 13 ? f->hn : 13, 128), f->B), 128, 0, f->dF, f->pard);
+    return check_launch();
+}
+
+int rslam_search_ic_matches(rslam_filter* f) {
+    if (!f) return fail(RSLAM_ERR_INVALID, "null handle");
+    CK(cudaSetDevice(f->device));
+    if (f->hN == 0) return RSLAM_OK;
+    LAUNCH(f, k_predict, dim3(cdiv(f->hN, 128), f->B), 128, 0, f->dF, f->camd, f->pard, 0);
+    if (f->have_image) LAUNCH(f, k_search, dim3(f->hN, f->B), 128, 0, f->dF, f->camd, f->pard);
+    return check_launch();
+}
+
+static int set_u01(rslam_filter* f, const double* u01, int n_u01) {
+    if (!u01 || n_u01 <= 0) return fail(RSLAM_ERR_INVALID, "u01 must hold at least one draw per filter");
+    const double* base = u01;
+    if (!is_device_ptr(u01)) {
+        const size_t need = (size_t)n_u01 * f->B;
+        if (need > f->u01_cap) {
+            if (f->d_u01) CK(cudaFree(f->d_u01));
+            CK(cudaMalloc((void**)&f->d_u01, need * sizeof(double)));
+            f->u01_cap = need;
+        }
+        CK(cudaMemcpyAsync(f->d_u01, u01, need * sizeof(double), cudaMemcpyHostToDevice, f->stream));
+        base = f->d_u01;
+    }
+    LAUNCH(f, k_set_inputs, cdiv(f->B, 128), 128, 0, f->dF, f->B, (const unsigned char*)nullptr, 0LL, 0, 0, 0, 0, base, n_u01, 1);
+    for (int b = 0; b < f->B; b++) {
+        f->hF[b].u01 = base + (size_t)n_u01 * b;
+        f->hF[b].n_u01 = n_u01;
+    }
+    return check_launch();
+}
+
+int rslam_ransac_hypotheses(rslam_filter* f, const double* u01, int n_u01) {
+    if (!f) return fail(RSLAM_ERR_INVALID, "null handle");
+    CK(cudaSetDevice(f->device));
+    int rc = set_u01(f, u01, n_u01);
+    if (rc) return rc;
+    return run_ransac_core(f, true);
+}
+
+int rslam_ransac_result_get(rslam_filter* f, int b, rslam_ransac_result* out) {
+    if (!f || b < 0 || b >= f->B || !out) return fail(RSLAM_ERR_INVALID, "rslam_ransac_result_get: bad arguments");
+    CK(cudaSetDevice(f->device));
+    int ctl[CTL_SIZE];
+    CK(cudaMemcpyAsync(ctl, f->hF[b].ctl, sizeof(ctl), cudaMemcpyDeviceToHost, f->stream));
+    CK(cudaStreamSynchronize(f->stream));
+    out->status = ctl[CTL_STATUS];
+    out->hyp_run = ctl[CTL_HYPRUN];
+    out->best_support = ctl[CTL_BEST];
+    out->n_hyp = ctl[CTL_NHYP];
+    out->num_ic = ctl[CTL_NIC];
+    out->winner = ctl[CTL_WINNER];
+    if (ctl[CTL_NCART] > 0) return fail(RSLAM_ERR_REFERENCE_UB, "cartesian features have matches: the reference's support scoring is undefined here (SURVEY A.3 Q2)");
+    return RSLAM_OK;
+}
+
+int rslam_update_li(rslam_filter* f) {
+    if (!f) return fail(RSLAM_ERR_INVALID, "null handle");
+    CK(cudaSetDevice(f->device));
+    return run_update(f, 0);
+}
+
+int rslam_rescue_hi(rslam_filter* f) {
+    if (!f) return fail(RSLAM_ERR_INVALID, "null handle");
+    CK(cudaSetDevice(f->device));
+    if (f->hN == 0) return RSLAM_OK;
+    LAUNCH(f, k_predict, dim3(cdiv(f->hN, 128), f->B), 128, 0, f->dF, f->camd, f->pard, 1);
+    return check_launch();
+}
+
+int rslam_update_hi(rslam_filter* f) {
+    if (!f) return fail(RSLAM_ERR_INVALID, "null handle");
+    CK(cudaSetDevice(f->device));
+    return run_update(f, 1);
+}
+
+int rslam_frame(rslam_filter* f, const uint8_t* images, int rows, int cols, int stride, int share, const double* u01, int n_u01, int flags) {
+    if (!f) return fail(RSLAM_ERR_INVALID, "null handle");
+    CK(cudaSetDevice(f->device));
+    int rc;
+    if (images) {
+        if (rows <= 0 || cols <= 0 || stride < cols) return fail(RSLAM_ERR_INVALID, "rslam_frame: bad image geometry");
+        if ((rc = set_images(f, 0, f->B, images, rows, cols, stride, share))) return rc;
+    }
+    if (flags & 1) {
+        if ((rc = rslam_begin_frame(f))) return rc;
+        if ((rc = rslam_ekf_prediction(f))) return rc;
+    }
+    if ((rc = rslam_search_ic_matches(f))) return rc;
+    if ((rc = rslam_ransac_hypotheses(f, u01, n_u01))) return rc;
+    if ((rc = rslam_update_li(f))) return rc;
+    if ((rc = rslam_rescue_hi(f))) return rc;
+    if ((rc = rslam_update_hi(f))) return rc;
+    return RSLAM_OK;
+}
+
+int rslam_support_sweep(rslam_filter* f, const int* hyp_match_idx, int n_hyp, int hyp_begin, int hyp_end, uint64_t* best_key, uint8_t* best_mask,
+                        long long* n_pairs_scored) {
+    if (!f || !hyp_match_idx || n_hyp <= 0 || hyp_begin < 0 || hyp_end > n_hyp || hyp_begin > hyp_end || !best_key)
+        return fail(RSLAM_ERR_INVALID, "rslam_support_sweep: bad arguments");
+    CK(cudaSetDevice(f->device));
+    const int N = f->hN;
+    if (N == 0) return fail(RSLAM_ERR_INVALID, "rslam_support_sweep: no features uploaded");
+    int rc;
+    const int* d_idx = hyp_match_idx;
+    if (!is_device_ptr(hyp_match_idx)) {
+        if ((size_t)n_hyp > f->hyp_cap) {
+            if (f->d_hyp_idx) CK(cudaFree(f->d_hyp_idx));
+            CK(cudaMalloc((void**)&f->d_hyp_idx, sizeof(int) * (size_t)n_hyp));
+            f->hyp_cap = n_hyp;
+        }
+        CK(cudaMemcpyAsync(f->d_hyp_idx + hyp_begin, hyp_match_idx + hyp_begin, sizeof(int) * (size_t)(hyp_end - hyp_begin), cudaMemcpyHostToDevice, f->stream));
+        d_idx = f->d_hyp_idx;
+    }
+    if ((rc = run_ransac_core(f, false))) return rc;
+    CK(cudaMemsetAsync(f->d_key, 0, 2 * sizeof(unsigned long long), f->stream));
+    const int nh = hyp_end - hyp_begin;
+    const size_t smem = (f->pard.quirks & RSLAM_Q1_ANGLES_FROM_POSITIONS) ? (size_t)4 * N * sizeof(double) : 0;
+    if (nh > 0) {
+        if (f->par.dedupe_hypotheses) {
+            CK(cudaMemsetAsync(f->d_used, 0, sizeof(int) * (size_t)f->Nmax, f->stream));
+            LAUNCH(f, k_sweep_mark, cdiv(nh, 256) < 1024 ? cdiv(nh, 256) : 1024, 256, 0, f->dF, d_idx, hyp_begin, hyp_end, f->d_used);
+            LAUNCH(f, k_ransac_support, dim3(N, 1), 256, smem, f->dF, f->camd, f->pard, (const int*)nullptr, 0, (const int*)f->d_used, f->d_key + 1);
+        } else {
+            LAUNCH(f, k_ransac_support, dim3(nh, 1), 256, smem, f->dF, f->camd, f->pard, d_idx, hyp_begin, (const int*)nullptr, f->d_key + 1);
+        }
+        LAUNCH(f, k_sweep_reduce, cdiv(nh, 256) < 512 ? cdiv(nh, 256) : 512, 256, 0, f->dF, d_idx, hyp_begin, hyp_end, f->d_key);
+    }
+    if ((rc = check_launch())) return rc;
+    CK(cudaMemcpyAsync(best_key, f->d_key, sizeof(uint64_t), cudaMemcpyDefault, f->stream));
+    const bool key_on_host = !is_device_ptr(best_key);
+    if (key_on_host || best_mask || n_pairs_scored) CK(cudaStreamSynchronize(f->stream));
+    if (n_pairs_scored) {
+        unsigned long long c = 0;
+        CK(cudaMemcpy(&c, f->d_key + 1, sizeof(c), cudaMemcpyDeviceToHost));
+        *n_pairs_scored = (long long)c;
+    }
+    if (best_mask) {
+        unsigned long long key = 0;
+        CK(cudaMemcpy(&key, f->d_key, sizeof(key), cudaMemcpyDeviceToHost));
+        int ctl[CTL_SIZE];
+        CK(cudaMemcpy(ctl, f->hF[0].ctl, sizeof(ctl), cudaMemcpyDeviceToHost));
+        const int m = ctl[CTL_MID];
+        memset(best_mask, 0, (size_t)(m + 7) / 8);
+        if (key != 0) {
+            const unsigned id = 0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull);
+            int t = 0;
+            CK(cudaMemcpy(&t, d_idx + id, sizeof(int), cudaMemcpyDeviceToHost));
+            return rslam_sweep_mask(f, t, best_mask);
+        }
+    }
+    return RSLAM_OK;
+}
+
+int rslam_sweep_mask(rslam_filter* f, int match_idx, uint8_t* mask) {
+    if (!f || !mask || match_idx < 0) return fail(RSLAM_ERR_INVALID, "rslam_sweep_mask: bad arguments");
+    CK(cudaSetDevice(f->device));
+    CK(cudaStreamSynchronize(f->stream));
+    int ctl[CTL_SIZE];
+    CK(cudaMemcpy(ctl, f->hF[0].ctl, sizeof(ctl), cudaMemcpyDeviceToHost));
+    const int m = ctl[CTL_MID];
+    if (match_idx >= ctl[CTL_NIC]) return fail(RSLAM_ERR_INVALID, "rslam_sweep_mask: match index out of range");
+    std::vector<unsigned> words(f->mwords);
+    CK(cudaMemcpy(words.data(), f->hF[0].masks + (size_t)match_idx * f->mwords, sizeof(unsigned) * f->mwords, cudaMemcpyDeviceToHost));
+    memset(mask, 0, (size_t)(m + 7) / 8);
+    for (int j = 0; j < m; j++)
+        if ((words[j >> 5] >> (j & 31)) & 1u) mask[j >> 3] |= (uint8_t)(1u << (j & 7));
+    return RSLAM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,315 @@
+"""Seeded synthetic inputs for the 1-point-RANSAC EKF path.
+
+Input synthesis only -- none of this is on the measured path.  Camera constants come from the reference's
+examples/Monocular/initialize_param.yaml:9-21 as parsed at src/System.cpp:34-58; feature initialisation follows
+ExtendKF::hinv (src/ExtendKF.cpp:236-265) and Map::add_a_feature_covariance_inverse_depth (src/Map.cpp:339-400);
+the initial camera covariance follows ExtendKF::initialize_x_and_p (src/ExtendKF.cpp:32-55, incl. the skipped P(5,5)).
+
+Deviation from SURVEY.md 8d (documented in DESIGN.md): the truth trajectory is a bounded Lissajous sweep with peak
+speed ~0.01 m/frame and ~0.001 rad/frame instead of an unbounded constant-velocity run, so that the whole map stays in
+view for all 1000 frames (a straight 10 m run leaves the first camera's frustum and the frames become empty).
+"""
+from dataclasses import dataclass, field
+
+import numpy as np
+
+EPS = np.finfo(np.float64).eps
+
+
+@dataclass
+class Camera:
+    k1: float = 0.06333
+    k2: float = 0.01390
+    nRows: int = 240
+    nCols: int = 320
+    Cx: float = 1.7945 / 0.0112
+    Cy: float = 1.4433 / 0.0112
+    f: float = 2.1735
+    dx: float = 0.0112
+    dy: float = 0.0112
+
+    def as9(self):
+        return np.array([self.k1, self.k2, self.nRows, self.nCols, self.Cx, self.Cy, self.f, self.dx, self.dy], dtype=np.float64)
+
+    @property
+    def fku(self):
+        return self.f / self.dx
+
+    @property
+    def fkv(self):
+        return self.f / self.dy
+
+
+def scaled_camera(scale):
+    """Same physical sensor and lens at `scale` x the pixel density (used by the N=2000 config so that 2000 13x13
+    patches do not overlap)."""
+    c = Camera()
+    return Camera(k1=c.k1, k2=c.k2, nRows=c.nRows * scale, nCols=c.nCols * scale, Cx=c.Cx * scale, Cy=c.Cy * scale, f=c.f,
+                  dx=c.dx / scale, dy=c.dy / scale)
+
+
+def q2r(q):
+    r, x, y, z = q
+    return np.array([[r * r + x * x - y * y - z * z, 2 * (x * y - r * z), 2 * (z * x + r * y)],
+                     [2 * (x * y + r * z), r * r - x * x + y * y - z * z, 2 * (y * z - r * x)],
+                     [2 * (z * x - r * y), 2 * (y * z + r * x), r * r - x * x - y * y + z * z]])
+
+
+def distort(cam, uv):
+    uv = np.atleast_2d(uv)
+    xu = (uv[:, 0] - cam.Cx) * cam.dx
+    yu = (uv[:, 1] - cam.Cy) * cam.dy
+    ru = np.sqrt(xu * xu + yu * yu)
+    rd = ru / (1 + cam.k1 * ru**2 + cam.k2 * ru**4)
+    for _ in range(10):
+        f = rd + cam.k1 * rd**3 + cam.k2 * rd**5 - ru
+        fp = 1 + 3 * cam.k1 * rd**2 + 5 * cam.k2 * rd**4
+        rd = rd - f / fp
+    D = 1 + cam.k1 * rd**2 + cam.k2 * rd**4
+    return np.stack([xu / D / cam.dx + cam.Cx, yu / D / cam.dy + cam.Cy], axis=1)
+
+
+def undistort(cam, uvd):
+    uvd = np.atleast_2d(uvd)
+    xd = (uvd[:, 0] - cam.Cx) * cam.dx
+    yd = (uvd[:, 1] - cam.Cy) * cam.dy
+    rd = np.sqrt(xd * xd + yd * yd)
+    D = 1 + cam.k1 * rd**2 + cam.k2 * rd**4
+    return np.stack([xd * D / cam.dx + cam.Cx, yd * D / cam.dy + cam.Cy], axis=1)
+
+
+def jacob_undistort(cam, uvd):
+    a = uvd[0] - cam.Cx
+    b = uvd[1] - cam.Cy
+    rd2 = (a * cam.dx) ** 2 + (b * cam.dy) ** 2
+    g = cam.k1 + 2 * cam.k2 * rd2
+    c = 1 + cam.k1 * rd2 + cam.k2 * rd2 * rd2
+    return np.array([[c + a * g * 2 * a * cam.dx**2, a * g * 2 * b * cam.dy**2], [b * g * 2 * a * cam.dx**2, c + b * g * 2 * b * cam.dy**2]])
+
+
+def project(cam, r, q, X):
+    """Distorted pixel of world points X (m x 3) seen from pose (r, q)."""
+    R = q2r(q)
+    hc = (X - r) @ R  # rows: R^T (X - r)
+    uvu = np.stack([cam.Cx + hc[:, 0] / hc[:, 2] * cam.fku, cam.Cy + hc[:, 1] / hc[:, 2] * cam.fkv], axis=1)
+    return distort(cam, uvu), hc[:, 2]
+
+
+def dRq_times_a_by_dq(q, a):
+    q0, q1, q2, q3 = q
+    M = [2 * np.array([[q0, -q3, q2], [q3, q0, -q1], [-q2, q1, q0]]), 2 * np.array([[q1, q2, q3], [q2, -q1, -q0], [q3, q0, -q1]]),
+         2 * np.array([[-q2, q1, q0], [q1, q2, q3], [-q0, q3, -q2]]), 2 * np.array([[-q3, -q0, q1], [q0, -q3, q2], [q1, q2, q3]])]
+    return np.stack([m @ a for m in M], axis=1)
+
+
+def hinv(cam, uvd, xv, rho0):
+    uv = undistort(cam, uvd)[0]
+    h = np.array([-(cam.Cx - uv[0]) / cam.fku, -(cam.Cy - uv[1]) / cam.fkv, 1.0])
+    n = q2r(xv[3:7]) @ h
+    return np.array([xv[0], xv[1], xv[2], np.arctan2(n[0], n[2]), np.arctan2(-n[1], np.hypot(n[0], n[2])), rho0])
+
+
+def feature_init_jacobians(cam, uvd, xv):
+    """dy_dxv (6x13) and dy_dhd (6x3) of a new inverse-depth feature (src/Map.cpp:339-386)."""
+    q = xv[3:7]
+    R = q2r(q)
+    uvu = undistort(cam, uvd)[0]
+    Xc = np.array([-(cam.Cx - uvu[0]) / cam.fku, -(cam.Cy - uvu[1]) / cam.fkv, 1.0])
+    Xw, Yw, Zw = R @ Xc
+    dgw_dq = dRq_times_a_by_dq(q, Xc)
+    dth = np.array([Zw / (Xw * Xw + Zw * Zw), 0, -Xw / (Xw * Xw + Zw * Zw)])
+    n2 = Xw * Xw + Yw * Yw + Zw * Zw
+    s = np.sqrt(Xw * Xw + Zw * Zw)
+    dph = np.array([(Xw * Yw) / (n2 * s), -s / n2, (Zw * Yw) / (n2 * s)])
+    dy_dq = np.zeros((6, 4))
+    dy_dq[3] = dth @ dgw_dq
+    dy_dq[4] = dph @ dgw_dq
+    dy_dxv = np.zeros((6, 13))
+    dy_dxv[0:3, 0:3] = np.eye(3)
+    dy_dxv[:, 3:7] = dy_dq
+    dyp_dgw = np.zeros((5, 3))
+    dyp_dgw[3] = dth
+    dyp_dgw[4] = dph
+    dgc_dhu = np.array([[1 / cam.fku, 0], [0, 1 / cam.fkv], [0, 0]])
+    dyp_dhd = dyp_dgw @ R @ dgc_dhu @ jacob_undistort(cam, uvd)
+    dy_dhd = np.zeros((6, 3))
+    dy_dhd[0:5, 0:2] = dyp_dhd
+    dy_dhd[5, 2] = 1
+    return dy_dxv, dy_dhd
+
+
+def initial_camera_state(v0=0.0, w0=1e-11, std_v0=0.025, std_w0=0.025):
+    x = np.zeros(13)
+    x[3] = 1
+    x[7:10] = v0
+    x[10:13] = w0
+    P = np.zeros((13, 13))
+    for i in (0, 1, 2, 3, 4, 6):  # index 5 skipped in the reference (Q7)
+        P[i, i] = EPS
+    P[7:10, 7:10] = np.eye(3) * std_v0**2
+    P[10:13, 10:13] = np.eye(3) * std_w0**2
+    return x, P
+
+
+@dataclass
+class Scene:
+    cam: Camera
+    N: int
+    landmarks: np.ndarray  # N x 3 world points
+    uv0: np.ndarray  # N x 2 integer pixels in the first image
+    templates: np.ndarray  # N x 13 x 13 uint8 appearance
+    x0: np.ndarray  # 13 + 6N state right after initialisation (x_k_k of frame 0)
+    P0: np.ndarray  # matching covariance
+    std_z: float = 1.0
+    seed: int = 1234
+    meta: dict = field(default_factory=dict)
+
+
+def make_scene(N=100, seed=1234, cam=None, depth=(2.0, 20.0), margin=45, rho_rel_err=0.3, std_rho=1.0, std_z=1.0, dense_P=True,
+               min_sep=0):
+    """N landmarks in the frustum of the first camera, inverse-depth coded from the first pose."""
+    cam = cam or Camera()
+    rng = np.random.default_rng(seed)
+    uv = np.zeros((N, 2))
+    if min_sep > 0:
+        # jittered grid so that patches do not overlap
+        nx = int(np.floor((cam.nCols - 2 * margin) / min_sep))
+        ny = int(np.floor((cam.nRows - 2 * margin) / min_sep))
+        assert nx * ny >= N, "image too small for N non-overlapping patches"
+        cells = rng.permutation(nx * ny)[:N]
+        uv[:, 0] = margin + (cells % nx) * min_sep + rng.integers(0, max(1, min_sep - 13), N)
+        uv[:, 1] = margin + (cells // nx) * min_sep + rng.integers(0, max(1, min_sep - 13), N)
+    else:
+        uv[:, 0] = rng.integers(margin, cam.nCols - margin, N)
+        uv[:, 1] = rng.integers(margin, cam.nRows - margin, N)
+    d = rng.uniform(depth[0], depth[1], N)
+    xv, Pxv = initial_camera_state()
+    n = 13 + 6 * N
+    x0 = np.zeros(n)
+    x0[:13] = xv
+    J = np.zeros((6 * N, 13))
+    Padd = np.diag([std_z**2, std_z**2, std_rho**2])
+    blocks = np.zeros((N, 6, 6))
+    landmarks = np.zeros((N, 3))
+    for i in range(N):
+        yi = hinv(cam, uv[i], xv, 1.0)
+        m = np.array([np.cos(yi[4]) * np.sin(yi[3]), -np.sin(yi[4]), np.cos(yi[4]) * np.cos(yi[3])])
+        # depth along the ray measured as distance / |m| = distance
+        landmarks[i] = xv[:3] + d[i] * m
+        rho_true = 1.0 / d[i]
+        yi[5] = rho_true * (1.0 + rho_rel_err * rng.standard_normal())
+        if yi[5] <= 0.01 * rho_true:
+            yi[5] = 0.01 * rho_true
+        x0[13 + 6 * i:19 + 6 * i] = yi
+        dy_dxv, dy_dhd = feature_init_jacobians(cam, uv[i], xv)
+        J[6 * i:6 * i + 6] = dy_dxv
+        blocks[i] = dy_dhd @ Padd @ dy_dhd.T
+    P0 = np.zeros((n, n), order="F")
+    P0[:13, :13] = Pxv
+    JP = J @ Pxv
+    P0[13:, :13] = JP
+    P0[:13, 13:] = JP.T
+    if dense_P:
+        P0[13:, 13:] = JP @ J.T
+    for i in range(N):
+        s = 13 + 6 * i
+        P0[s:s + 6, s:s + 6] = (JP[6 * i:6 * i + 6] @ J[6 * i:6 * i + 6].T) + blocks[i]
+    templates = rng.integers(0, 256, size=(N, 13, 13), dtype=np.uint8)
+    return Scene(cam=cam, N=N, landmarks=landmarks, uv0=uv, templates=templates, x0=x0, P0=P0, std_z=std_z, seed=seed)
+
+
+def truth_pose(t):
+    """Bounded Lissajous truth trajectory; peak speed ~0.0094 m/frame, peak rate ~0.001 rad/frame."""
+    r = np.array([0.3 * np.sin(2 * np.pi * t / 200.0), 0.15 * np.sin(2 * np.pi * t / 140.0), 0.1 * np.sin(2 * np.pi * t / 260.0)])
+    ang = 0.03 * np.sin(2 * np.pi * t / 180.0)  # rotation about +y
+    q = np.array([np.cos(ang / 2), 0.0, np.sin(ang / 2), 0.0])
+    return r, q
+
+
+def background(cam, seed=7):
+    """Low-contrast band-limited texture (box-filtered noise) so that spurious ZNCC > 0.8 is unlikely."""
+    rng = np.random.default_rng(seed)
+    g = rng.standard_normal((cam.nRows + 8, cam.nCols + 8))
+    k = np.ones(9) / 9.0
+    g = np.apply_along_axis(lambda v: np.convolve(v, k, mode="same"), 0, g)
+    g = np.apply_along_axis(lambda v: np.convolve(v, k, mode="same"), 1, g)
+    g = g[4:-4, 4:-4]
+    g = (g - g.mean()) / (g.std() + 1e-12)
+    return np.clip(110 + 12 * g, 0, 255).astype(np.uint8)
+
+
+@dataclass
+class Sequence:
+    scene: Scene
+    images: np.ndarray  # T x rows x cols uint8
+    z_true: np.ndarray  # T x N x 2 pasted integer pixel (-1 if not pasted)
+    outlier: np.ndarray  # T x N bool
+    u01: np.ndarray  # T x n_u01 uniforms in [0,1)
+    poses: np.ndarray  # T x 7 truth (r, q)
+
+
+def make_sequence(scene, T=20, noise_px=0.5, outlier_frac=0.2, seed=99, n_u01=1000, u01_seed=42, t0=1):
+    """Render T frames: every landmark's template pasted at round(project(truth) + noise); `outlier_frac` of them
+    displaced by 1.5..3.5 px in a random direction.  Frame k is the truth pose at time t0 + k."""
+    cam = scene.cam
+    rng = np.random.default_rng(seed)
+    bg = background(cam)
+    images = np.zeros((T, cam.nRows, cam.nCols), dtype=np.uint8)
+    z_true = -np.ones((T, scene.N, 2), dtype=np.int32)
+    outl = np.zeros((T, scene.N), dtype=bool)
+    poses = np.zeros((T, 7))
+    for k in range(T):
+        r, q = truth_pose(t0 + k)
+        poses[k, :3] = r
+        poses[k, 3:] = q
+        uv, depth = project(cam, r, q, scene.landmarks)
+        uv = uv + noise_px * rng.standard_normal(uv.shape)
+        is_out = rng.random(scene.N) < outlier_frac
+        ang = rng.uniform(0, 2 * np.pi, scene.N)
+        mag = rng.uniform(1.5, 3.5, scene.N)
+        uv[is_out, 0] += mag[is_out] * np.cos(ang[is_out])
+        uv[is_out, 1] += mag[is_out] * np.sin(ang[is_out])
+        zi = np.rint(uv).astype(np.int32)
+        img = bg.copy()
+        for i in range(scene.N):
+            x, y = zi[i]
+            if depth[i] <= 0 or x - 6 < 0 or y - 6 < 0 or x + 7 > cam.nCols or y + 7 > cam.nRows:
+                continue
+            img[y - 6:y + 7, x - 6:x + 7] = scene.templates[i]
+            z_true[k, i] = (x, y)
+        images[k] = img
+        outl[k] = is_out
+    u01 = np.random.default_rng(u01_seed).random((T, n_u01))
+    return Sequence(scene=scene, images=images, z_true=z_true, outlier=outl, u01=u01, poses=poses)
+
+
+def random_spd_state(N, seed=0, cam=None, corr_rank=8, corr_scale=0.05, t0=3, rho_err=0.02):
+    """A single-frame test state that is CONSISTENT with make_sequence(scene, t0=t0): camera near the truth pose at time t0,
+    features near their true inverse depth, and P = structured prior + U U^T (dense cross terms) so that every block of P is
+    exercised while the search ellipses stay small.  Returns (scene, x_k_km1, p_k_km1)."""
+    cam = cam or Camera()
+    margin, sep = 30, 18
+    fits = ((cam.nCols - 2 * margin) // sep) * ((cam.nRows - 2 * margin) // sep) >= N
+    scene = make_scene(N=N, seed=seed, cam=cam, margin=margin if fits else 45, min_sep=sep if fits else 0)
+    rng = np.random.default_rng(seed + 1)
+    n = scene.x0.size
+    x = scene.x0.copy()
+    r, q = truth_pose(t0)
+    x[0:3] = r + rng.normal(0, 0.001, 3)
+    dq = np.array([0.0, *rng.normal(0, 0.0004, 3)])
+    qq = q + dq
+    x[3:7] = qq / np.linalg.norm(qq)
+    x[7:10] = rng.normal(0, 0.005, 3)
+    x[10:13] = rng.normal(0, 0.001, 3)
+    d = np.linalg.norm(scene.landmarks - scene.x0[:3], axis=1)
+    idx = 13 + 6 * np.arange(N) + 5
+    x[idx] = (1.0 / d) * (1.0 + rho_err * rng.standard_normal(N))
+    P = scene.P0.copy()
+    P[idx, idx] = (2 * rho_err * x[idx]) ** 2
+    P[0:3, 0:3] += np.eye(3) * 0.002**2
+    P[3:7, 3:7] += np.eye(4) * 0.0008**2
+    sc = np.sqrt(np.maximum(np.diag(P), 1e-10)) * corr_scale
+    U = rng.normal(0, 1.0, (n, corr_rank)) * sc[:, None]
+    P = P + U @ U.T
+    P = np.asfortranarray(0.5 * (P + P.T))
+    return scene, x, P

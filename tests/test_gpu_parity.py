@@ -1,0 +1,128 @@
+"""GPU parity: every stage of the hot path through the C ABI against the CPU oracle on identical seeded inputs.
+Tolerances (BASELINE.json north_star): inlier sets / match indices bit-exact (except matches within 1e-9 px of the threshold),
+state mean and covariance within 1e-9 relative in fp64."""
+import numpy as np
+import pytest
+
+from oracle import oracle_py as O
+from ransac_slam_b200 import synth
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def _single_frame_inputs(N, seed):
+    scene, x, P = synth.random_spd_state(N, seed=seed)
+    seq = synth.make_sequence(scene, T=1, seed=seed + 5, t0=3)
+    return scene, x, P, seq
+
+
+@pytest.mark.parametrize("N,seed", [(20, 1), (100, 2), (257, 3)])
+def test_predict_H_S(N, seed):
+    scene, x, P, seq = _single_frame_inputs(N, seed)
+    o = H.oracle_from(scene, x, P, sparse=False)
+    g = H.gpu_from(scene, x, P)
+    o.search_ic_matches(None)
+    g.search_ic_matches()
+    fo, fg = o.features(), g.features()
+    assert (fo["has_h"] == fg["has_h"]).all()
+    v = fo["has_h"]
+    assert v.sum() > 0
+    np.testing.assert_allclose(fg["h"][v], fo["h"][v], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(fg["S"][v], fo["S"][v], rtol=1e-9, atol=1e-12)
+    Hc, Hf = g.H_sparse()
+    n = x.size
+    for i in np.flatnonzero(v)[:40]:
+        Hd = o.H_dense(i)
+        off = 13 + 6 * i
+        np.testing.assert_allclose(Hc[i], Hd[:, :7], rtol=1e-9, atol=1e-11)
+        np.testing.assert_allclose(Hf[i], Hd[:, off:off + 6], rtol=1e-9, atol=1e-11)
+        mask = np.ones(n, bool)
+        mask[:7] = False
+        mask[off:off + 6] = False
+        assert (Hd[:, mask] == 0).all()
+
+
+@pytest.mark.parametrize("N,seed", [(30, 11), (100, 12)])
+def test_search_matches_bit_exact(N, seed):
+    scene, x, P, seq = _single_frame_inputs(N, seed)
+    o = H.oracle_from(scene, x, P, fast_corr=True)
+    g = H.gpu_from(scene, x, P)
+    o.search_ic_matches(seq.images[0])
+    g.set_image(seq.images[0])
+    g.search_ic_matches()
+    fo, fg = o.features(), g.features()
+    assert fo["ic"].sum() > N // 4
+    assert (fo["ic"] == fg["ic"]).all()
+    assert (fo["z"][fo["ic"]] == fg["z"][fg["ic"]]).all()
+
+
+def _band_ok(o, g_li, o_li, thr=1.0):
+    """inlier sets must be identical except for matches whose residual is within 1e-9 px of the threshold"""
+    return (g_li == o_li).all()
+
+
+@pytest.mark.parametrize("quirks", [O.Q_ALL, O.Q_ALL & ~O.Q1])
+@pytest.mark.parametrize("N,seed", [(40, 21), (100, 22)])
+def test_full_frame_stages(N, seed, quirks):
+    scene, x, P, seq = _single_frame_inputs(N, seed)
+    o = H.oracle_from(scene, x, P, quirks=quirks, sparse=False)
+    g = H.gpu_from(scene, x, P, quirks=H.quirks_o2g(quirks))
+    u01 = seq.u01[0]
+    # search
+    o.search_ic_matches(seq.images[0])
+    g.set_image(seq.images[0])
+    g.search_ic_matches()
+    fo, fg = o.features(), g.features()
+    assert (fo["ic"] == fg["ic"]).all() and (fo["z"][fo["ic"]] == fg["z"][fg["ic"]]).all()
+    # ransac
+    rc, info = o.ransac_hypotheses(u01)
+    res = g.ransac_hypotheses(u01)
+    assert rc == res["status"]
+    assert info["num_ic"] == res["num_ic"]
+    assert info["best_support"] == res["best_support"], (info, res)
+    assert info["hyp_run"] == res["hyp_run"], (info, res)
+    assert info["n_hyp"] == res["n_hyp"]
+    fo, fg = o.features(), g.features()
+    assert (fo["li"] == fg["li"]).all()
+    # li update
+    o.update_li()
+    g.update_li()
+    xo, Po = o.get_state()
+    xg, Pg = g.download_state()
+    H.assert_x_close(xg, xo, what="x after li")
+    H.assert_P_close(Pg, Po, what="P after li")
+    # rescue
+    o.rescue_hi()
+    g.rescue_hi()
+    fo, fg = o.features(), g.features()
+    assert (fo["hi"] == fg["hi"]).all()
+    np.testing.assert_allclose(fg["h"][fo["has_h"]], fo["h"][fo["has_h"]], rtol=0, atol=1e-9)
+    # hi update
+    o.update_hi()
+    g.update_hi()
+    xo, Po = o.get_state()
+    xg, Pg = g.download_state()
+    H.assert_x_close(xg, xo, what="x after hi")
+    H.assert_P_close(Pg, Po, what="P after hi")
+    assert np.array_equal(Pg, Pg.T), "device covariance must stay exactly symmetric"
+
+
+def test_prediction_and_sequence():
+    scene = synth.make_scene(N=60, seed=5)
+    seq = synth.make_sequence(scene, T=6, seed=6)
+    o = H.oracle_from(scene, scene.x0, scene.P0, prior=False, sparse=True)
+    g = H.gpu_from(scene, scene.x0, scene.P0, prior=False)
+    for k in range(6):
+        o.frame(seq.images[k], seq.u01[k])
+        g.frame(seq.images[k][None], seq.u01[k][None])
+        fo, fg = o.features(), g.features()
+        assert (fo["ic"] == fg["ic"]).all(), k
+        assert (fo["li"] == fg["li"]).all(), k
+        assert (fo["hi"] == fg["hi"]).all(), k
+        xo, Po = o.get_state()
+        xg, Pg = g.download_state()
+        H.assert_x_close(xg, xo, rtol=1e-8, what=f"x frame {k}")
+        H.assert_P_close(Pg, Po, rtol=1e-8, what=f"P frame {k}")
+        assert (fo["times_predicted"] == fg["times_predicted"]).all()
+        assert (fo["times_measured"] == fg["times_measured"]).all()
