@@ -127,7 +127,10 @@ __global__ void __launch_bounds__(128) k_ekf_prediction(DevFilter* Fs, ParDev pa
             const int i = e / 13, j = e % 13;
             double s = 0;
             for (int k = 0; k < 13; k++) s += sT[i * 13 + k] * sF[j * 13 + k];
-            F.P[i + (size_t)j * ld] = s + sQ[e];
+            if (i >= j) {  // lower triangle is authoritative; mirror so that P stays exactly symmetric
+                F.P[i + (size_t)j * ld] = s + sQ[e];
+                F.P[j + (size_t)i * ld] = s + sQ[e];
+            }
         }
         if (threadIdx.x < 13) F.x_km1[threadIdx.x] = sX[threadIdx.x];
     }

@@ -479,7 +479,10 @@ __global__ void __launch_bounds__(256) k_upd_jnorm(DevFilter* Fs, ParDev par) {
         const int i = threadIdx.x / 4, j = threadIdx.x % 4;
         double s = 0;
         for (int l = 0; l < 4; l++) s += sT[i * 4 + l] * sJ[j * 4 + l];
-        P[(3 + i) + (size_t)(3 + j) * ld] = s;
+        if (i >= j) {  // lower triangle is authoritative; mirror so that P stays exactly symmetric
+            P[(3 + i) + (size_t)(3 + j) * ld] = s;
+            P[(3 + j) + (size_t)(3 + i) * ld] = s;
+        }
     }
     for (int c = threadIdx.x; c < F.n; c += blockDim.x) {
         if (c >= 3 && c < 7) continue;
