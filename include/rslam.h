@@ -126,6 +126,12 @@ int rslam_update_hi(rslam_filter* f);
  * images: batch images (or one shared, see rslam_set_image) host or device, may be NULL to keep the current one. */
 int rslam_frame(rslam_filter* f, const uint8_t* images, int rows, int cols, int stride, int share, const double* u01, int n_u01,
                 int flags);
+/* rslam_frame replays its fixed launch sequence as a CUDA graph (default on); 0 = plain stream launches */
+int rslam_set_graph(rslam_filter* f, int enable);
+/* diagnostics: per-launch CUDA-event timing of every kernel (slow path -- never enable inside a timed region).
+ * rslam_profile_read writes "kernel_name launches total_ms\n" lines accumulated since the previous read. */
+int rslam_profile_enable(rslam_filter* f, int enable);
+int rslam_profile_read(rslam_filter* f, char* buf, size_t buflen);
 /* camera pose of filter b after the frame: x_k_k[0..6] plus the 13-state head (13 doubles) */
 int rslam_download_pose(rslam_filter* f, int b, double* x13);
 

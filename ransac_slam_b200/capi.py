@@ -41,7 +41,7 @@ EXPORTS = [
     "rslam_launch_count", "rslam_num_features", "rslam_state_dim", "rslam_upload_state", "rslam_download_state", "rslam_upload_patches",
     "rslam_download_features", "rslam_download_H", "rslam_set_matches", "rslam_set_image", "rslam_begin_frame", "rslam_ekf_prediction",
     "rslam_search_ic_matches", "rslam_ransac_hypotheses", "rslam_ransac_result_get", "rslam_update_li", "rslam_rescue_hi", "rslam_update_hi",
-    "rslam_frame", "rslam_download_pose", "rslam_support_sweep", "rslam_sweep_mask",
+    "rslam_frame", "rslam_set_graph", "rslam_profile_enable", "rslam_profile_read", "rslam_download_pose", "rslam_support_sweep", "rslam_sweep_mask",
 ]
 
 _lib = None
@@ -82,6 +82,9 @@ def load():
     L.rslam_ransac_result_get.argtypes = [vp, ci, C.POINTER(RansacResult)]
     L.rslam_frame.argtypes = [vp, vp, ci, ci, ci, ci, vp, ci, ci]
     L.rslam_download_pose.argtypes = [vp, ci, vp]
+    L.rslam_set_graph.argtypes = [vp, ci]
+    L.rslam_profile_enable.argtypes = [vp, ci]
+    L.rslam_profile_read.argtypes = [vp, C.c_char_p, C.c_size_t]
     L.rslam_support_sweep.argtypes = [vp, vp, ci, ci, ci, vp, vp, vp]
     L.rslam_sweep_mask.argtypes = [vp, ci, vp]
     _lib = L
@@ -104,13 +107,15 @@ def make_camera(cam9):
 class Filter:
     """A batch of `batch` filters on one GPU (thin wrapper over the opaque rslam_filter handle)."""
 
-    def __init__(self, cam9, max_features, batch=1, device=0, quirks=Q_ALL, std_z=1.0, dedupe=True, n_hyp_initial=1000):
+    def __init__(self, cam9, max_features, batch=1, device=0, quirks=Q_ALL, std_z=1.0, dedupe=True, n_hyp_initial=1000, std_a=0.007, std_alpha=0.007):
         self.L = load()
         self.cam = make_camera(cam9)
         self.par = Params()
         self.L.rslam_default_params(C.byref(self.par))
         self.par.quirks = quirks
         self.par.std_z = std_z
+        self.par.std_a = std_a
+        self.par.std_alpha = std_alpha
         self.par.dedupe_hypotheses = int(dedupe)
         self.par.n_hyp_initial = n_hyp_initial
         self.h = C.c_void_p()
@@ -250,6 +255,21 @@ class Filter:
             up = _p(u)
             self._keep.append(u)
         self._ck(self.L.rslam_frame(self.h, ip, rows, cols, stride, int(share), up, n_u01, 1 if predict else 0))
+
+    def set_graph(self, enable):
+        self._ck(self.L.rslam_set_graph(self.h, int(enable)))
+
+    def profile(self, enable):
+        self._ck(self.L.rslam_profile_enable(self.h, int(enable)))
+
+    def profile_read(self):
+        buf = C.create_string_buffer(1 << 16)
+        self._ck(self.L.rslam_profile_read(self.h, buf, len(buf)))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, cnt, ms = line.split()
+            out[name] = (int(cnt), float(ms))
+        return out
 
     def sync(self):
         self._ck(self.L.rslam_sync(self.h))

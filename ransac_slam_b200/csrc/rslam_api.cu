@@ -58,6 +58,20 @@ struct rslam_filter {
     bool upd_ws = false;
     int hN = 0, hn = 0;  // max over filters of the uploaded N / n
     bool descr_dirty = false;
+    // CUDA-graph replay of the per-frame launch sequence
+    bool graph_enabled = true;
+    bool capturing = false;
+    cudaGraphExec_t graph_exec = nullptr;
+    long long graph_key = -1;
+    long long graph_nodes = 0;
+    // optional per-launch event timing (diagnostics only; never enabled inside a timed region)
+    bool prof = false;
+    struct ProfRec {
+        const char* name;
+        cudaEvent_t e0, e1;
+    };
+    std::vector<ProfRec> prof_recs;
+    std::vector<cudaEvent_t> prof_pool;
 };
 
 namespace {
@@ -121,10 +135,32 @@ __global__ void k_set_inputs(DevFilter* Fs, int B, const unsigned char* img, lon
     }
 }
 
-#define LAUNCH(f, kern, grid, block, smem, ...)                   \
-    do {                                                          \
-        kern<<<grid, block, smem, (f)->stream>>>(__VA_ARGS__);    \
-        (f)->launches++;                                          \
+cudaEvent_t prof_event(rslam_filter* f) {
+    if (!f->prof_pool.empty()) {
+        cudaEvent_t e = f->prof_pool.back();
+        f->prof_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+
+#define LAUNCH(f, kern, grid, block, smem, ...)                               \
+    do {                                                                      \
+        const bool prof__ = (f)->prof && !(f)->capturing;                     \
+        cudaEvent_t e0__ = nullptr, e1__ = nullptr;                           \
+        if (prof__) {                                                         \
+            e0__ = prof_event(f);                                             \
+            e1__ = prof_event(f);                                             \
+            cudaEventRecord(e0__, (f)->stream);                               \
+        }                                                                     \
+        kern<<<grid, block, smem, (f)->stream>>>(__VA_ARGS__);                \
+        if (prof__) {                                                         \
+            cudaEventRecord(e1__, (f)->stream);                               \
+            (f)->prof_recs.push_back(rslam_filter::ProfRec{#kern, e0__, e1__}); \
+        }                                                                     \
+        (f)->launches++;                                                      \
     } while (0)
 
 int check_launch() {
@@ -319,6 +355,12 @@ int rslam_destroy(rslam_filter* f) {
     if (!f) return RSLAM_OK;
     cudaSetDevice(f->device);
     if (f->stream) cudaStreamSynchronize(f->stream);
+    if (f->graph_exec) cudaGraphExecDestroy(f->graph_exec);
+    for (auto& r : f->prof_recs) {
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    for (auto e : f->prof_pool) cudaEventDestroy(e);
     for (void* p : f->allocs) cudaFree(p);
     if (f->d_images) cudaFree(f->d_images);
     if (f->d_u01) cudaFree(f->d_u01);
@@ -607,23 +649,158 @@ int rslam_update_hi(rslam_filter* f) {
     return run_update(f, 1);
 }
 
-int rslam_frame(rslam_filter* f, const uint8_t* images, int rows, int cols, int stride, int share, const double* u01, int n_u01, int flags) {
-    if (!f) return fail(RSLAM_ERR_INVALID, "null handle");
-    CK(cudaSetDevice(f->device));
-    int rc;
-    if (images) {
-        if (rows <= 0 || cols <= 0 || stride < cols) return fail(RSLAM_ERR_INVALID, "rslam_frame: bad image geometry");
-        if ((rc = set_images(f, 0, f->B, images, rows, cols, stride, share))) return rc;
+// resolve a host-or-device image batch to a device base pointer (copying host data into the handle's staging buffer)
+static int resolve_images(rslam_filter* f, const uint8_t* images, int rows, int stride, int share, const unsigned char** base, long long* per_filter) {
+    const size_t per = (size_t)rows * stride;
+    *per_filter = share ? 0 : (long long)per;
+    if (is_device_ptr(images)) {
+        *base = images;
+        return 0;
     }
+    const size_t need = per * (share ? 1 : f->B);
+    if (need > f->image_cap) {
+        if (f->d_images) CK(cudaFree(f->d_images));
+        CK(cudaMalloc((void**)&f->d_images, need));
+        f->image_cap = need;
+    }
+    CK(cudaMemcpyAsync(f->d_images, images, need, cudaMemcpyHostToDevice, f->stream));
+    *base = f->d_images;
+    return 0;
+}
+static int resolve_u01(rslam_filter* f, const double* u01, int n_u01, const double** base) {
+    if (is_device_ptr(u01)) {
+        *base = u01;
+        return 0;
+    }
+    const size_t need = (size_t)n_u01 * f->B;
+    if (need > f->u01_cap) {
+        if (f->d_u01) CK(cudaFree(f->d_u01));
+        CK(cudaMalloc((void**)&f->d_u01, need * sizeof(double)));
+        f->u01_cap = need;
+    }
+    CK(cudaMemcpyAsync(f->d_u01, u01, need * sizeof(double), cudaMemcpyHostToDevice, f->stream));
+    *base = f->d_u01;
+    return 0;
+}
+
+// the fixed launch sequence of one frame (src/System.cpp:111-129); inputs already bound by k_set_inputs
+static int run_frame_stages(rslam_filter* f, int flags) {
+    int rc;
     if (flags & 1) {
         if ((rc = rslam_begin_frame(f))) return rc;
         if ((rc = rslam_ekf_prediction(f))) return rc;
     }
     if ((rc = rslam_search_ic_matches(f))) return rc;
-    if ((rc = rslam_ransac_hypotheses(f, u01, n_u01))) return rc;
-    if ((rc = rslam_update_li(f))) return rc;
+    if ((rc = run_ransac_core(f, true))) return rc;
+    if ((rc = run_update(f, 0))) return rc;
     if ((rc = rslam_rescue_hi(f))) return rc;
-    if ((rc = rslam_update_hi(f))) return rc;
+    if ((rc = run_update(f, 1))) return rc;
+    return 0;
+}
+
+int rslam_frame(rslam_filter* f, const uint8_t* images, int rows, int cols, int stride, int share, const double* u01, int n_u01, int flags) {
+    if (!f) return fail(RSLAM_ERR_INVALID, "null handle");
+    if (!u01 || n_u01 <= 0) return fail(RSLAM_ERR_INVALID, "rslam_frame: u01 must hold at least one draw per filter");
+    CK(cudaSetDevice(f->device));
+    int rc;
+    const unsigned char* ibase = nullptr;
+    long long iper = 0;
+    if (images) {
+        if (rows <= 0 || cols <= 0 || stride < cols) return fail(RSLAM_ERR_INVALID, "rslam_frame: bad image geometry");
+        if ((rc = resolve_images(f, images, rows, stride, share, &ibase, &iper))) return rc;
+    }
+    const double* ubase = nullptr;
+    if ((rc = resolve_u01(f, u01, n_u01, &ubase))) return rc;
+    if ((rc = ensure_update_ws(f))) return rc;
+    LAUNCH(f, k_set_inputs, cdiv(f->B, 128), 128, 0, f->dF, f->B, ibase, iper, rows, cols, stride, images ? 1 : 0, ubase, n_u01, 1);
+    for (int b = 0; b < f->B; b++) {
+        if (images) {
+            f->hF[b].image = ibase + iper * b;
+            f->hF[b].img_rows = rows;
+            f->hF[b].img_cols = cols;
+            f->hF[b].img_stride = stride;
+        }
+        f->hF[b].u01 = ubase + (size_t)n_u01 * b;
+        f->hF[b].n_u01 = n_u01;
+    }
+    if (images) f->have_image = true;
+    if (!f->graph_enabled || f->prof) {
+        if ((rc = run_frame_stages(f, flags))) return rc;
+        return check_launch();
+    }
+    const long long key = ((long long)f->hN << 40) ^ ((long long)f->hn << 16) ^ ((long long)f->B << 4) ^ ((flags & 1) << 1) ^ (f->have_image ? 1 : 0);
+    if (!f->graph_exec || key != f->graph_key) {
+        if (f->graph_exec) {
+            cudaGraphExecDestroy(f->graph_exec);
+            f->graph_exec = nullptr;
+        }
+        cudaGraph_t graph = nullptr;
+        const long long before = f->launches;
+        CK(cudaStreamBeginCapture(f->stream, cudaStreamCaptureModeThreadLocal));
+        f->capturing = true;
+        rc = run_frame_stages(f, flags);
+        f->capturing = false;
+        cudaError_t e = cudaStreamEndCapture(f->stream, &graph);
+        if (rc) {
+            if (graph) cudaGraphDestroy(graph);
+            return rc;
+        }
+        if (e != cudaSuccess) return fail(RSLAM_ERR_CUDA, "stream capture failed: %s", cudaGetErrorString(e));
+        f->graph_nodes = f->launches - before;
+        f->launches = before;
+        CK(cudaGraphInstantiate(&f->graph_exec, graph, 0));
+        cudaGraphDestroy(graph);
+        f->graph_key = key;
+    }
+    CK(cudaGraphLaunch(f->graph_exec, f->stream));
+    f->launches += f->graph_nodes;
+    return RSLAM_OK;
+}
+
+int rslam_set_graph(rslam_filter* f, int enable) {
+    if (!f) return fail(RSLAM_ERR_INVALID, "null handle");
+    f->graph_enabled = enable != 0;
+    return RSLAM_OK;
+}
+
+int rslam_profile_enable(rslam_filter* f, int enable) {
+    if (!f) return fail(RSLAM_ERR_INVALID, "null handle");
+    f->prof = enable != 0;
+    return RSLAM_OK;
+}
+
+// text report "kernel count total_ms\n" per kernel name since the last read; waits for the stream
+int rslam_profile_read(rslam_filter* f, char* buf, size_t buflen) {
+    if (!f || !buf || buflen == 0) return fail(RSLAM_ERR_INVALID, "rslam_profile_read: bad arguments");
+    CK(cudaSetDevice(f->device));
+    CK(cudaStreamSynchronize(f->stream));
+    std::vector<const char*> names;
+    std::vector<double> ms;
+    std::vector<long long> cnt;
+    for (auto& r : f->prof_recs) {
+        float t = 0.f;
+        cudaEventElapsedTime(&t, r.e0, r.e1);
+        size_t k = 0;
+        for (; k < names.size(); k++)
+            if (names[k] == r.name || !strcmp(names[k], r.name)) break;
+        if (k == names.size()) {
+            names.push_back(r.name);
+            ms.push_back(0.0);
+            cnt.push_back(0);
+        }
+        ms[k] += t;
+        cnt[k] += 1;
+        f->prof_pool.push_back(r.e0);
+        f->prof_pool.push_back(r.e1);
+    }
+    f->prof_recs.clear();
+    std::string out;
+    char line[256];
+    for (size_t k = 0; k < names.size(); k++) {
+        snprintf(line, sizeof(line), "%s %lld %.6f\n", names[k], cnt[k], ms[k]);
+        out += line;
+    }
+    snprintf(buf, buflen, "%s", out.c_str());
     return RSLAM_OK;
 }
 

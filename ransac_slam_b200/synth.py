@@ -159,14 +159,14 @@ class Scene:
     uv0: np.ndarray  # N x 2 integer pixels in the first image
     templates: np.ndarray  # N x 13 x 13 uint8 appearance
     x0: np.ndarray  # 13 + 6N state right after initialisation (x_k_k of frame 0)
-    P0: np.ndarray  # matching covariance
+    P0: np.ndarray  # matching covariance (None when assemble_P=False; use P_factors + assemble_P_torch)
     std_z: float = 1.0
     seed: int = 1234
     meta: dict = field(default_factory=dict)
 
 
 def make_scene(N=100, seed=1234, cam=None, depth=(2.0, 20.0), margin=45, rho_rel_err=0.3, std_rho=1.0, std_z=1.0, dense_P=True,
-               min_sep=0):
+               min_sep=0, assemble_P=True, motion_scale=1.0):
     """N landmarks in the frustum of the first camera, inverse-depth coded from the first pose."""
     cam = cam or Camera()
     rng = np.random.default_rng(seed)
@@ -183,7 +183,11 @@ def make_scene(N=100, seed=1234, cam=None, depth=(2.0, 20.0), margin=45, rho_rel
         uv[:, 0] = rng.integers(margin, cam.nCols - margin, N)
         uv[:, 1] = rng.integers(margin, cam.nRows - margin, N)
     d = rng.uniform(depth[0], depth[1], N)
-    xv, Pxv = initial_camera_state()
+    # motion_scale < 1: a finer-pixel camera watching a proportionally slower motion (keeps the pixel-domain uncertainties of
+    # the reference configuration when the pixel density is raised, see scaled_camera)
+    xv, Pxv = initial_camera_state(std_v0=0.025 * motion_scale, std_w0=0.025 * motion_scale)
+    std_rho = std_rho * motion_scale
+    rho_rel_err = rho_rel_err * motion_scale
     n = 13 + 6 * N
     x0 = np.zeros(n)
     x0[:13] = xv
@@ -204,6 +208,12 @@ def make_scene(N=100, seed=1234, cam=None, depth=(2.0, 20.0), margin=45, rho_rel
         dy_dxv, dy_dhd = feature_init_jacobians(cam, uv[i], xv)
         J[6 * i:6 * i + 6] = dy_dxv
         blocks[i] = dy_dhd @ Padd @ dy_dhd.T
+    templates = rng.integers(0, 256, size=(N, 13, 13), dtype=np.uint8)
+    if not assemble_P:
+        sc = Scene(cam=cam, N=N, landmarks=landmarks, uv0=uv, templates=templates, x0=x0, P0=None, std_z=std_z, seed=seed)
+        sc.meta["P_factors"] = (J, Pxv, blocks)
+        sc.meta["motion_scale"] = motion_scale
+        return sc
     P0 = np.zeros((n, n), order="F")
     P0[:13, :13] = Pxv
     JP = J @ Pxv
@@ -214,14 +224,15 @@ def make_scene(N=100, seed=1234, cam=None, depth=(2.0, 20.0), margin=45, rho_rel
     for i in range(N):
         s = 13 + 6 * i
         P0[s:s + 6, s:s + 6] = (JP[6 * i:6 * i + 6] @ J[6 * i:6 * i + 6].T) + blocks[i]
-    templates = rng.integers(0, 256, size=(N, 13, 13), dtype=np.uint8)
-    return Scene(cam=cam, N=N, landmarks=landmarks, uv0=uv, templates=templates, x0=x0, P0=P0, std_z=std_z, seed=seed)
+    sc = Scene(cam=cam, N=N, landmarks=landmarks, uv0=uv, templates=templates, x0=x0, P0=P0, std_z=std_z, seed=seed)
+    sc.meta["motion_scale"] = motion_scale
+    return sc
 
 
-def truth_pose(t):
-    """Bounded Lissajous truth trajectory; peak speed ~0.0094 m/frame, peak rate ~0.001 rad/frame."""
-    r = np.array([0.3 * np.sin(2 * np.pi * t / 200.0), 0.15 * np.sin(2 * np.pi * t / 140.0), 0.1 * np.sin(2 * np.pi * t / 260.0)])
-    ang = 0.03 * np.sin(2 * np.pi * t / 180.0)  # rotation about +y
+def truth_pose(t, scale=1.0):
+    """Bounded Lissajous truth trajectory; peak speed ~0.0094 m/frame, peak rate ~0.001 rad/frame (times `scale`)."""
+    r = scale * np.array([0.3 * np.sin(2 * np.pi * t / 200.0), 0.15 * np.sin(2 * np.pi * t / 140.0), 0.1 * np.sin(2 * np.pi * t / 260.0)])
+    ang = scale * 0.03 * np.sin(2 * np.pi * t / 180.0)  # rotation about +y
     q = np.array([np.cos(ang / 2), 0.0, np.sin(ang / 2), 0.0])
     return r, q
 
@@ -259,7 +270,7 @@ def make_sequence(scene, T=20, noise_px=0.5, outlier_frac=0.2, seed=99, n_u01=10
     outl = np.zeros((T, scene.N), dtype=bool)
     poses = np.zeros((T, 7))
     for k in range(T):
-        r, q = truth_pose(t0 + k)
+        r, q = truth_pose(t0 + k, scene.meta.get("motion_scale", 1.0))
         poses[k, :3] = r
         poses[k, 3:] = q
         uv, depth = project(cam, r, q, scene.landmarks)
@@ -313,3 +324,33 @@ def random_spd_state(N, seed=0, cam=None, corr_rank=8, corr_scale=0.05, t0=3, rh
     P = P + U @ U.T
     P = np.asfortranarray(0.5 * (P + P.T))
     return scene, x, P
+
+
+def assemble_P_torch(scene, device, rho_std_rel=None, x=None, lowrank=0, lowrank_scale=0.05, seed=0):
+    """Assemble the initial covariance of a large scene on the GPU with torch (setup plumbing for the N=2000 / 5000-match
+    configs: avoids building and copying multi-GB matrices on the host).  P = [I;J] Pxv [I;J]^T + blockdiag(...) (+ U U^T).
+    With rho_std_rel the inverse-depth variances are replaced by (rho_std_rel * rho)^2 (a converged map)."""
+    import torch
+
+    J, Pxv, blocks = scene.meta["P_factors"]
+    N = scene.N
+    n = 13 + 6 * N
+    Jf = torch.zeros((n, 13), dtype=torch.float64, device=device)
+    Jf[:13] = torch.eye(13, dtype=torch.float64, device=device)
+    Jf[13:] = torch.from_numpy(J).to(device)
+    P = Jf @ torch.from_numpy(Pxv).to(device) @ Jf.T
+    blk = torch.from_numpy(blocks).to(device)
+    idx = 13 + 6 * torch.arange(N, device=device)
+    for a in range(6):
+        for b in range(6):
+            P[idx + a, idx + b] += blk[:, a, b]
+    if rho_std_rel is not None:
+        xr = torch.from_numpy(np.asarray(x if x is not None else scene.x0)).to(device)
+        P[idx + 5, idx + 5] = (rho_std_rel * xr[idx + 5]) ** 2
+    if lowrank > 0:
+        g = torch.Generator(device="cpu").manual_seed(seed)
+        U = torch.randn((n, lowrank), dtype=torch.float64, generator=g).to(device)
+        U = U * (torch.sqrt(torch.clamp(torch.diagonal(P), min=1e-10)) * lowrank_scale)[:, None]
+        P += U @ U.T
+    P = 0.5 * (P + P.T)
+    return P.contiguous()

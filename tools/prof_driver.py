@@ -1,0 +1,64 @@
+#!/usr/bin/env python
+"""Minimal driver for ncu captures: runs a few frames / sweeps of one workload through the C ABI and exits.
+usage: python tools/prof_driver.py {c2|c3|c4|c5} [frames]"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+import bench as B  # noqa: E402
+import bench_extras as X  # noqa: E402
+from ransac_slam_b200 import capi, synth  # noqa: E402
+
+
+def main():
+    wl = sys.argv[1] if len(sys.argv) > 1 else "c2"
+    frames = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+    graph = os.environ.get("RSLAM_GRAPH", "0") == "1"
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    if wl == "c2":
+        scene, seq = B.make_c2(1234, frames)
+        g = B.new_gpu_filter(scene)
+        g.set_graph(graph)
+        for k in range(frames):
+            g.frame(seq.images[k][None], seq.u01[k][None])
+        g.sync()
+        print("c2 done", g.launches, g.download_pose()[:3])
+    elif wl == "c3":
+        N = 2000
+        cam = synth.scaled_camera(4)
+        scene = synth.make_scene(N=N, seed=1234, cam=cam, margin=30, min_sep=18, assemble_P=False, motion_scale=0.25)
+        seq = synth.make_sequence(scene, T=frames, seed=1235, n_u01=8192)
+        P0 = synth.assemble_P_torch(scene, dev)
+        g = capi.Filter(cam.as9(), N, std_a=0.007 * 0.25, std_alpha=0.007 * 0.25)
+        g.set_graph(graph)
+        x0 = torch.from_numpy(scene.x0).to(dev)
+        g.upload_state_device(x0.data_ptr(), P0.data_ptr(), scene.x0.size, scene.x0.size, N)
+        g.upload_patches(scene.templates.astype(np.float64))
+        for k in range(frames):
+            g.frame(seq.images[k][None], seq.u01[k][None])
+        g.sync()
+        print("c3 done", g.launches, B.frame_stats(g))
+    elif wl == "c4":
+        N, H = 5000, 100000
+        scene, x, P, z = X.make_c4(dev, N)
+        hyp = np.random.Generator(np.random.MT19937(99)).integers(0, N, H).astype(np.int32)
+        g = capi.Filter(scene.cam.as9(), N)
+        xd = torch.from_numpy(x).to(dev)
+        g.upload_state_device(xd.data_ptr(), P.data_ptr(), x.size, x.size, N, prior=True)
+        g.set_matches(z, np.ones(N, dtype=np.uint8))
+        g.search_ic_matches()
+        for _ in range(frames):
+            key, _, pairs = g.support_sweep(hyp, want_mask=False)
+        print("c4 done", capi.decode_key(key), pairs)
+    else:
+        raise SystemExit("unknown workload")
+
+
+if __name__ == "__main__":
+    main()
