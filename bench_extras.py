@@ -78,7 +78,8 @@ def bench_c3(args, world, rank, local):
     breakdown = {k: dict(launches=v[0], ms=v[1], share=v[1] / tot) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
     fp64_peak = B.fp64_gemm_peak()
     kk = 2.0 * (st["m_li"] + st["m_hi"])
-    gemm_ms = prof.get("k_gemm_dmma", (0, 0.0))[1]
+    gemm_ms = sum(v[1] for kname, v in prof.items() if kname.startswith("k_gemm_dmma"))
+    syrk_ms = prof.get("k_gemm_dmma/syrk_P", (0, 0.0))[1]
     # fp64 flops issued on DMMA tiles in that frame: SYRK n^2 k (lower triangle) + TRSM trailing n k^2 + Cholesky trailing k^3/3
     k_li, k_hi = 2.0 * st["m_li"], 2.0 * st["m_hi"]
     flops = sum(float(n) * n * k + float(n) * k * k + k**3 / 3.0 for k in (k_li, k_hi))
@@ -87,6 +88,7 @@ def bench_c3(args, world, rank, local):
                roofline=dict(kernel="k_gemm_dmma", bound="tensor", unit="TFLOP/s", achieved=flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms else None,
                              peak=fp64_peak, frac=(flops / (gemm_ms * 1e-3) / 1e12 / fp64_peak) if gemm_ms else None,
                              flops_per_frame=flops, gemm_ms_per_frame=gemm_ms, k_li=k_li, k_hi=k_hi,
+                             syrk=dict(ms=syrk_ms, tflops=(sum(float(n) * n * k for k in (k_li, k_hi)) / (syrk_ms * 1e-3) / 1e12) if syrk_ms else None),
                              note="peak = cuBLAS fp64 GEMM (torch.matmul 6144^3) measured in the same process; flops = n^2 k + n k^2 + k^3/3 per update"),
                cpu_baseline=dict(value=None, note="dense reference path at N=2000 is ~7e12 flop/frame plus up to ~9000 dense RANSAC hypotheses (SURVEY Appendix B): hours per frame on one core, not run"))
     g.close()

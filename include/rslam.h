@@ -132,6 +132,7 @@ int rslam_set_graph(rslam_filter* f, int enable);
  * rslam_profile_read writes "kernel_name launches total_ms\n" lines accumulated since the previous read. */
 int rslam_profile_enable(rslam_filter* f, int enable);
 int rslam_profile_read(rslam_filter* f, char* buf, size_t buflen);
+int rslam_debug_scratch(rslam_filter* f, int b, double* out32);
 /* camera pose of filter b after the frame: x_k_k[0..6] plus the 13-state head (13 doubles) */
 int rslam_download_pose(rslam_filter* f, int b, double* x13);
 

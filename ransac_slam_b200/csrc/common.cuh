@@ -73,6 +73,7 @@ struct DevFilter {
     double* W;         // ldw x kmax : P H^T, then V = W L^-T; row n holds the innovation (then y = L^-1 nu)
     double* Sm;        // lds x kmax : innovation covariance, then its Cholesky factor (lower)
     double* Jn;        // 16 + scratch
+    double* Linv;      // [ceil(kmax/64)][64 x 64] inverses of the Cholesky factor's diagonal blocks (column-major)
 };
 
 enum CtlSlot {

@@ -728,80 +728,105 @@ __global__ void __launch_bounds__(256) k_ransac_support(DevFilter* Fs, CamDev ca
 }
 
 // c.4 replay of the reference's sequential, adaptive control flow (src/Tracking.cpp:403-415, 506-537) over the uniform draws,
-//     then write-back of the winner's low_innovation_inlier flags.  One CTA per filter.
+//     then write-back of the winner's low_innovation_inlier flags.  One CTA per filter; warp 0 walks the draws 32 at a time:
+//     a chunk without a new record (support > best so far) only has to be checked against the current budget n_hyp, so the
+//     scalar loop body runs only for the (rare) record-setting hypotheses.
 __global__ void __launch_bounds__(256) k_ransac_select(DevFilter* Fs, ParDev par) {
     DevFilter& F = Fs[blockIdx.y];
-    __shared__ int s_sup[1024];
-    __shared__ int s_state[8];  // 0 done, 1 max, 2 n_hyp, 3 winner i, 4 winner t, 5 hyp_run, 6 status
+    __shared__ int s_state[8];  // 1 max, 2 n_hyp, 3 winner i, 5 hyp_run, 6 status
+    __shared__ int s_sup[2048];
     const int nIC = F.ctl[CTL_NIC];
-    if (threadIdx.x == 0) {
-        s_state[0] = 0;
-        s_state[1] = 0;
-        s_state[2] = par.n_hyp0;
-        s_state[3] = -1;
-        s_state[4] = -1;
-        s_state[5] = 0;
-        s_state[6] = 0;
-        if (nIC == 0) {
-            s_state[0] = 1;
-            s_state[6] = 1;  // Q9
+    const int n_u01 = F.n_u01;
+    const double* u01 = F.u01;
+    const int* support = F.support;
+    // the first 2048 draws are resolved to supports by the whole CTA up front (parallel, latency paid once)
+    for (int i = threadIdx.x; i < 2048; i += blockDim.x) {
+        int s = -1;
+        if (i < n_u01 && nIC > 0) {
+            const int pos = (int)floor(u01[i] * (double)nIC);
+            s = support[pos < nIC ? pos : nIC - 1];
         }
+        s_sup[i] = s;
     }
     __syncthreads();
-    for (int base = 0; !s_state[0]; base += 1024) {
-        for (int e = threadIdx.x; e < 1024; e += blockDim.x) {
-            const int i = base + e;
-            int s = -1;
-            if (i < F.n_u01) {
-                const int pos = (int)floor(F.u01[i] * (double)nIC);
-                s = F.support[pos < nIC ? pos : nIC - 1];
-            }
-            s_sup[e] = s;
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        int mx = 0, n_hyp = par.n_hyp0, win = -1, run = 0, status = 0;
+        bool done = false;
+        if (nIC == 0) {
+            done = true;
+            status = 1;  // Q9
         }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            int mx = s_state[1], n_hyp = s_state[2], win = s_state[3], run = s_state[5], status = 0, done = 0;
-            for (int e = 0; e < 1024; e++) {
-                const int i = base + e;
-                if (!(i < n_hyp)) {
-                    done = 1;
+        for (int base = 0; !done; base += 32) {
+            const int i = base + lane;
+            int s = -1;
+            if (i < 2048) {
+                s = s_sup[i];
+            } else if (i < n_u01) {
+                const int pos = (int)floor(u01[i] * (double)nIC);
+                s = support[pos < nIC ? pos : nIC - 1];
+            }
+            // lanes that would stop the loop if no record happens before them
+            const bool over = !(i < n_hyp);           // for-condition fails at i
+            const bool exhausted = (i < n_hyp) && s < 0;  // ran out of draws
+            const unsigned m_rec = __ballot_sync(0xffffffffu, s > mx);
+            const unsigned m_stop = __ballot_sync(0xffffffffu, over || exhausted);
+            const int first_rec = m_rec ? __ffs(m_rec) - 1 : 32;
+            const int first_stop = m_stop ? __ffs(m_stop) - 1 : 32;
+            if (first_rec == 32 && first_stop == 32) {
+                run = base + 32;  // whole chunk evaluated, nothing changed
+                continue;
+            }
+            if (first_stop <= first_rec) {  // loop ends before any new record in this chunk
+                const bool ex = __shfl_sync(0xffffffffu, (int)exhausted, first_stop) != 0;
+                run = base + first_stop;
+                if (ex) status = 3;
+                done = true;
+                continue;
+            }
+            // a record inside the chunk: replay the chunk sequentially (all lanes run the same scalar code on shuffled values)
+            for (int e = 0; e < 32 && !done; e++) {
+                const int ie = base + e;
+                const int se = __shfl_sync(0xffffffffu, s, e);
+                if (!(ie < n_hyp)) {
+                    done = true;
                     break;
                 }
-                const int s = s_sup[e];
-                if (s < 0) {
-                    done = 1;
-                    status = 3;  // uniform draws exhausted
+                if (se < 0) {
+                    done = true;
+                    status = 3;
                     break;
                 }
-                run = i + 1;
-                if (s > mx) {
-                    mx = s;
-                    win = i;
-                    const double epsilon = 1 - ((double)s / (double)nIC);
+                run = ie + 1;
+                if (se > mx) {
+                    mx = se;
+                    win = ie;
+                    const double epsilon = 1 - ((double)se / (double)nIC);
                     n_hyp = (int)ceil(log(1 - par.p_free) / log(1 - (1 - epsilon)));
                     if (n_hyp == 0) {
-                        done = 1;
+                        done = true;
                         break;
                     }
                 }
-                if (i > n_hyp) {
-                    done = 1;
+                if (ie > n_hyp) {
+                    done = true;
                     break;
                 }
             }
-            s_state[0] = done;
+        }
+        if (lane == 0) {
             s_state[1] = mx;
             s_state[2] = n_hyp;
             s_state[3] = win;
             s_state[5] = run;
-            if (status) s_state[6] = status;
+            s_state[6] = status;
         }
-        __syncthreads();
     }
+    __syncthreads();
     const int win = s_state[3];
     int wt = -1;
     if (win >= 0) {
-        const int pos = (int)floor(F.u01[win] * (double)nIC);
+        const int pos = (int)floor(u01[win] * (double)nIC);
         wt = pos < nIC ? pos : nIC - 1;
         const int m = F.ctl[CTL_MID];
         for (int jj = threadIdx.x; jj < m; jj += blockDim.x) {

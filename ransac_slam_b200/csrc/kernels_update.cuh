@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(256) k_upd_gather(DevFilter* Fs, int which) {
 }
 
 // ---- U2: W = P H^T.  Thread per state row r, CTA handles a chunk of measurements. ---------------------------------------
-constexpr int kWChunk = 32;  // measurements (features) per CTA in y
+constexpr int kWChunk = 8;   // measurements (features) per CTA in y
 __global__ void __launch_bounds__(256) k_upd_W(DevFilter* Fs) {
     DevFilter& F = Fs[blockIdx.z];
     const int m = F.ctl[CTL_M];
@@ -145,38 +145,170 @@ __global__ void __launch_bounds__(256) k_upd_S(DevFilter* Fs) {
     S[(2 * ti + 1) + (size_t)(2 * tj + 1) * ld] = s11;
 }
 
-// ---- shared helper: solve X * L^T = A for one row held in registers (forward substitution), L (NB x NB, lower) in smem ----
-// sL is padded to identity beyond the active width.
-__device__ __forceinline__ void row_solve_LT(double* xr, const double (*sL)[kNB + 1]) {
-#pragma unroll
-    for (int c = 0; c < kNB; c++) {
-        double s = xr[c];
-#pragma unroll
-        for (int t = 0; t < c; t++) s -= xr[t] * sL[c][t];
-        xr[c] = s / sL[c][c];
-    }
-}
+// ---- shared helpers for the 64-wide panels (all are CTA-collective: 256 threads, every thread must call them) -------------
+// On this part fp64 sqrt / divide / dependent FMA chains cost hundreds of cycles, so the panel code is organised to keep the
+// per-column serial chain minimal (one rsqrt + one multiply + one barrier) and to do everything else as wide, independent work.
 
-// factor the NB x NB diagonal block held in smem (unblocked right-looking Cholesky, all threads of the CTA)
-__device__ __forceinline__ void smem_potrf(double (*sL)[kNB + 1], int w) {
-    for (int j = 0; j < w; j++) {
+// Right-looking Cholesky of the NB x NB block in smem (lower part valid, identity padding beyond w).  16 x 16 thread grid, thread
+// (ty,tx) owns elements (i,c) with i = ty (mod 16), c = tx (mod 16).  Per column j: every thread recomputes rd = rsqrt(a_jj)
+// itself (no barrier to broadcast it) and applies the rank-1 update straight from the UNSCALED column j,
+//     a_ic -= a_ij * a_cj * rd^2 ,
+// while column j-1 is scaled to l = a * rd_{j-1} by its owners (nobody reads it any more).  One barrier per column.
+// (A register-resident variant was measured slower: the loop is instruction-issue bound, not shared-memory bound.)
+__device__ __forceinline__ void smem_potrf(double (*sL)[kNB + 1], double* sRd, int w) {
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    if (threadIdx.x < kNB) sRd[threadIdx.x] = 1.0;
+    double rd_prev = 1.0;
+    for (int j = 0; j <= w; j++) {
         __syncthreads();
-        const double d = sqrt(sL[j][j]);
-        __syncthreads();
-        for (int i = j + threadIdx.x; i < w; i += blockDim.x) sL[i][j] = (i == j) ? d : sL[i][j] / d;
-        __syncthreads();
-        const int rem = w - j - 1;
-        for (int e = threadIdx.x; e < rem * rem; e += blockDim.x) {
-            const int i = j + 1 + e / rem, c = j + 1 + e % rem;
-            if (i >= c) sL[i][c] -= sL[i][j] * sL[c][j];
+        if (j > 0 && tx == ((j - 1) & 15)) {  // scale the previous column (rows >= j-1)
+#pragma unroll
+            for (int a = 0; a < 4; a++) {
+                const int i = ty + 16 * a;
+                if (i >= j - 1 && i < w) sL[i][j - 1] *= rd_prev;
+            }
+            if (ty == 0) sRd[j - 1] = rd_prev;
         }
+        if (j == w) break;
+        const double rd = rsqrt(sL[j][j]);
+        const double r2 = rd * rd;
+        // rows i = ty + 16a > j and columns c = tx + 16b in (j, i]: skip whole a / b slices that cannot be active
+        const int a0 = (j >= ty) ? ((j - ty) >> 4) + 1 : 0;   // first a with i > j
+        if (a0 < 4) {
+            double lc[4];
+#pragma unroll
+            for (int bq = 0; bq < 4; bq++) lc[bq] = sL[tx + 16 * bq][j];
+#pragma unroll
+            for (int a = 0; a < 4; a++) {
+                const int i = ty + 16 * a;
+                if (a < a0 || i >= w) continue;
+                const double lia = sL[i][j] * r2;
+#pragma unroll
+                for (int bq = 0; bq < 4; bq++) {
+                    const int c = tx + 16 * bq;
+                    if (c > j && c <= i) sL[i][c] -= lia * lc[bq];
+                }
+            }
+        }
+        rd_prev = rd;
     }
     __syncthreads();
 }
 
-// ---- U4a: Cholesky panel at block column `step`: factor the diagonal block (every CTA redundantly, CTA 0 stores it) and
-//           solve the sub-diagonal blocks  L[rb, step] = S[rb, step] * L_jj^-T.  grid.x = row blocks below (and incl.) diagonal
-__global__ void __launch_bounds__(128) k_chol_panel(DevFilter* Fs, int step) {
+// inverse of the lower-triangular block in sL (identity padded) -> sX (full 64 x 64, zeros above the diagonal), recursively:
+// four 16 x 16 diagonal inverses by forward substitution (short chains), then inv([[A,0],[B,C]]) = [[iA,0],[-iC B iA, iC]] twice,
+// the products as wide independent dot products.  sT: 32 x 33 scratch.
+__device__ __forceinline__ void smem_trinv(const double (*sL)[kNB + 1], const double* sRd, double (*sX)[kNB + 1], double (*sT)[33]) {
+    const int tid = threadIdx.x;
+    for (int e = tid; e < kNB * kNB; e += blockDim.x) {
+        const int i = e / kNB, c = e % kNB;
+        if (c > i) sX[i][c] = 0.0;
+    }
+    if (tid < kNB) {  // level 0: column c of diagonal block d
+        const int d0 = (tid >> 4) * 16, c = tid & 15;
+        for (int i = 0; i < c; i++) sX[d0 + i][d0 + c] = 0.0;
+        sX[d0 + c][d0 + c] = sRd[d0 + c];
+        for (int i = c + 1; i < 16; i++) {
+            double s0 = 0.0, s1 = 0.0;
+            int t = c;
+            for (; t + 1 < i; t += 2) {
+                s0 += sL[d0 + i][d0 + t] * sX[d0 + t][d0 + c];
+                s1 += sL[d0 + i][d0 + t + 1] * sX[d0 + t + 1][d0 + c];
+            }
+            if (t < i) s0 += sL[d0 + i][d0 + t] * sX[d0 + t][d0 + c];
+            sX[d0 + i][d0 + c] = -(s0 + s1) * sRd[d0 + i];
+        }
+    }
+    __syncthreads();
+    // level 1: blocks (16..31, 0..15) and (48..63, 32..47);  T = B * iA ,  X = -iC * T
+    for (int e = tid; e < 512; e += blockDim.x) {
+        const int blk = e >> 8, i = (e >> 4) & 15, c = e & 15;
+        const int r0 = blk * 32 + 16, c0 = blk * 32;
+        double s = 0.0;
+        for (int t = c; t < 16; t++) s += sL[r0 + i][c0 + t] * sX[c0 + t][c0 + c];
+        sT[blk * 16 + i][c] = s;
+    }
+    __syncthreads();
+    for (int e = tid; e < 512; e += blockDim.x) {
+        const int blk = e >> 8, i = (e >> 4) & 15, c = e & 15;
+        const int r0 = blk * 32 + 16, c0 = blk * 32;
+        double s = 0.0;
+        for (int t = 0; t <= i; t++) s += sX[r0 + i][r0 + t] * sT[blk * 16 + t][c];
+        sX[r0 + i][c0 + c] = -s;
+    }
+    __syncthreads();
+    // level 2: block (32..63, 0..31)
+    for (int e = tid; e < 1024; e += blockDim.x) {
+        const int i = e >> 5, c = e & 31;
+        double s0 = 0.0, s1 = 0.0;
+        int t = c;
+        for (; t + 1 < 32; t += 2) {
+            s0 += sL[32 + i][t] * sX[t][c];
+            s1 += sL[32 + i][t + 1] * sX[t + 1][c];
+        }
+        if (t < 32) s0 += sL[32 + i][t] * sX[t][c];
+        sT[i][c] = s0 + s1;
+    }
+    __syncthreads();
+    for (int e = tid; e < 1024; e += blockDim.x) {
+        const int i = e >> 5, c = e & 31;
+        double s0 = 0.0, s1 = 0.0;
+        int t = 0;
+        for (; t + 1 <= i; t += 2) {
+            s0 += sX[32 + i][32 + t] * sT[t][c];
+            s1 += sX[32 + i][32 + t + 1] * sT[t + 1][c];
+        }
+        if (t <= i) s0 += sX[32 + i][32 + t] * sT[t][c];
+        sX[32 + i][c] = -(s0 + s1);
+    }
+    __syncthreads();
+}
+
+// rows [0, nr) of sPan (nr x 64, row stride NB+1) <- sPan * inv(L)^T with inv(L) = sX:  out[r][c] = sum_{t<=c} A[r][t] iL[c][t].
+// 4 threads per row (16 output columns each) accumulate into registers, then store after a barrier (in-place safe).
+__device__ __forceinline__ void smem_panel_mul(double (*sPan)[kNB + 1], const double (*sX)[kNB + 1], int nr) {
+    for (int base = 0; base < nr; base += 64) {  // uniform trip count across the CTA
+        const int r = base + (threadIdx.x & 63), cg = (threadIdx.x >> 6) * 16;
+        double o[16];
+#pragma unroll
+        for (int q = 0; q < 16; q++) o[q] = 0.0;
+        if (r < nr) {
+#pragma unroll
+            for (int q = 0; q < 16; q++) {
+                const int c = cg + q;
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+                int t = 0;
+                for (; t + 3 <= c; t += 4) {
+                    s0 += sPan[r][t] * sX[c][t];
+                    s1 += sPan[r][t + 1] * sX[c][t + 1];
+                    s2 += sPan[r][t + 2] * sX[c][t + 2];
+                    s3 += sPan[r][t + 3] * sX[c][t + 3];
+                }
+                for (; t <= c; t++) s0 += sPan[r][t] * sX[c][t];
+                o[q] = (s0 + s1) + (s2 + s3);
+            }
+        }
+        __syncthreads();
+        if (r < nr) {
+#pragma unroll
+            for (int q = 0; q < 16; q++) sPan[r][cg + q] = o[q];
+        }
+        __syncthreads();
+    }
+}
+
+__device__ __forceinline__ void store_linv(const double (*sX)[kNB + 1], double* out) {  // 64 x 64 column-major
+    for (int e = threadIdx.x; e < kNB * kNB; e += blockDim.x) out[e] = sX[e % kNB][e / kNB];
+}
+
+// smem carve-up shared by the panel kernels: sL[64][65], sX[64][65], sT[32][33], sRd[64], then (chol_small only) sPan[192][65]
+constexpr int kPanelDoubles = 2 * kNB * (kNB + 1) + 32 * 33 + kNB;  // sL, sX, sT, sRd
+constexpr int kPanelSmemBytes = (kPanelDoubles + kNB * (kNB + 1)) * (int)sizeof(double);  // + one 64-row panel
+
+// ---- U4a: Cholesky panel at block column `step` (multi-launch path, k > 256): every CTA factors the diagonal block and inverts
+//           it (redundantly: ~10 us, cheaper than a dependent launch); CTA 0 stores L_jj and inv(L_jj) (the TRSM needs it);
+//           CTA b > 0 forms row block b of the panel:  L[rb,step] = S[rb,step] * inv(L_jj)^T
+__global__ void __launch_bounds__(256) k_chol_panel(DevFilter* Fs, int step) {
     DevFilter& F = Fs[blockIdx.y];
     const int kk = F.ctl[CTL_K];
     const int j0 = kNB * step;
@@ -184,73 +316,307 @@ __global__ void __launch_bounds__(128) k_chol_panel(DevFilter* Fs, int step) {
     const int r0 = j0 + kNB * blockIdx.x;
     if (r0 >= kk) return;
     const int w = min(kNB, kk - j0);
-    __shared__ double sL[kNB][kNB + 1];
+    extern __shared__ __align__(16) double psm[];
+    double(*sL)[kNB + 1] = reinterpret_cast<double(*)[kNB + 1]>(psm);
+    double(*sX)[kNB + 1] = reinterpret_cast<double(*)[kNB + 1]>(psm + kNB * (kNB + 1));
+    double(*sT)[33] = reinterpret_cast<double(*)[33]>(psm + 2 * kNB * (kNB + 1));
+    double* sRd = psm + 2 * kNB * (kNB + 1) + 32 * 33;
+    double(*sPan)[kNB + 1] = reinterpret_cast<double(*)[kNB + 1]>(psm + kPanelDoubles);
     double* S = F.Sm;
     const int ld = F.lds;
+    const int nr = blockIdx.x == 0 ? 0 : min(kNB, kk - r0);
     for (int e = threadIdx.x; e < kNB * kNB; e += blockDim.x) {
         const int i = e % kNB, c = e / kNB;
         double v = (i == c) ? 1.0 : 0.0;
         if (i < w && c < w && i >= c) v = S[(j0 + i) + (size_t)(j0 + c) * ld];
         sL[i][c] = v;
+        if (nr) sPan[i][c] = (i < nr && c < w) ? S[(r0 + i) + (size_t)(j0 + c) * ld] : 0.0;
     }
-    smem_potrf(sL, w);
+    smem_potrf(sL, sRd, w);
+    smem_trinv(sL, sRd, sX, sT);
     if (blockIdx.x == 0) {
         for (int e = threadIdx.x; e < kNB * kNB; e += blockDim.x) {
             const int i = e % kNB, c = e / kNB;
             if (i < w && c < w) S[(j0 + i) + (size_t)(j0 + c) * ld] = (i >= c) ? sL[i][c] : 0.0;
         }
+        store_linv(sX, F.Linv + (size_t)step * kNB * kNB);
         return;
     }
-    const int r = r0 + threadIdx.x;
-    if (threadIdx.x >= kNB || r >= kk) return;
-    double xr[kNB];
-#pragma unroll
-    for (int c = 0; c < kNB; c++) xr[c] = (c < w) ? S[r + (size_t)(j0 + c) * ld] : 0.0;
-    row_solve_LT(xr, sL);
-#pragma unroll
-    for (int c = 0; c < kNB; c++)
-        if (c < w) S[r + (size_t)(j0 + c) * ld] = xr[c];
-}
-
-// ---- U5a: TRSM panel at block column `step`:  V[:, step] = W[:, step] * L_jj^-T  for the n+1 rows of W --------------------
-__global__ void __launch_bounds__(128) k_trsm_panel(DevFilter* Fs, int step) {
-    DevFilter& F = Fs[blockIdx.y];
-    const int kk = F.ctl[CTL_K];
-    const int j0 = kNB * step;
-    if (j0 >= kk) return;
-    const int w = min(kNB, kk - j0);
-    __shared__ double sL[kNB][kNB + 1];
-    const double* S = F.Sm;
-    const int ld = F.lds;
+    smem_panel_mul(sPan, sX, nr);
     for (int e = threadIdx.x; e < kNB * kNB; e += blockDim.x) {
         const int i = e % kNB, c = e / kNB;
-        double v = (i == c) ? 1.0 : 0.0;
-        if (i < w && c < w && i >= c) v = S[(j0 + i) + (size_t)(j0 + c) * ld];
-        sL[i][c] = v;
+        if (i < nr && c < w) S[(r0 + i) + (size_t)(j0 + c) * ld] = sPan[i][c];
     }
-    __syncthreads();
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r > F.n) return;  // rows 0..n (row n = innovation)
-    double* Wp = F.W;
-    const int ldw = F.ldw;
-    double xr[kNB];
+}
+
+// ---- U4s: whole Cholesky (+ inverses of the diagonal blocks) in ONE CTA for small systems (k <= 256): the launch-latency
+//           path of the 100-feature configuration.
+constexpr int kCholSmallMaxK = 256;
+constexpr int kCholSmallSmemBytes = (kPanelDoubles + (kCholSmallMaxK - kNB) * (kNB + 1)) * (int)sizeof(double);
+__global__ void __launch_bounds__(256) k_chol_small(DevFilter* Fs) {
+    DevFilter& F = Fs[blockIdx.y];
+    const int kk = F.ctl[CTL_K];
+    if (kk <= 0) return;
+    extern __shared__ __align__(16) double psm[];
+    double(*sL)[kNB + 1] = reinterpret_cast<double(*)[kNB + 1]>(psm);
+    double(*sX)[kNB + 1] = reinterpret_cast<double(*)[kNB + 1]>(psm + kNB * (kNB + 1));
+    double(*sT)[33] = reinterpret_cast<double(*)[33]>(psm + 2 * kNB * (kNB + 1));
+    double* sRd = psm + 2 * kNB * (kNB + 1) + 32 * 33;
+    double(*sPan)[kNB + 1] = reinterpret_cast<double(*)[kNB + 1]>(psm + kPanelDoubles);
+    double* S = F.Sm;
+    const int ld = F.lds;
+#ifdef RSLAM_PHASE_CLOCKS
+    long long tc[6] = {0, 0, 0, 0, 0, 0};
+#define PH(i) do { __syncthreads(); const long long now__ = clock64(); tc[i] += now__ - tprev; tprev = now__; } while (0)
+    long long tprev = clock64();
+#else
+#define PH(i)
+#endif
+    for (int j0 = 0; j0 < kk; j0 += kNB) {
+        const int w = min(kNB, kk - j0);
+        const int rem = max(0, kk - (j0 + kNB));
+        for (int e = threadIdx.x; e < kNB * kNB; e += blockDim.x) {
+            const int i = e % kNB, c = e / kNB;
+            double v = (i == c) ? 1.0 : 0.0;
+            if (i < w && c < w && i >= c) v = S[(j0 + i) + (size_t)(j0 + c) * ld];
+            sL[i][c] = v;
+        }
+        for (int e = threadIdx.x; e < rem * kNB; e += blockDim.x) {
+            const int i = e % rem, c = e / rem;
+            sPan[i][c] = S[(j0 + kNB + i) + (size_t)(j0 + c) * ld];
+        }
+        PH(0);
+        smem_potrf(sL, sRd, w);
+        PH(1);
+        smem_trinv(sL, sRd, sX, sT);
+        for (int e = threadIdx.x; e < kNB * kNB; e += blockDim.x) {
+            const int i = e % kNB, c = e / kNB;
+            if (i < w && c < w) S[(j0 + i) + (size_t)(j0 + c) * ld] = (i >= c) ? sL[i][c] : 0.0;
+        }
+        store_linv(sX, F.Linv + (size_t)(j0 / kNB) * kNB * kNB);
+        PH(2);
+        if (rem <= 0) break;
+        smem_panel_mul(sPan, sX, rem);
+        PH(3);
+        for (int e = threadIdx.x; e < rem * kNB; e += blockDim.x) {
+            const int i = e % rem, c = e / rem;
+            S[(j0 + kNB + i) + (size_t)(j0 + c) * ld] = sPan[i][c];
+        }
+        PH(4);
+        // trailing update (lower triangle): lanes run down a column (coalesced), warps over columns
+        const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+        for (int bcol = wrp; bcol < rem; bcol += 8) {
+            for (int arow = bcol + lane; arow < rem; arow += 32) {
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll 4
+                for (int c = 0; c < kNB; c += 4) {
+                    s0 += sPan[arow][c] * sPan[bcol][c];
+                    s1 += sPan[arow][c + 1] * sPan[bcol][c + 1];
+                    s2 += sPan[arow][c + 2] * sPan[bcol][c + 2];
+                    s3 += sPan[arow][c + 3] * sPan[bcol][c + 3];
+                }
+                S[(j0 + kNB + arow) + (size_t)(j0 + kNB + bcol) * ld] -= (s0 + s1) + (s2 + s3);
+            }
+        }
+        __syncthreads();
+        PH(5);
+    }
+#ifdef RSLAM_PHASE_CLOCKS
+    if (threadIdx.x == 0)
+        for (int i = 0; i < 6; i++) F.Jn[16 + i] = (double)tc[i];
+#endif
+#undef PH
+}
+
+// ---- async-copy / DMMA primitives ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    const int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+__device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// ---- U5: TRSM  V = W L^-T  for all n+1 rows of W (row n: the innovation, which becomes y = L^-1 nu), ONE launch ---------------
+// Left-looking over 64-wide column blocks, a CTA owns R rows for the whole solve (no inter-CTA dependency):
+//     V_j = ( W_j - sum_{i<j} V_i L_ji^T ) * inv(L_jj)^T
+// Both products run on fp64 tensor cores (DMMA m8n8k4); the K = 64 j accumulation streams V (own rows, written earlier by this
+// CTA) and L through a 3-stage cp.async pipeline; the diagonal step multiplies by the explicit inverse of the 64 x 64 diagonal
+// block produced by the Cholesky kernels, so there is no serial substitution on the n-row side.
+constexpr int GBK_T = 16, GSTAGES_T = 3;
+template <int R, int WM>
+struct TrsmCfg {
+    static constexpr int kThreads = WM * 2 * 32;
+    static constexpr int kMT = R / (8 * WM);       // m8 tiles per warp
+    static constexpr int kLdA = R + 4;             // doubles per k-row of the A / T staging (== 8 mod 32 words -> conflict free)
+    static constexpr int kLdB = kNB + 4;
+    static constexpr int kSmemBytes = (GSTAGES_T * GBK_T * (kLdA + kLdB) + kNB * kLdA + kNB * kLdB) * (int)sizeof(double);
+};
+
+template <int R, int WM>
+__global__ void __launch_bounds__(WM * 64) k_trsm_ll(DevFilter* Fs) {
+    using Cfg = TrsmCfg<R, WM>;
+    constexpr int MT = Cfg::kMT, LDA = Cfg::kLdA, LDB = Cfg::kLdB, NT = 4;
+    static_assert(R % (8 * WM) == 0 && (LDA % 2) == 0, "tile shape");
+    DevFilter& F = Fs[blockIdx.y];
+    const int kk = F.ctl[CTL_K];
+    if (kk <= 0) return;
+    const int M = F.n + 1;
+    const int r0 = blockIdx.x * R;
+    if (r0 >= M) return;
+    extern __shared__ __align__(16) double tsm[];
+    double* As = tsm;                                   // [stage][GBK][LDA]
+    double* Bs = As + GSTAGES_T * GBK_T * LDA;          // [stage][GBK][LDB]
+    double* Ts = Bs + GSTAGES_T * GBK_T * LDB;          // [64][LDA]   T = W_j - acc   (k-major, like an A tile)
+    double* Ls = Ts + kNB * LDA;                        // [64][LDB]   Ls[k][n] = inv(L_jj)[n][k]
+    double* W = F.W;
+    const double* Sm = F.Sm;
+    const int ldw = F.ldw, lds = F.lds;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm0 = (warp % WM) * (MT * 8), wn0 = (warp / WM) * 32;
+    const int nb = (kk + kNB - 1) / kNB;
+    constexpr int A_CHUNKS = GBK_T * (R / 2), B_CHUNKS = GBK_T * (kNB / 2);
+
+    for (int j = 0; j < nb; j++) {
+        const int c0 = j * kNB;
+        const int w = min(kNB, kk - c0);
+        // inverse of the diagonal block -> Ls (async, overlaps the accumulation)
+        {
+            const double* Li = F.Linv + (size_t)j * kNB * kNB;
+            for (int ch = tid; ch < kNB * (kNB / 2); ch += Cfg::kThreads) {
+                const int kc = ch / (kNB / 2), r2 = ch % (kNB / 2);
+                cp_async16(&Ls[kc * LDB + 2 * r2], Li + 2 * r2 + (size_t)kc * kNB, true);
+            }
+            cp_async_commit();
+        }
+        double acc[MT][NT][2];
 #pragma unroll
-    for (int c = 0; c < kNB; c++) xr[c] = (c < w) ? Wp[r + (size_t)(j0 + c) * ldw] : 0.0;
-    row_solve_LT(xr, sL);
+        for (int a = 0; a < MT; a++)
 #pragma unroll
-    for (int c = 0; c < kNB; c++)
-        if (c < w) Wp[r + (size_t)(j0 + c) * ldw] = xr[c];
+            for (int b = 0; b < NT; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+        const int nkt = c0 / GBK_T;  // K = 64 j
+        auto load_stage = [&](int stage, int kt) {
+            const int k0 = kt * GBK_T;
+            for (int ch = tid; ch < A_CHUNKS; ch += Cfg::kThreads) {
+                const int kc = ch / (R / 2), r2 = ch % (R / 2);
+                const int row = r0 + 2 * r2;
+                const bool v = row < M;
+                cp_async16(&As[(stage * GBK_T + kc) * LDA + 2 * r2], v ? (W + row + (size_t)(k0 + kc) * ldw) : W, v);
+            }
+            for (int ch = tid; ch < B_CHUNKS; ch += Cfg::kThreads) {
+                const int kc = ch / (kNB / 2), r2 = ch % (kNB / 2);
+                const int row = c0 + 2 * r2;
+                const bool v = row < kk;
+                cp_async16(&Bs[(stage * GBK_T + kc) * LDB + 2 * r2], v ? (Sm + row + (size_t)(k0 + kc) * lds) : Sm, v);
+            }
+        };
+#pragma unroll
+        for (int s = 0; s < GSTAGES_T - 1; s++) {
+            if (s < nkt) load_stage(s, s);
+            cp_async_commit();
+        }
+        for (int kt = 0; kt < nkt; kt++) {
+            cp_async_wait<GSTAGES_T - 2>();
+            __syncthreads();
+            {
+                const int nk = kt + GSTAGES_T - 1;
+                if (nk < nkt) load_stage(nk % GSTAGES_T, nk);
+                cp_async_commit();
+            }
+            const double* as = As + (kt % GSTAGES_T) * GBK_T * LDA;
+            const double* bs = Bs + (kt % GSTAGES_T) * GBK_T * LDB;
+#pragma unroll
+            for (int ks = 0; ks < GBK_T / 4; ks++) {
+                const int krow = ks * 4 + (lane & 3);
+                double af[MT], bf[NT];
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++) af[mt] = as[krow * LDA + wm0 + mt * 8 + (lane >> 2)];
+#pragma unroll
+                for (int nt = 0; nt < NT; nt++) bf[nt] = bs[krow * LDB + wn0 + nt * 8 + (lane >> 2)];
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+                    for (int nt = 0; nt < NT; nt++) dmma8x8x4(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+            }
+        }
+        cp_async_wait<0>();
+        __syncthreads();
+        // T = W_j - acc  -> Ts[col][row]
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++) {
+            const int rl = wm0 + mt * 8 + (lane >> 2);
+            const int row = r0 + rl;
+#pragma unroll
+            for (int nt = 0; nt < NT; nt++) {
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const int cl = wn0 + nt * 8 + 2 * (lane & 3) + e;
+                    double v = 0.0;
+                    if (row < M && cl < w) v = W[row + (size_t)(c0 + cl) * ldw] - acc[mt][nt][e];
+                    Ts[cl * LDA + rl] = v;
+                }
+            }
+        }
+        __syncthreads();
+        // V_j = T * inv(L_jj)^T
+#pragma unroll
+        for (int a = 0; a < MT; a++)
+#pragma unroll
+            for (int b = 0; b < NT; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+#pragma unroll 4
+        for (int ks = 0; ks < kNB / 4; ks++) {
+            const int krow = ks * 4 + (lane & 3);
+            double af[MT], bf[NT];
+#pragma unroll
+            for (int mt = 0; mt < MT; mt++) af[mt] = Ts[krow * LDA + wm0 + mt * 8 + (lane >> 2)];
+#pragma unroll
+            for (int nt = 0; nt < NT; nt++) bf[nt] = Ls[krow * LDB + wn0 + nt * 8 + (lane >> 2)];
+#pragma unroll
+            for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+                for (int nt = 0; nt < NT; nt++) dmma8x8x4(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+        }
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++) {
+            const int row = r0 + wm0 + mt * 8 + (lane >> 2);
+#pragma unroll
+            for (int nt = 0; nt < NT; nt++) {
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const int cl = wn0 + nt * 8 + 2 * (lane & 3) + e;
+                    if (row < M && cl < w) W[row + (size_t)(c0 + cl) * ldw] = acc[mt][nt][e];
+                }
+            }
+        }
+        __threadfence();  // the V_j stores must have reached L2 before the next block's cp.async (L2 path) reads them
+        __syncthreads();  // V_j visible to this CTA's next accumulation; Ts / Ls free for reuse
+    }
 }
 
 // ---- fp64 tensor-core GEMM:  C -= A * B^T  (A: M x K, B: N x K, C: M x N, all column-major) ------------------------------
 // DMMA m8n8k4 (mma.sync.aligned.m8n8k4.row.col.f64): tcgen05 has no fp64 kind, so mma.sync DMMA is the fp64 tensor path on
-// sm_100a.  CTA tile 128 x 128 x 16, 8 warps (2 x 4), warp tile 64 x 32, 3-stage cp.async pipeline, padded smem (+4 doubles per
-// k-row) so that the fragment loads are bank-conflict free.
-constexpr int GBM = 128, GBN = 128, GBK = 16, GSTAGES = 3, GPAD = 4;
-constexpr int GLDS = GBM + GPAD;  // 132 doubles per k-row
-constexpr int kGemmSmemBytes = GSTAGES * 2 * GBK * GLDS * (int)sizeof(double);
+// sm_100a.  3-stage cp.async pipeline, padded smem (+4 doubles per k-row) so that the fragment loads are bank-conflict free.
+// Two tile shapes: 128 x 128 (8 warps, warp tile 64 x 32) for large problems, 64 x 64 (4 warps, 32 x 32) when the large tiling
+// would leave most SMs idle (the 100-feature configuration).
+constexpr int GBK = 16, GSTAGES = 3, GPAD = 4;
+template <int BM>
+struct GemmCfg {
+    static constexpr int kBM = BM, kBN = BM;
+    static constexpr int kThreads = BM == 128 ? 256 : 128;
+    static constexpr int kWM = 2, kWN = BM == 128 ? 4 : 2;
+    static constexpr int kMT = BM / (8 * kWM), kNT = 4;
+    static constexpr int kLds = BM + GPAD;
+    static constexpr int kSmemBytes = GSTAGES * 2 * GBK * kLds * (int)sizeof(double);
+};
+constexpr int GBM = 128, GBN = 128;
 
-enum GemmMode { GEMM_SYRK_P = 0, GEMM_CHOL_TRAIL = 1, GEMM_TRSM_TRAIL = 2 };
+enum GemmMode { GEMM_SYRK_P = 0, GEMM_CHOL_TRAIL = 1 };
 
 struct GemmProb {
     const double* A;
@@ -268,59 +634,36 @@ __device__ __forceinline__ bool gemm_setup(const DevFilter& F, int mode, int ste
         g.lda = g.ldb = F.ldw;
         g.C = F.P;
         g.ldc = F.ldp;
-        g.M = g.N = F.n;
+        g.M = g.N = F.n + 1;  // row n of W is y = L^-1 nu: row n of V V^T is V y, i.e. the state correction (fused x update)
         g.K = kk;
         g.lower = g.mirror = true;
         return true;
     }
     const int o = kNB * (step + 1);
     if (kk <= o) return false;
-    if (mode == GEMM_CHOL_TRAIL) {
-        g.A = g.B = F.Sm + o + (size_t)(o - kNB) * F.lds;
-        g.lda = g.ldb = F.lds;
-        g.C = F.Sm + o + (size_t)o * F.lds;
-        g.ldc = F.lds;
-        g.M = g.N = kk - o;
-        g.K = kNB;
-        g.lower = true;
-        g.mirror = false;
-        return true;
-    }
-    // GEMM_TRSM_TRAIL: W[:, o:] -= V[:, o-NB:o] * L[o:, o-NB:o]^T
-    g.A = F.W + (size_t)(o - kNB) * F.ldw;
-    g.lda = F.ldw;
-    g.B = F.Sm + o + (size_t)(o - kNB) * F.lds;
-    g.ldb = F.lds;
-    g.C = F.W + (size_t)o * F.ldw;
-    g.ldc = F.ldw;
-    g.M = F.n + 1;
-    g.N = kk - o;
+    g.A = g.B = F.Sm + o + (size_t)(o - kNB) * F.lds;
+    g.lda = g.ldb = F.lds;
+    g.C = F.Sm + o + (size_t)o * F.lds;
+    g.ldc = F.lds;
+    g.M = g.N = kk - o;
     g.K = kNB;
-    g.lower = g.mirror = false;
+    g.lower = true;
+    g.mirror = false;
     return true;
 }
 
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    const int sz = valid ? 16 : 0;
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(sz));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
-}
-__device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
-}
-
-// tiles_x: number of tile columns in the launch (for full problems); lower-triangular problems enumerate (ti >= tj) linearly.
-__global__ void __launch_bounds__(256, 1) k_gemm_dmma(DevFilter* Fs, int mode, int step) {
+// In SYRK mode the product is taken over the n+1 rows of W: entries (n, c) of V V^T are (V y)[c] and update the state,
+//   x_k_k[c] = x0[c] + (V y)[c]   (x0 = x_k_km1 for the low-innovation update, x_k_k for the high-innovation one),
+// everything else is the covariance downdate P -= V V^T.
+template <int BM>
+__global__ void __launch_bounds__(GemmCfg<BM>::kThreads, 1) k_gemm_dmma(DevFilter* Fs, int mode, int step) {
+    using Cfg = GemmCfg<BM>;
+    constexpr int BN = Cfg::kBN, LDS = Cfg::kLds, MT = Cfg::kMT, NT = Cfg::kNT, THREADS = Cfg::kThreads;
     const DevFilter& F = Fs[blockIdx.z];
     GemmProb g;
-    if (!gemm_setup(F, mode, step, g)) return;
+    if (!gemm_setup(F, mode & 0xff, step, g)) return;
     int ti, tj;
-    const int tm = (g.M + GBM - 1) / GBM, tn = (g.N + GBN - 1) / GBN;
+    const int tm = (g.M + BM - 1) / BM, tn = (g.N + BN - 1) / BN;
     if (g.lower) {
         const long long t = blockIdx.x;
         if (t >= (long long)tm * (tm + 1) / 2) return;
@@ -335,41 +678,41 @@ __global__ void __launch_bounds__(256, 1) k_gemm_dmma(DevFilter* Fs, int mode, i
         tj = blockIdx.x / tm;
     }
     extern __shared__ __align__(16) double gsm[];
-    double* As = gsm;                               // [stage][GBK][GLDS]
-    double* Bs = gsm + GSTAGES * GBK * GLDS;        // [stage][GBK][GLDS]
-    const int m0 = ti * GBM, n0 = tj * GBN;
+    double* As = gsm;                          // [stage][GBK][LDS]
+    double* Bs = gsm + GSTAGES * GBK * LDS;    // [stage][GBK][LDS]
+    const int m0 = ti * BM, n0 = tj * BN;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm0 = (warp & 1) * 64, wn0 = (warp >> 1) * 32;
+    const int wm0 = (warp % Cfg::kWM) * (MT * 8), wn0 = (warp / Cfg::kWM) * (NT * 8);
     const int nkt = (g.K + GBK - 1) / GBK;
+    constexpr int CHUNKS = GBK * (BM / 2);
 
     auto load_stage = [&](int stage, int kt) {
         const int k0 = kt * GBK;
-        // A tile: GBK columns x 64 16-byte chunks; 1024 chunks / 256 threads = 4 each (same for B)
 #pragma unroll
-        for (int it = 0; it < 4; it++) {
-            const int ch = tid + it * 256;
-            const int kc = ch >> 6, r2 = ch & 63;
+        for (int it = 0; it < CHUNKS / THREADS; it++) {
+            const int ch = tid + it * THREADS;
+            const int kc = ch / (BM / 2), r2 = ch % (BM / 2);
             const int row = m0 + 2 * r2, col = k0 + kc;
             const bool v = (row < g.M) && (col < g.K);
             const double* src = v ? (g.A + row + (size_t)col * g.lda) : g.A;
-            cp_async16(&As[(stage * GBK + kc) * GLDS + 2 * r2], src, v);
+            cp_async16(&As[(stage * GBK + kc) * LDS + 2 * r2], src, v);
         }
 #pragma unroll
-        for (int it = 0; it < 4; it++) {
-            const int ch = tid + it * 256;
-            const int kc = ch >> 6, r2 = ch & 63;
+        for (int it = 0; it < CHUNKS / THREADS; it++) {
+            const int ch = tid + it * THREADS;
+            const int kc = ch / (BM / 2), r2 = ch % (BM / 2);
             const int row = n0 + 2 * r2, col = k0 + kc;
             const bool v = (row < g.N) && (col < g.K);
             const double* src = v ? (g.B + row + (size_t)col * g.ldb) : g.B;
-            cp_async16(&Bs[(stage * GBK + kc) * GLDS + 2 * r2], src, v);
+            cp_async16(&Bs[(stage * GBK + kc) * LDS + 2 * r2], src, v);
         }
     };
 
-    double acc[8][4][2];
+    double acc[MT][NT][2];
 #pragma unroll
-    for (int a = 0; a < 8; a++)
+    for (int a = 0; a < MT; a++)
 #pragma unroll
-        for (int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+        for (int b = 0; b < NT; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
 
 #pragma unroll
     for (int s = 0; s < GSTAGES - 1; s++) {
@@ -384,29 +727,32 @@ __global__ void __launch_bounds__(256, 1) k_gemm_dmma(DevFilter* Fs, int mode, i
             if (nk < nkt) load_stage(nk % GSTAGES, nk);
             cp_async_commit();
         }
-        const double* as = As + (kt % GSTAGES) * GBK * GLDS;
-        const double* bs = Bs + (kt % GSTAGES) * GBK * GLDS;
+        const double* as = As + (kt % GSTAGES) * GBK * LDS;
+        const double* bs = Bs + (kt % GSTAGES) * GBK * LDS;
 #pragma unroll
         for (int ks = 0; ks < GBK / 4; ks++) {
             const int krow = ks * 4 + (lane & 3);
-            double af[8], bf[4];
+            double af[MT], bf[NT];
 #pragma unroll
-            for (int mt = 0; mt < 8; mt++) af[mt] = as[krow * GLDS + wm0 + mt * 8 + (lane >> 2)];
+            for (int mt = 0; mt < MT; mt++) af[mt] = as[krow * LDS + wm0 + mt * 8 + (lane >> 2)];
 #pragma unroll
-            for (int nt = 0; nt < 4; nt++) bf[nt] = bs[krow * GLDS + wn0 + nt * 8 + (lane >> 2)];
+            for (int nt = 0; nt < NT; nt++) bf[nt] = bs[krow * LDS + wn0 + nt * 8 + (lane >> 2)];
 #pragma unroll
-            for (int mt = 0; mt < 8; mt++)
+            for (int mt = 0; mt < MT; mt++)
 #pragma unroll
-                for (int nt = 0; nt < 4; nt++) dmma8x8x4(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+                for (int nt = 0; nt < NT; nt++) dmma8x8x4(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
         }
     }
     cp_async_wait<0>();
+    const bool syrk = (mode & 0xff) == GEMM_SYRK_P;
+    const int xrow = syrk ? F.n : -1;
+    const double* x0 = (mode >> 8) ? F.x_kk : F.x_km1;
     // epilogue: C -= acc ; lower: only row >= col ; mirror: also store the transposed element
 #pragma unroll
-    for (int mt = 0; mt < 8; mt++) {
+    for (int mt = 0; mt < MT; mt++) {
         const int row = m0 + wm0 + mt * 8 + (lane >> 2);
 #pragma unroll
-        for (int nt = 0; nt < 4; nt++) {
+        for (int nt = 0; nt < NT; nt++) {
             const int col = n0 + wn0 + nt * 8 + 2 * (lane & 3);
             if (row >= g.M) continue;
 #pragma unroll
@@ -414,6 +760,10 @@ __global__ void __launch_bounds__(256, 1) k_gemm_dmma(DevFilter* Fs, int mode, i
                 const int cc = col + e;
                 if (cc >= g.N) continue;
                 if (g.lower && row < cc) continue;
+                if (row == xrow) {
+                    if (cc < xrow) F.x_kk[cc] = x0[cc] + acc[mt][nt][e];
+                    continue;
+                }
                 double* cp = g.C + row + (size_t)cc * g.ldc;
                 const double v = *cp - acc[mt][nt][e];
                 *cp = v;
@@ -423,25 +773,12 @@ __global__ void __launch_bounds__(256, 1) k_gemm_dmma(DevFilter* Fs, int mode, i
     }
 }
 
-// ---- U7: x+ = x + V y  (y = row n of W after the TRSM).  Thread per state row. ------------------------------------------
-__global__ void __launch_bounds__(128) k_upd_x(DevFilter* Fs, int which) {
+// ---- U7: x+ = x + V y is fused into the SYRK kernel (row n of V V^T); with no measurements the prior is copied ----------------
+__global__ void __launch_bounds__(128) k_upd_x_copy(DevFilter* Fs) {  // low-innovation update with an empty inlier set (:635-638)
     DevFilter& F = Fs[blockIdx.y];
+    if (F.ctl[CTL_K] > 0) return;
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= F.n) return;
-    const int kk = F.ctl[CTL_K];
-    const double* x0 = which == 0 ? F.x_km1 : F.x_kk;
-    const double* W = F.W;
-    const int ldw = F.ldw;
-    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-    int c = 0;
-    for (; c + 3 < kk; c += 4) {
-        s0 += W[r + (size_t)c * ldw] * W[F.n + (size_t)c * ldw];
-        s1 += W[r + (size_t)(c + 1) * ldw] * W[F.n + (size_t)(c + 1) * ldw];
-        s2 += W[r + (size_t)(c + 2) * ldw] * W[F.n + (size_t)(c + 2) * ldw];
-        s3 += W[r + (size_t)(c + 3) * ldw] * W[F.n + (size_t)(c + 3) * ldw];
-    }
-    for (; c < kk; c++) s0 += W[r + (size_t)c * ldw] * W[F.n + (size_t)c * ldw];
-    F.x_kk[r] = x0[r] + ((s0 + s1) + (s2 + s3));
+    if (r < F.n) F.x_kk[r] = F.x_km1[r];
 }
 
 // ---- U9: quaternion normalisation and its Jacobian applied to P (src/ExtendKF.cpp:611-634).  One CTA per filter. -----------

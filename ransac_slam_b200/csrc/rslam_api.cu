@@ -97,14 +97,16 @@ int push_descr(rslam_filter* f) {
 
 int ensure_update_ws(rslam_filter* f) {
     if (f->upd_ws) return 0;
-    const size_t wsz = (size_t)f->ldw * f->kmax, ssz = (size_t)f->lds * f->kmax;
-    double *W = nullptr, *S = nullptr;
+    const size_t wsz = (size_t)f->ldw * f->kmax, ssz = (size_t)f->lds * f->kmax, lsz = (size_t)cdiv(f->kmax, kNB) * kNB * kNB;
+    double *W = nullptr, *S = nullptr, *Li = nullptr;
     int rc;
     if ((rc = dev_alloc(f, &W, wsz * f->B))) return rc;
     if ((rc = dev_alloc(f, &S, ssz * f->B))) return rc;
+    if ((rc = dev_alloc(f, &Li, lsz * f->B))) return rc;
     for (int b = 0; b < f->B; b++) {
         f->hF[b].W = W + wsz * b;
         f->hF[b].Sm = S + ssz * b;
+        f->hF[b].Linv = Li + lsz * b;
     }
     f->upd_ws = true;
     return push_descr(f);
@@ -146,7 +148,8 @@ cudaEvent_t prof_event(rslam_filter* f) {
     return e;
 }
 
-#define LAUNCH(f, kern, grid, block, smem, ...)                               \
+#define LAUNCH(f, kern, grid, block, smem, ...) LAUNCH_N(f, #kern, kern, grid, block, smem, __VA_ARGS__)
+#define LAUNCH_N(f, name, kern, grid, block, smem, ...)                       \
     do {                                                                      \
         const bool prof__ = (f)->prof && !(f)->capturing;                     \
         cudaEvent_t e0__ = nullptr, e1__ = nullptr;                           \
@@ -158,7 +161,7 @@ cudaEvent_t prof_event(rslam_filter* f) {
         kern<<<grid, block, smem, (f)->stream>>>(__VA_ARGS__);                \
         if (prof__) {                                                         \
             cudaEventRecord(e1__, (f)->stream);                               \
-            (f)->prof_recs.push_back(rslam_filter::ProfRec{#kern, e0__, e1__}); \
+            (f)->prof_recs.push_back(rslam_filter::ProfRec{name, e0__, e1__}); \
         }                                                                     \
         (f)->launches++;                                                      \
     } while (0)
@@ -179,26 +182,33 @@ int run_update(rslam_filter* f, int which) {
     LAUNCH(f, k_upd_gather, dim3(1, B), 256, 0, f->dF, which);
     LAUNCH(f, k_upd_W, dim3(cdiv(n, 256), cdiv(N, kWChunk), B), 256, 0, f->dF);
     LAUNCH(f, k_upd_S, dim3(cdiv(N, 16), cdiv(N, 16), B), 256, 0, f->dF);
-    for (int s = 0; s < nsteps; s++) {
-        LAUNCH(f, k_chol_panel, dim3(nsteps - s, B), 128, 0, f->dF, s);
-        const int rem = kmax - kNB * (s + 1);
-        if (rem > 0) {
-            const int tm = cdiv(rem, GBM);
-            LAUNCH(f, k_gemm_dmma, dim3(tm * (tm + 1) / 2, 1, B), 256, kGemmSmemBytes, f->dF, (int)GEMM_CHOL_TRAIL, s);
+    if (kmax <= kCholSmallMaxK) {
+        LAUNCH(f, k_chol_small, dim3(1, B), 256, kCholSmallSmemBytes, f->dF);
+    } else {
+        for (int s = 0; s < nsteps; s++) {
+            LAUNCH(f, k_chol_panel, dim3(nsteps - s, B), 256, kPanelSmemBytes, f->dF, s);
+            const int rem = kmax - kNB * (s + 1);
+            if (rem > 0) {
+                const int tm = cdiv(rem, 128);
+                LAUNCH_N(f, "k_gemm_dmma/chol_trail", k_gemm_dmma<128>, dim3(tm * (tm + 1) / 2, 1, B), 256, GemmCfg<128>::kSmemBytes, f->dF, (int)GEMM_CHOL_TRAIL, s);
+            }
         }
     }
-    for (int s = 0; s < nsteps; s++) {
-        LAUNCH(f, k_trsm_panel, dim3(cdiv(n + 1, 128), B), 128, 0, f->dF, s);
-        const int rem = kmax - kNB * (s + 1);
-        if (rem > 0) {
-            const int tm = cdiv(n + 1, GBM), tn = cdiv(rem, GBN);
-            LAUNCH(f, k_gemm_dmma, dim3(tm * tn, 1, B), 256, kGemmSmemBytes, f->dF, (int)GEMM_TRSM_TRAIL, s);
-        }
+    if (cdiv(n + 1, 96) * B >= 100) {
+        LAUNCH_N(f, "k_trsm_ll", (k_trsm_ll<96, 4>), dim3(cdiv(n + 1, 96), B), 256, (TrsmCfg<96, 4>::kSmemBytes), f->dF);
+    } else {
+        LAUNCH_N(f, "k_trsm_ll", (k_trsm_ll<32, 2>), dim3(cdiv(n + 1, 32), B), 128, (TrsmCfg<32, 2>::kSmemBytes), f->dF);
     }
-    LAUNCH(f, k_upd_x, dim3(cdiv(n, 128), B), 128, 0, f->dF, which);
+    if (which == 0) LAUNCH(f, k_upd_x_copy, dim3(cdiv(n, 128), B), 128, 0, f->dF);
     {
-        const int tm = cdiv(n, GBM);
-        LAUNCH(f, k_gemm_dmma, dim3(tm * (tm + 1) / 2, 1, B), 256, kGemmSmemBytes, f->dF, (int)GEMM_SYRK_P, 0);
+        const int tm = cdiv(n + 1, 128);
+        const int smode = (int)GEMM_SYRK_P | (which << 8);
+        if ((long long)tm * (tm + 1) / 2 * B >= 96) {
+            LAUNCH_N(f, "k_gemm_dmma/syrk_P", k_gemm_dmma<128>, dim3(tm * (tm + 1) / 2, 1, B), 256, GemmCfg<128>::kSmemBytes, f->dF, smode, 0);
+        } else {
+            const int ts = cdiv(n + 1, 64);
+            LAUNCH_N(f, "k_gemm_dmma/syrk_P", k_gemm_dmma<64>, dim3(ts * (ts + 1) / 2, 1, B), 128, GemmCfg<64>::kSmemBytes, f->dF, smode, 0);
+        }
     }
     LAUNCH(f, k_upd_jnorm, dim3(1, B), 256, 0, f->dF, f->pard);
     return check_launch();
@@ -271,7 +281,12 @@ int rslam_create(const rslam_camera* cam, const rslam_params* par, int max_featu
         delete f;
         return fail(RSLAM_ERR_CAPACITY, "rslam_create: max_features %d exceeds the shared-memory staging limit of the Q1 support kernel (7040)", max_features);
     }
-    CK(cudaFuncSetAttribute(k_gemm_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
+    CK(cudaFuncSetAttribute(k_gemm_dmma<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<128>::kSmemBytes));
+    CK(cudaFuncSetAttribute(k_gemm_dmma<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<64>::kSmemBytes));
+    CK(cudaFuncSetAttribute(k_trsm_ll<96, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TrsmCfg<96, 4>::kSmemBytes));
+    CK(cudaFuncSetAttribute(k_trsm_ll<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TrsmCfg<32, 2>::kSmemBytes));
+    CK(cudaFuncSetAttribute(k_chol_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPanelSmemBytes));
+    CK(cudaFuncSetAttribute(k_chol_small, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholSmallSmemBytes));
     if (smem_support > 48 * 1024) CK(cudaFuncSetAttribute(k_ransac_support, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_support));
 
     const int B = batch, N = max_features, n = f->nmax;
@@ -341,6 +356,7 @@ int rslam_create(const rslam_camera* cam, const rslam_params* par, int max_featu
         D.W = nullptr;
         D.Sm = nullptr;
         D.Jn = Jn + (size_t)32 * b;
+        D.Linv = nullptr;
     }
     if ((rc = push_descr(f))) {
         rslam_destroy(f);
@@ -754,6 +770,15 @@ int rslam_frame(rslam_filter* f, const uint8_t* images, int rows, int cols, int 
     }
     CK(cudaGraphLaunch(f->graph_exec, f->stream));
     f->launches += f->graph_nodes;
+    return RSLAM_OK;
+}
+
+// diagnostics: the 32-double scratch block of filter b (phase clocks when built with -DRSLAM_PHASE_CLOCKS)
+int rslam_debug_scratch(rslam_filter* f, int b, double* out32) {
+    if (!f || b < 0 || b >= f->B || !out32) return fail(RSLAM_ERR_INVALID, "rslam_debug_scratch: bad arguments");
+    CK(cudaSetDevice(f->device));
+    CK(cudaStreamSynchronize(f->stream));
+    CK(cudaMemcpy(out32, f->hF[b].Jn, 32 * sizeof(double), cudaMemcpyDeviceToHost));
     return RSLAM_OK;
 }
 
