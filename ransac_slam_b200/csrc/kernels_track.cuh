@@ -608,91 +608,139 @@ __global__ void __launch_bounds__(128) k_ransac_hyp(DevFilter* Fs) {
     }
 }
 
-// c.3 support scoring (compute_hypothesis_support_fast, inlined at src/Tracking.cpp:424-503): one CTA per distinct hypothesis.
-//     For every matched inverse-depth feature j the hypothesised feature rows are formed on the fly,
-//         x_i[y_j] = x[y_j] + P[y_j, 0..6] a + P[y_j, y_p] b,
+// c.3 support scoring (compute_hypothesis_support_fast, inlined at src/Tracking.cpp:424-503).
+//     CTA = tile of SJT matched inverse-depth features x batch of SHB distinct hypotheses.  The hypothesised feature rows are
+//     formed on the fly,      x_i[row] = x[row] + P[row, 0..6] a_p + P[row, y_p] b_p ,
 //     so K (n x 2) is never materialised; the only pair-unique HBM traffic is the 6x6 block P[y_j, y_p] (288 B).
-//     Quirk Q1 (reference): the angles of match jj are read from the stacked POSITION vector, entries (2jj, 2jj+1); the
-//     positions/rho of all matches are therefore staged in shared memory first (4*m doubles).
-__global__ void __launch_bounds__(256) k_ransac_support(DevFilter* Fs, CamDev cam, ParDev par, const int* t_indirect, int t_begin,
-                                                        const int* used, unsigned long long* pair_counter) {
-    DevFilter& F = Fs[blockIdx.y];
-    extern __shared__ double smem[];
-    int t = t_begin + blockIdx.x;
-    if (t_indirect) t = t_indirect[t];
-    if (t < 0 || t >= F.ctl[CTL_NIC]) return;
-    if (used && !used[t]) return;
+//       phase 1: one thread per needed state row (coalesced down the columns of P, 6*SHB independent loads in flight per thread;
+//                the 7 camera columns are read once per row and reused for the SHB hypotheses) -> x_i tile in shared memory
+//       phase 2: one thread per (match, hypothesis) pair: re-projection, 10-step Newton distortion, residual < std_z;
+//                a warp covers 32 consecutive matches of one hypothesis, so its ballot IS the mask word.
+//     Quirk Q1 (reference): the angles of match jj are entries (2jj, 2jj+1) of the stacked POSITION vector of all matches; those
+//     two extra rows replace the (unused) theta / phi rows, so the row count per pair is 6 either way.
+constexpr int SJT = 64, SHB = 8;
+__global__ void __launch_bounds__(256, 4) k_ransac_support(DevFilter* Fs, CamDev cam, ParDev par, const int* t_indirect, int t_begin, int t_end,
+                                                        const int* used, int* sup_alt, unsigned long long* pair_counter) {
+    DevFilter& F = Fs[blockIdx.z];
+    const int nIC = F.ctl[CTL_NIC];
     const int m = F.ctl[CTL_MID];
-    if (pair_counter && threadIdx.x == 0) atomicAdd(pair_counter, (unsigned long long)m);
+    const int J0 = blockIdx.x * SJT;
+    if (J0 >= m) return;
+    __shared__ int s_t[SHB], s_slot[SHB], s_offp[SHB], s_fsp[SHB];
+    __shared__ double s_ab[SHB][13], s_xc[SHB][7], s_R[SHB][9];
+    __shared__ int s_row[6 * SJT];
+    __shared__ double xi[SHB][6 * SJT];
+    const int tid = threadIdx.x;
     const bool q1 = (par.quirks & RSLAM_Q1_ANGLES_FROM_POSITIONS) != 0;
-    double* s_ri = smem;           // 3m (only with Q1)
-    double* s_rho = smem + 3 * m;  // m
-    __shared__ double s_ab[13], s_xc[7], s_R[9];
-    __shared__ int s_cnt[8];
-    const int p = F.ic_list[t];
-    const int offp = F.foff[p];
-    const int fsp = F.ftype[p] == 0 ? 6 : 3;
-    if (threadIdx.x < 13) s_ab[threadIdx.x] = F.hyp_ab[(size_t)t * 13 + threadIdx.x];
-    if (threadIdx.x < 7) s_xc[threadIdx.x] = F.hyp_xcam[(size_t)t * 7 + threadIdx.x];
+    if (tid < SHB) {
+        const int slot = t_begin + blockIdx.y * SHB + tid;
+        int t = -1;
+        if (slot < t_end) {
+            t = t_indirect ? t_indirect[slot] : slot;
+            if (t < 0 || t >= nIC) t = -1;
+            if (t >= 0 && used && !used[t]) t = -1;
+        }
+        s_t[tid] = t;
+        s_slot[tid] = slot;
+        if (t >= 0) {
+            const int p = F.ic_list[t];
+            s_offp[tid] = F.foff[p];
+            s_fsp[tid] = F.ftype[p] == 0 ? 6 : 3;
+        } else {
+            s_offp[tid] = 0;
+            s_fsp[tid] = 0;
+        }
+    }
+    const int nv = __syncthreads_count(tid < SHB && s_t[tid] >= 0);
+    if (nv == 0) return;
+    for (int e = tid; e < SHB * 13; e += blockDim.x) {
+        const int pl = e / 13, c = e % 13;
+        s_ab[pl][c] = s_t[pl] >= 0 ? F.hyp_ab[(size_t)s_t[pl] * 13 + c] : 0.0;
+    }
+    for (int e = tid; e < SHB * 7; e += blockDim.x) {
+        const int pl = e / 7, c = e % 7;
+        s_xc[pl][c] = s_t[pl] >= 0 ? F.hyp_xcam[(size_t)s_t[pl] * 7 + c] : 0.0;
+    }
+    for (int k = tid; k < 6 * SJT; k += blockDim.x) {
+        int row = -1;
+        if (q1) {
+            if (k < 4 * SJT) {
+                const int jj = J0 + (k >> 2), e = k & 3;
+                if (jj < m) row = F.foff[F.id_list[jj]] + (e < 3 ? e : 5);
+            } else {
+                const int tt = 2 * J0 + (k - 4 * SJT);  // index into the stacked position vector ri_v
+                const int feat = tt / 3;
+                if (feat < m && (tt >> 1) < m) row = F.foff[F.id_list[feat]] + tt % 3;
+            }
+        } else {
+            const int jj = J0 + k / 6;
+            if (jj < m) row = F.foff[F.id_list[jj]] + k % 6;
+        }
+        s_row[k] = row;
+    }
     __syncthreads();
-    if (threadIdx.x == 0) q2r_dev(&s_xc[3], s_R);
+    if (tid < SHB && s_t[tid] >= 0) q2r_dev(&s_xc[tid][3], s_R[tid]);
+    if (pair_counter && tid == 0) atomicAdd(pair_counter, (unsigned long long)nv * (unsigned long long)min(SJT, m - J0));
+    // ---- phase 1 ----
     const int ld = F.ldp;
     const double* P = F.P;
     const double* x = F.x_km1;
-    const double* pcol = P + (size_t)offp * ld;
-    if (q1) {
-        for (int jj = threadIdx.x; jj < m; jj += blockDim.x) {
-            const int oj = F.foff[F.id_list[jj]];
-            const int rows[4] = {oj, oj + 1, oj + 2, oj + 5};
-            double v[4];
+    for (int k = tid; k < 6 * SJT; k += blockDim.x) {
+        const int row = s_row[k];
+        if (row < 0) {
 #pragma unroll
-            for (int e = 0; e < 4; e++) {
-                const int r = rows[e];
-                double s = 0;
+            for (int pl = 0; pl < SHB; pl++) xi[pl][k] = 0.0;
+            continue;
+        }
+        double pc[7];
 #pragma unroll
-                for (int c = 0; c < 7; c++) s += P[r + (size_t)c * ld] * s_ab[c];
-                for (int c = 0; c < fsp; c++) s += pcol[r + (size_t)c * ld] * s_ab[7 + c];
-                v[e] = x[r] + s;
+        for (int c = 0; c < 7; c++) pc[c] = P[row + (size_t)c * ld];
+        const double xr = x[row];
+#pragma unroll 1
+        for (int g = 0; g < SHB; g += 2) {  // 2 hypotheses = 12 independent loads in flight per thread (x 512+ threads per SM)
+            double pv[2][6];
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                const double* col = P + (size_t)s_offp[g + q] * ld + row;
+                const int fs = s_fsp[g + q];
+#pragma unroll
+                for (int c = 0; c < 6; c++) pv[q][c] = (c < fs) ? col[(size_t)c * ld] : 0.0;
             }
-            s_ri[3 * jj] = v[0];
-            s_ri[3 * jj + 1] = v[1];
-            s_ri[3 * jj + 2] = v[2];
-            s_rho[jj] = v[3];
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                double sacc = xr;
+#pragma unroll
+                for (int c = 0; c < 7; c++) sacc += pc[c] * s_ab[g + q][c];
+#pragma unroll
+                for (int c = 0; c < 6; c++) sacc += pv[q][c] * s_ab[g + q][7 + c];
+                xi[g + q][k] = sacc;
+            }
         }
     }
     __syncthreads();
-    int cnt = 0;
-    const int mpad = (m + 31) & ~31;
-    for (int jj = threadIdx.x; jj < mpad; jj += blockDim.x) {
+    // ---- phase 2 ----
+    const double fku = cam.f * (1.0 / cam.dx);
+    for (int e = tid; e < SHB * SJT; e += blockDim.x) {
+        const int pl = e / SJT, jl = e % SJT;
+        const int jj = J0 + jl;
+        const int t = s_t[pl];
         bool inl = false;
-        if (jj < m) {
-            const int fj = F.id_list[jj];
+        if (t >= 0 && jj < m) {
             double r3[3], a0, a1, rho;
             if (q1) {
-                r3[0] = s_ri[3 * jj];
-                r3[1] = s_ri[3 * jj + 1];
-                r3[2] = s_ri[3 * jj + 2];
-                rho = s_rho[jj];
-                a0 = s_ri[2 * jj];
-                a1 = s_ri[2 * jj + 1];
+                r3[0] = xi[pl][4 * jl];
+                r3[1] = xi[pl][4 * jl + 1];
+                r3[2] = xi[pl][4 * jl + 2];
+                rho = xi[pl][4 * jl + 3];
+                a0 = xi[pl][4 * SJT + 2 * jl];
+                a1 = xi[pl][4 * SJT + 2 * jl + 1];
             } else {
-                const int oj = F.foff[fj];
-                double v[6];
-#pragma unroll
-                for (int e = 0; e < 6; e++) {
-                    const int r = oj + e;
-                    double s = 0;
-#pragma unroll
-                    for (int c = 0; c < 7; c++) s += P[r + (size_t)c * ld] * s_ab[c];
-                    for (int c = 0; c < fsp; c++) s += pcol[r + (size_t)c * ld] * s_ab[7 + c];
-                    v[e] = x[r] + s;
-                }
-                r3[0] = v[0];
-                r3[1] = v[1];
-                r3[2] = v[2];
-                a0 = v[3];
-                a1 = v[4];
-                rho = v[5];
+                r3[0] = xi[pl][6 * jl];
+                r3[1] = xi[pl][6 * jl + 1];
+                r3[2] = xi[pl][6 * jl + 2];
+                a0 = xi[pl][6 * jl + 3];
+                a1 = xi[pl][6 * jl + 4];
+                rho = xi[pl][6 * jl + 5];
             }
             double s0, c0, s1, c1;
             sincos(a0, &s0, &c0);
@@ -700,30 +748,24 @@ __global__ void __launch_bounds__(256) k_ransac_support(DevFilter* Fs, CamDev ca
             const double mi[3] = {c1 * s0, -s1, c1 * c0};
             double v3[3];
 #pragma unroll
-            for (int k = 0; k < 3; k++) v3[k] = (r3[k] - s_xc[k]) * rho + mi[k];
+            for (int k = 0; k < 3; k++) v3[k] = (r3[k] - s_xc[pl][k]) * rho + mi[k];
             double hc[3];
 #pragma unroll
-            for (int k = 0; k < 3; k++) hc[k] = s_R[k] * v3[0] + s_R[3 + k] * v3[1] + s_R[6 + k] * v3[2];  // R^T v
-            const double fku = cam.f * (1.0 / cam.dx);
+            for (int k = 0; k < 3; k++) hc[k] = s_R[pl][k] * v3[0] + s_R[pl][3 + k] * v3[1] + s_R[pl][6 + k] * v3[2];  // R^T v
             const double u = fku * (hc[0] / hc[2]) + cam.Cx;
             const double v = fku * (hc[1] / hc[2]) + cam.Cy;  // ku for both rows (src/Tracking.cpp:471)
             double ud, vd;
             distort_dev(cam, u, v, ud, vd);
+            const int fj = F.id_list[jj];
             const double n0 = F.z[2 * fj] - ud, n1 = F.z[2 * fj + 1] - vd;
-            const double res = sqrt(n0 * n0 + n1 * n1);
-            inl = res < par.std_z;
+            inl = sqrt(n0 * n0 + n1 * n1) < par.std_z;
         }
         const unsigned bal = __ballot_sync(0xffffffffu, inl);
-        if ((threadIdx.x & 31) == 0) F.masks[(size_t)t * F.mwords + (jj >> 5)] = bal;
-        cnt += inl ? 1 : 0;
-    }
-    cnt = warp_sum_int(cnt);
-    if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = cnt;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int s = 0;
-        for (int k = 0; k < (int)(blockDim.x >> 5); k++) s += s_cnt[k];
-        F.support[t] = s;
+        if ((tid & 31) == 0 && t >= 0 && (jj >> 5) < F.mwords) {
+            F.masks[(size_t)t * F.mwords + (jj >> 5)] = bal;
+            const int cnt = __popc(bal);
+            if (cnt) atomicAdd(sup_alt ? &sup_alt[s_slot[pl]] : &F.support[t], cnt);
+        }
     }
 }
 
@@ -845,14 +887,14 @@ __global__ void __launch_bounds__(256) k_ransac_select(DevFilter* Fs, ParDev par
 }
 
 // sweep (config C4): reduce key = (support << 32) | (0xFFFFFFFF - hypothesis id) over hypotheses [h0, h1)
-__global__ void __launch_bounds__(256) k_sweep_reduce(DevFilter* Fs, const int* hyp_idx, int h0, int h1, unsigned long long* out_key) {
+__global__ void __launch_bounds__(256) k_sweep_reduce(DevFilter* Fs, const int* hyp_idx, int h0, int h1, const int* sup_alt, unsigned long long* out_key) {
     DevFilter& F = Fs[0];
     unsigned long long best = 0ull;
     const int nIC = F.ctl[CTL_NIC];
     for (int i = h0 + blockIdx.x * blockDim.x + threadIdx.x; i < h1; i += gridDim.x * blockDim.x) {
         const int t = hyp_idx[i];
         if (t < 0 || t >= nIC) continue;
-        const unsigned long long key = ((unsigned long long)(unsigned)F.support[t] << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
+        const unsigned long long key = ((unsigned long long)(unsigned)(sup_alt ? sup_alt[i] : F.support[t]) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
         best = key > best ? key : best;
     }
 #pragma unroll

@@ -53,6 +53,9 @@ struct rslam_filter {
     int* d_hyp_idx = nullptr;
     size_t hyp_cap = 0;
     int* d_used = nullptr;
+    int* d_support_all = nullptr;  // base of the per-filter support arrays (zeroed before every scoring pass)
+    int* d_sup_h = nullptr;        // per-hypothesis supports of a brute-force sweep
+    size_t sup_h_cap = 0;
     unsigned long long* d_key = nullptr;  // [0] key, [1] pair counter
     bool have_image = false;
     bool upd_ws = false;
@@ -219,10 +222,10 @@ int run_ransac_core(rslam_filter* f, bool select) {
     if (N == 0) return 0;
     LAUNCH(f, k_ransac_compact, dim3(1, B), 256, 0, f->dF);
     LAUNCH(f, k_ransac_hyp, dim3(cdiv(N, 128), B), 128, 0, f->dF);
+    CK(cudaMemsetAsync(f->d_support_all, 0, sizeof(int) * (size_t)f->Nmax * B, f->stream));
     if (select) {
-        const size_t smem = (f->pard.quirks & RSLAM_Q1_ANGLES_FROM_POSITIONS) ? (size_t)4 * N * sizeof(double) : 0;
-        LAUNCH(f, k_ransac_support, dim3(N, B), 256, smem, f->dF, f->camd, f->pard, (const int*)nullptr, 0, (const int*)nullptr,
-               (unsigned long long*)nullptr);
+        LAUNCH(f, k_ransac_support, dim3(cdiv(N, SJT), cdiv(N, SHB), B), 256, 0, f->dF, f->camd, f->pard, (const int*)nullptr, 0, N, (const int*)nullptr,
+               (int*)nullptr, (unsigned long long*)nullptr);
         LAUNCH(f, k_ransac_select, dim3(1, B), 256, 0, f->dF, f->pard);
     }
     return check_launch();
@@ -276,18 +279,12 @@ int rslam_create(const rslam_camera* cam, const rslam_params* par, int max_featu
     f->pard = ParDev{f->par.std_z, f->par.chi2_095_2, f->par.corr_threshold, f->par.p_spurious_free, f->par.max_ellipse_eig,
                      (f->par.std_a * 1.0) * (f->par.std_a * 1.0), (f->par.std_alpha * 1.0) * (f->par.std_alpha * 1.0), f->par.n_hyp_initial, f->par.quirks};
     CK(cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking));
-    const size_t smem_support = (size_t)4 * max_features * sizeof(double);
-    if ((f->pard.quirks & RSLAM_Q1_ANGLES_FROM_POSITIONS) && smem_support > 220 * 1024) {
-        delete f;
-        return fail(RSLAM_ERR_CAPACITY, "rslam_create: max_features %d exceeds the shared-memory staging limit of the Q1 support kernel (7040)", max_features);
-    }
     CK(cudaFuncSetAttribute(k_gemm_dmma<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<128>::kSmemBytes));
     CK(cudaFuncSetAttribute(k_gemm_dmma<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<64>::kSmemBytes));
     CK(cudaFuncSetAttribute(k_trsm_ll<96, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TrsmCfg<96, 4>::kSmemBytes));
     CK(cudaFuncSetAttribute(k_trsm_ll<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TrsmCfg<32, 2>::kSmemBytes));
     CK(cudaFuncSetAttribute(k_chol_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPanelSmemBytes));
     CK(cudaFuncSetAttribute(k_chol_small, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholSmallSmemBytes));
-    if (smem_support > 48 * 1024) CK(cudaFuncSetAttribute(k_ransac_support, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_support));
 
     const int B = batch, N = max_features, n = f->nmax;
     f->hF.assign(B, DevFilter{});
@@ -348,6 +345,7 @@ int rslam_create(const rslam_camera* cam, const rslam_params* par, int max_featu
         D.hyp_ab = hyp_ab + (size_t)13 * N * b;
         D.hyp_xcam = hyp_xcam + (size_t)7 * N * b;
         D.support = support + (size_t)N * b;
+        f->d_support_all = support;
         D.masks = masks + (size_t)N * f->mwords * b;
         D.u01 = nullptr;
         D.n_u01 = 0;
@@ -381,6 +379,7 @@ int rslam_destroy(rslam_filter* f) {
     if (f->d_images) cudaFree(f->d_images);
     if (f->d_u01) cudaFree(f->d_u01);
     if (f->d_hyp_idx) cudaFree(f->d_hyp_idx);
+    if (f->d_sup_h) cudaFree(f->d_sup_h);
     if (f->stream) cudaStreamDestroy(f->stream);
     delete f;
     return RSLAM_OK;
@@ -850,16 +849,24 @@ int rslam_support_sweep(rslam_filter* f, const int* hyp_match_idx, int n_hyp, in
     if ((rc = run_ransac_core(f, false))) return rc;
     CK(cudaMemsetAsync(f->d_key, 0, 2 * sizeof(unsigned long long), f->stream));
     const int nh = hyp_end - hyp_begin;
-    const size_t smem = (f->pard.quirks & RSLAM_Q1_ANGLES_FROM_POSITIONS) ? (size_t)4 * N * sizeof(double) : 0;
     if (nh > 0) {
         if (f->par.dedupe_hypotheses) {
             CK(cudaMemsetAsync(f->d_used, 0, sizeof(int) * (size_t)f->Nmax, f->stream));
             LAUNCH(f, k_sweep_mark, cdiv(nh, 256) < 1024 ? cdiv(nh, 256) : 1024, 256, 0, f->dF, d_idx, hyp_begin, hyp_end, f->d_used);
-            LAUNCH(f, k_ransac_support, dim3(N, 1), 256, smem, f->dF, f->camd, f->pard, (const int*)nullptr, 0, (const int*)f->d_used, f->d_key + 1);
+            LAUNCH(f, k_ransac_support, dim3(cdiv(N, SJT), cdiv(N, SHB), 1), 256, 0, f->dF, f->camd, f->pard, (const int*)nullptr, 0, N, (const int*)f->d_used,
+                   (int*)nullptr, f->d_key + 1);
+            LAUNCH(f, k_sweep_reduce, cdiv(nh, 256) < 512 ? cdiv(nh, 256) : 512, 256, 0, f->dF, d_idx, hyp_begin, hyp_end, (const int*)nullptr, f->d_key);
         } else {
-            LAUNCH(f, k_ransac_support, dim3(nh, 1), 256, smem, f->dF, f->camd, f->pard, d_idx, hyp_begin, (const int*)nullptr, f->d_key + 1);
+            if ((size_t)n_hyp > f->sup_h_cap) {
+                if (f->d_sup_h) CK(cudaFree(f->d_sup_h));
+                CK(cudaMalloc((void**)&f->d_sup_h, sizeof(int) * (size_t)n_hyp));
+                f->sup_h_cap = n_hyp;
+            }
+            CK(cudaMemsetAsync(f->d_sup_h + hyp_begin, 0, sizeof(int) * (size_t)nh, f->stream));
+            LAUNCH(f, k_ransac_support, dim3(cdiv(N, SJT), cdiv(nh, SHB), 1), 256, 0, f->dF, f->camd, f->pard, d_idx, hyp_begin, hyp_end, (const int*)nullptr,
+                   f->d_sup_h, f->d_key + 1);
+            LAUNCH(f, k_sweep_reduce, cdiv(nh, 256) < 512 ? cdiv(nh, 256) : 512, 256, 0, f->dF, d_idx, hyp_begin, hyp_end, (const int*)f->d_sup_h, f->d_key);
         }
-        LAUNCH(f, k_sweep_reduce, cdiv(nh, 256) < 512 ? cdiv(nh, 256) : 512, 256, 0, f->dF, d_idx, hyp_begin, hyp_end, f->d_key);
     }
     if ((rc = check_launch())) return rc;
     CK(cudaMemcpyAsync(best_key, f->d_key, sizeof(uint64_t), cudaMemcpyDefault, f->stream));
