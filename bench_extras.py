@@ -129,12 +129,16 @@ def bench_c4(args, world, rank, local):
         g.set_matches(z, np.ones(N, dtype=np.uint8))
         d_hyp = torch.from_numpy(hyp).to(dev)
         d_key = torch.zeros(1, dtype=torch.int64, device=dev)
-        h0, h1 = rank * H // world, (rank + 1) * H // world
+        # sharding axis: dedupe -> by match index (each distinct hypothesis scored on exactly one GPU); brute force -> by hypothesis id
+        if dedupe:
+            h0, h1, t0, t1 = 0, H, rank * N // world, (rank + 1) * N // world
+        else:
+            h0, h1, t0, t1 = rank * H // world, (rank + 1) * H // world, 0, N
         stream = torch.cuda.ExternalStream(g.stream)
         reps = 5 if dedupe else 2
 
         def sweep():
-            g.support_sweep(d_hyp.data_ptr(), h0, h1, want_mask=False, key_device_ptr=d_key.data_ptr(), n_hyp=H)
+            g.support_sweep(d_hyp.data_ptr(), h0, h1, want_mask=False, key_device_ptr=d_key.data_ptr(), n_hyp=H, match_begin=t0, match_end=t1)
             if world > 1:
                 import torch.distributed as dist
 
@@ -156,7 +160,7 @@ def bench_c4(args, world, rank, local):
         key = int(d_key.item())
         support, hid = capi.decode_key(key)
         # distinct pairs actually scored (host read, outside the timed region)
-        _, _, pairs = g.support_sweep(hyp, h0, h1, want_mask=False)
+        _, _, pairs = g.support_sweep(hyp, h0, h1, want_mask=False, match_begin=t0, match_end=t1)
         pairs_all = B.sum_over_ranks(float(pairs), world)
         pk = B.peaks()
         name = "dedupe" if dedupe else "brute_force"

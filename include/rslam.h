@@ -137,14 +137,16 @@ int rslam_debug_scratch(rslam_filter* f, int b, double* out32);
 int rslam_download_pose(rslam_filter* f, int b, double* x13);
 
 /* --- support-scoring sweep (compute_hypothesis_support_fast, src/Tracking.cpp:424-503; Tracking.h:42) ---------- */
-/* Scores hypotheses [hyp_begin, hyp_end) of the list hyp_match_idx[n_hyp] (each entry: index into the filter's list of
- * individually compatible matches; host or device) against all matches of filter 0 at (x_k_km1, P).  Writes
- *   *best_key = (support << 32) | (0xFFFFFFFF - hypothesis id)   (max over the range; 0 if the range is empty)
+/* Scores the hypotheses i in [hyp_begin, hyp_end) of the list hyp_match_idx[n_hyp] (entry = index into the filter's list of
+ * individually compatible matches; host or device) whose match index lies in [match_begin, match_end), against all matches of filter 0
+ * at (x_k_km1, P).  The two ranges are the two ways to shard a sweep over GPUs: by hypothesis id (every hypothesis scored, the
+ * "no-reuse" convention) or by match index (with dedupe_hypotheses each DISTINCT hypothesis is scored once, on exactly one GPU).  Writes
+ *   *best_key = (support << 32) | (0xFFFFFFFF - hypothesis id)   (max over the selected hypotheses; 0 if none)
  * to best_key (host or device; device lets the caller all-reduce it with NCCL ncclMax without a host round trip), and,
  * if best_mask != NULL (host), the winner's inlier bit per matched feature (ceil(m/8) bytes, feature order).
  * n_pairs_scored (host, optional): number of (hypothesis, match) pairs actually evaluated on the device. */
-int rslam_support_sweep(rslam_filter* f, const int* hyp_match_idx, int n_hyp, int hyp_begin, int hyp_end, uint64_t* best_key,
-                        uint8_t* best_mask, long long* n_pairs_scored);
+int rslam_support_sweep(rslam_filter* f, const int* hyp_match_idx, int n_hyp, int hyp_begin, int hyp_end, int match_begin, int match_end,
+                        uint64_t* best_key, uint8_t* best_mask, long long* n_pairs_scored);
 /* inlier mask of one hypothesis id after a sweep that covered it (for the rank that owns the all-reduced winner) */
 int rslam_sweep_mask(rslam_filter* f, int match_idx, uint8_t* mask);
 

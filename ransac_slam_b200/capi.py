@@ -85,7 +85,7 @@ def load():
     L.rslam_set_graph.argtypes = [vp, ci]
     L.rslam_profile_enable.argtypes = [vp, ci]
     L.rslam_profile_read.argtypes = [vp, C.c_char_p, C.c_size_t]
-    L.rslam_support_sweep.argtypes = [vp, vp, ci, ci, ci, vp, vp, vp]
+    L.rslam_support_sweep.argtypes = [vp, vp, ci, ci, ci, ci, ci, vp, vp, vp]
     L.rslam_sweep_mask.argtypes = [vp, ci, vp]
     _lib = L
     return L
@@ -283,7 +283,7 @@ class Filter:
         return int(self.L.rslam_launch_count(self.h))
 
     # -- sweep ------------------------------------------------------------------------------------------------------
-    def support_sweep(self, hyp_idx, begin=0, end=None, want_mask=True, key_device_ptr=None, n_hyp=None):
+    def support_sweep(self, hyp_idx, begin=0, end=None, want_mask=True, key_device_ptr=None, n_hyp=None, match_begin=0, match_end=2**31 - 1):
         """hyp_idx: int32 host array or device pointer (int).  Returns (key, mask_bits or None, pairs_scored)."""
         if isinstance(hyp_idx, int):
             hp = C.c_void_p(hyp_idx)
@@ -298,7 +298,7 @@ class Filter:
         pairs = C.c_longlong(0)
         mask = np.zeros((self.max_features + 7) // 8, dtype=np.uint8) if want_mask else None
         kp = C.c_void_p(key_device_ptr) if key_device_ptr is not None else _p(key)
-        self._ck(self.L.rslam_support_sweep(self.h, hp, n_hyp, begin, end, kp, _p(mask), C.byref(pairs) if key_device_ptr is None else None))
+        self._ck(self.L.rslam_support_sweep(self.h, hp, n_hyp, begin, end, match_begin, match_end, kp, _p(mask), C.byref(pairs) if key_device_ptr is None else None))
         bits = np.unpackbits(mask, bitorder="little").astype(bool) if want_mask else None
         return int(key[0]), bits, int(pairs.value)
 

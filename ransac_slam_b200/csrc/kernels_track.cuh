@@ -620,7 +620,7 @@ __global__ void __launch_bounds__(128) k_ransac_hyp(DevFilter* Fs) {
 //     two extra rows replace the (unused) theta / phi rows, so the row count per pair is 6 either way.
 constexpr int SJT = 64, SHB = 8;
 __global__ void __launch_bounds__(256, 4) k_ransac_support(DevFilter* Fs, CamDev cam, ParDev par, const int* t_indirect, int t_begin, int t_end,
-                                                        const int* used, int* sup_alt, unsigned long long* pair_counter) {
+                                                        int t_lo, int t_hi, const int* used, int* sup_alt, unsigned long long* pair_counter) {
     DevFilter& F = Fs[blockIdx.z];
     const int nIC = F.ctl[CTL_NIC];
     const int m = F.ctl[CTL_MID];
@@ -637,7 +637,7 @@ __global__ void __launch_bounds__(256, 4) k_ransac_support(DevFilter* Fs, CamDev
         int t = -1;
         if (slot < t_end) {
             t = t_indirect ? t_indirect[slot] : slot;
-            if (t < 0 || t >= nIC) t = -1;
+            if (t < t_lo || t >= t_hi || t >= nIC) t = -1;
             if (t >= 0 && used && !used[t]) t = -1;
         }
         s_t[tid] = t;
@@ -887,13 +887,14 @@ __global__ void __launch_bounds__(256) k_ransac_select(DevFilter* Fs, ParDev par
 }
 
 // sweep (config C4): reduce key = (support << 32) | (0xFFFFFFFF - hypothesis id) over hypotheses [h0, h1)
-__global__ void __launch_bounds__(256) k_sweep_reduce(DevFilter* Fs, const int* hyp_idx, int h0, int h1, const int* sup_alt, unsigned long long* out_key) {
+__global__ void __launch_bounds__(256) k_sweep_reduce(DevFilter* Fs, const int* hyp_idx, int h0, int h1, int t_lo, int t_hi, const int* sup_alt,
+                                                      unsigned long long* out_key) {
     DevFilter& F = Fs[0];
     unsigned long long best = 0ull;
-    const int nIC = F.ctl[CTL_NIC];
+    const int nIC = min(F.ctl[CTL_NIC], t_hi);
     for (int i = h0 + blockIdx.x * blockDim.x + threadIdx.x; i < h1; i += gridDim.x * blockDim.x) {
         const int t = hyp_idx[i];
-        if (t < 0 || t >= nIC) continue;
+        if (t < t_lo || t >= nIC) continue;
         const unsigned long long key = ((unsigned long long)(unsigned)(sup_alt ? sup_alt[i] : F.support[t]) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
         best = key > best ? key : best;
     }
@@ -906,12 +907,12 @@ __global__ void __launch_bounds__(256) k_sweep_reduce(DevFilter* Fs, const int* 
 }
 
 // mark which distinct hypotheses are referenced by hyp_idx[h0, h1) (dedupe), then compact them
-__global__ void k_sweep_mark(DevFilter* Fs, const int* hyp_idx, int h0, int h1, int* used) {
+__global__ void k_sweep_mark(DevFilter* Fs, const int* hyp_idx, int h0, int h1, int t_lo, int t_hi, int* used) {
     DevFilter& F = Fs[0];
-    const int nIC = F.ctl[CTL_NIC];
+    const int nIC = min(F.ctl[CTL_NIC], t_hi);
     for (int i = h0 + blockIdx.x * blockDim.x + threadIdx.x; i < h1; i += gridDim.x * blockDim.x) {
         const int t = hyp_idx[i];
-        if (t >= 0 && t < nIC) used[t] = 1;
+        if (t >= t_lo && t < nIC) used[t] = 1;
     }
 }
 

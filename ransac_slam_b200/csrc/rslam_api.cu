@@ -224,7 +224,7 @@ int run_ransac_core(rslam_filter* f, bool select) {
     LAUNCH(f, k_ransac_hyp, dim3(cdiv(N, 128), B), 128, 0, f->dF);
     CK(cudaMemsetAsync(f->d_support_all, 0, sizeof(int) * (size_t)f->Nmax * B, f->stream));
     if (select) {
-        LAUNCH(f, k_ransac_support, dim3(cdiv(N, SJT), cdiv(N, SHB), B), 256, 0, f->dF, f->camd, f->pard, (const int*)nullptr, 0, N, (const int*)nullptr,
+        LAUNCH(f, k_ransac_support, dim3(cdiv(N, SJT), cdiv(N, SHB), B), 256, 0, f->dF, f->camd, f->pard, (const int*)nullptr, 0, N, 0, N, (const int*)nullptr,
                (int*)nullptr, (unsigned long long*)nullptr);
         LAUNCH(f, k_ransac_select, dim3(1, B), 256, 0, f->dF, f->pard);
     }
@@ -828,9 +828,9 @@ int rslam_profile_read(rslam_filter* f, char* buf, size_t buflen) {
     return RSLAM_OK;
 }
 
-int rslam_support_sweep(rslam_filter* f, const int* hyp_match_idx, int n_hyp, int hyp_begin, int hyp_end, uint64_t* best_key, uint8_t* best_mask,
-                        long long* n_pairs_scored) {
-    if (!f || !hyp_match_idx || n_hyp <= 0 || hyp_begin < 0 || hyp_end > n_hyp || hyp_begin > hyp_end || !best_key)
+int rslam_support_sweep(rslam_filter* f, const int* hyp_match_idx, int n_hyp, int hyp_begin, int hyp_end, int match_begin, int match_end,
+                        uint64_t* best_key, uint8_t* best_mask, long long* n_pairs_scored) {
+    if (!f || !hyp_match_idx || n_hyp <= 0 || hyp_begin < 0 || hyp_end > n_hyp || hyp_begin > hyp_end || match_begin < 0 || match_end < match_begin || !best_key)
         return fail(RSLAM_ERR_INVALID, "rslam_support_sweep: bad arguments");
     CK(cudaSetDevice(f->device));
     const int N = f->hN;
@@ -852,10 +852,13 @@ int rslam_support_sweep(rslam_filter* f, const int* hyp_match_idx, int n_hyp, in
     if (nh > 0) {
         if (f->par.dedupe_hypotheses) {
             CK(cudaMemsetAsync(f->d_used, 0, sizeof(int) * (size_t)f->Nmax, f->stream));
-            LAUNCH(f, k_sweep_mark, cdiv(nh, 256) < 1024 ? cdiv(nh, 256) : 1024, 256, 0, f->dF, d_idx, hyp_begin, hyp_end, f->d_used);
-            LAUNCH(f, k_ransac_support, dim3(cdiv(N, SJT), cdiv(N, SHB), 1), 256, 0, f->dF, f->camd, f->pard, (const int*)nullptr, 0, N, (const int*)f->d_used,
-                   (int*)nullptr, f->d_key + 1);
-            LAUNCH(f, k_sweep_reduce, cdiv(nh, 256) < 512 ? cdiv(nh, 256) : 512, 256, 0, f->dF, d_idx, hyp_begin, hyp_end, (const int*)nullptr, f->d_key);
+            const int tlo = match_begin < N ? match_begin : N, thi = match_end < N ? match_end : N;
+            LAUNCH(f, k_sweep_mark, cdiv(nh, 256) < 1024 ? cdiv(nh, 256) : 1024, 256, 0, f->dF, d_idx, hyp_begin, hyp_end, match_begin, match_end, f->d_used);
+            if (thi > tlo)
+                LAUNCH(f, k_ransac_support, dim3(cdiv(N, SJT), cdiv(thi - tlo, SHB), 1), 256, 0, f->dF, f->camd, f->pard, (const int*)nullptr, tlo, thi, tlo, thi,
+                       (const int*)f->d_used, (int*)nullptr, f->d_key + 1);
+            LAUNCH(f, k_sweep_reduce, cdiv(nh, 256) < 512 ? cdiv(nh, 256) : 512, 256, 0, f->dF, d_idx, hyp_begin, hyp_end, match_begin, match_end, (const int*)nullptr,
+                   f->d_key);
         } else {
             if ((size_t)n_hyp > f->sup_h_cap) {
                 if (f->d_sup_h) CK(cudaFree(f->d_sup_h));
@@ -863,9 +866,10 @@ int rslam_support_sweep(rslam_filter* f, const int* hyp_match_idx, int n_hyp, in
                 f->sup_h_cap = n_hyp;
             }
             CK(cudaMemsetAsync(f->d_sup_h + hyp_begin, 0, sizeof(int) * (size_t)nh, f->stream));
-            LAUNCH(f, k_ransac_support, dim3(cdiv(N, SJT), cdiv(nh, SHB), 1), 256, 0, f->dF, f->camd, f->pard, d_idx, hyp_begin, hyp_end, (const int*)nullptr,
-                   f->d_sup_h, f->d_key + 1);
-            LAUNCH(f, k_sweep_reduce, cdiv(nh, 256) < 512 ? cdiv(nh, 256) : 512, 256, 0, f->dF, d_idx, hyp_begin, hyp_end, (const int*)f->d_sup_h, f->d_key);
+            LAUNCH(f, k_ransac_support, dim3(cdiv(N, SJT), cdiv(nh, SHB), 1), 256, 0, f->dF, f->camd, f->pard, d_idx, hyp_begin, hyp_end, match_begin, match_end,
+                   (const int*)nullptr, f->d_sup_h, f->d_key + 1);
+            LAUNCH(f, k_sweep_reduce, cdiv(nh, 256) < 512 ? cdiv(nh, 256) : 512, 256, 0, f->dF, d_idx, hyp_begin, hyp_end, match_begin, match_end, (const int*)f->d_sup_h,
+                   f->d_key);
         }
     }
     if ((rc = check_launch())) return rc;

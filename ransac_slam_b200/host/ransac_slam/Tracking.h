@@ -13,7 +13,7 @@ class Tracking {
     void search_IC_matches(cv::Mat image);  // src/Tracking.cpp:32-70
     void ransac_hypotheses(void);           // src/Tracking.cpp:352-539
     void rescue_hi_inliers(void);           // src/Tracking.cpp:574-597
-    // explicit uniform draws for the next ransac_hypotheses() call (north_star: same seeded sequence as the oracle); without
+    // explicit uniform draws for the next ransac_hypotheses() call (north_star: hypothesis indices fed from the same seeded sequence); without
     // them the draws come from std::rand() like the reference (src/ExtendKF.cpp:230), mapped to [0,1)
     void set_uniform_draws(const double* u01, int n);
     rslam_ransac_result last_ransac() const { return last_; }

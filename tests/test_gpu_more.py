@@ -174,6 +174,9 @@ def test_support_sweep_against_numpy(q1):
         # sharded: max of the shard keys == global key
         keys = [f.support_sweep(hyp, *sweep.shard_range(len(hyp), 4, r), want_mask=False)[0] for r in range(4)]
         assert max(keys) == key
+        # sharded by match index instead (how the deduplicated sweep scales over GPUs)
+        keys_m = [f.support_sweep(hyp, want_mask=False, match_begin=sweep.shard_range(nic, 3, r)[0], match_end=sweep.shard_range(nic, 3, r)[1])[0] for r in range(3)]
+        assert max(keys_m) == key
     assert results[0][0] == results[1][0] and (results[0][1] == results[1][1]).all()
     # numpy restatement of every distinct hypothesis
     o = H.oracle_from(scene, x, P)
