@@ -752,10 +752,11 @@ __global__ void __launch_bounds__(256, 4) k_ransac_support(DevFilter* Fs, CamDev
             double hc[3];
 #pragma unroll
             for (int k = 0; k < 3; k++) hc[k] = s_R[pl][k] * v3[0] + s_R[pl][3 + k] * v3[1] + s_R[pl][6 + k] * v3[2];  // R^T v
-            const double u = fku * (hc[0] / hc[2]) + cam.Cx;
-            const double v = fku * (hc[1] / hc[2]) + cam.Cy;  // ku for both rows (src/Tracking.cpp:471)
+            const double ihz = 1.0 / hc[2];
+            const double u = fku * (hc[0] * ihz) + cam.Cx;
+            const double v = fku * (hc[1] * ihz) + cam.Cy;  // ku for both rows (src/Tracking.cpp:471)
             double ud, vd;
-            distort_dev(cam, u, v, ud, vd);
+            distort_fast_dev(cam, u, v, ud, vd);
             const int fj = F.id_list[jj];
             const double n0 = F.z[2 * fj] - ud, n1 = F.z[2 * fj + 1] - vd;
             inl = sqrt(n0 * n0 + n1 * n1) < par.std_z;
