@@ -94,6 +94,13 @@ int rslam_upload_state(rslam_filter* f, int b, int which, const double* x, const
 int rslam_download_state(rslam_filter* f, int b, int which, double* x, double* P, int ldp);
 /* predicted appearance patch_when_matching (13x13 row-major per feature, values must be float-exact) */
 int rslam_upload_patches(rslam_filter* f, int b, const double* patches, int N);
+/* Tracking::pred_patch_fc on the device (src/Tracking.cpp:164-278).  Upload, per feature, what Map::initialize_a_features stores
+ * (src/Map.cpp:286-294): the 41x41 8-bit patch cut at initialisation (row-major), the camera position r_wc[3] and rotation R_wc[9]
+ * (row-major) at that time and the initial pixel uv[2]; then enable the warp: rslam_search_ic_matches recomputes
+ * patch_when_matching for every predicted feature before the search (otherwise the patches given by rslam_upload_patches are used). */
+int rslam_upload_feature_init(rslam_filter* f, int b, const uint8_t* patches41, const double* r_wc, const double* R_wc, const double* uv, int N);
+int rslam_set_patch_warp(rslam_filter* f, int enable);
+int rslam_download_patches(rslam_filter* f, int b, float* patches, int N);
 /* per-feature outputs (any pointer may be NULL): h[2N], S[4N] row-major 2x2, z[2N], flags[4N] = {has_h, individually_compatible,
  * low_innovation_inlier, high_innovation_inlier}, counters[2N] = {times_predicted, times_measured} */
 int rslam_download_features(rslam_filter* f, int b, double* h, double* S, double* z, uint8_t* flags, int* counters);

@@ -39,7 +39,7 @@ class RansacResult(C.Structure):
 EXPORTS = [
     "rslam_default_params", "rslam_last_error", "rslam_version", "rslam_create", "rslam_destroy", "rslam_sync", "rslam_stream",
     "rslam_launch_count", "rslam_num_features", "rslam_state_dim", "rslam_upload_state", "rslam_download_state", "rslam_upload_patches",
-    "rslam_download_features", "rslam_download_H", "rslam_set_matches", "rslam_set_image", "rslam_begin_frame", "rslam_ekf_prediction",
+    "rslam_download_features", "rslam_upload_feature_init", "rslam_set_patch_warp", "rslam_download_patches", "rslam_debug_scratch", "rslam_download_H", "rslam_set_matches", "rslam_set_image", "rslam_begin_frame", "rslam_ekf_prediction",
     "rslam_search_ic_matches", "rslam_ransac_hypotheses", "rslam_ransac_result_get", "rslam_update_li", "rslam_rescue_hi", "rslam_update_hi",
     "rslam_frame", "rslam_set_graph", "rslam_profile_enable", "rslam_profile_read", "rslam_download_pose", "rslam_support_sweep", "rslam_sweep_mask",
 ]
@@ -73,6 +73,9 @@ def load():
     L.rslam_download_state.argtypes = [vp, ci, ci, vp, vp, ci]
     L.rslam_upload_patches.argtypes = [vp, ci, vp, ci]
     L.rslam_download_features.argtypes = [vp, ci, vp, vp, vp, vp, vp]
+    L.rslam_upload_feature_init.argtypes = [vp, ci, vp, vp, vp, vp, ci]
+    L.rslam_set_patch_warp.argtypes = [vp, ci]
+    L.rslam_download_patches.argtypes = [vp, ci, vp, ci]
     L.rslam_download_H.argtypes = [vp, ci, vp, vp]
     L.rslam_set_matches.argtypes = [vp, ci, vp, vp]
     L.rslam_set_image.argtypes = [vp, ci, vp, ci, ci, ci, ci]
@@ -174,6 +177,22 @@ class Filter:
     def upload_patches(self, patches, b=0):
         p = np.ascontiguousarray(patches, dtype=np.float64)
         self._ck(self.L.rslam_upload_patches(self.h, b, _p(p), p.shape[0]))
+
+    def upload_feature_init(self, patches41, r_wc, R_wc, uv, b=0):
+        p = np.ascontiguousarray(patches41, dtype=np.uint8)
+        r = np.ascontiguousarray(r_wc, dtype=np.float64)
+        R = np.ascontiguousarray(R_wc, dtype=np.float64)
+        u = np.ascontiguousarray(uv, dtype=np.float64)
+        self._ck(self.L.rslam_upload_feature_init(self.h, b, _p(p), _p(r), _p(R), _p(u), p.shape[0]))
+
+    def set_patch_warp(self, enable):
+        self._ck(self.L.rslam_set_patch_warp(self.h, int(enable)))
+
+    def download_patches(self, b=0):
+        N = self.L.rslam_num_features(self.h, b)
+        out = np.zeros((N, 13, 13), dtype=np.float32)
+        self._ck(self.L.rslam_download_patches(self.h, b, _p(out), N))
+        return out
 
     def features(self, b=0):
         N = self.L.rslam_num_features(self.h, b)

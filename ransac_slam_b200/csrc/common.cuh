@@ -54,6 +54,10 @@ struct DevFilter {
     int* times_predicted;
     int* times_measured;
     float* patch;  // N x 169 row-major (r*13+c) predicted appearance
+    // appearance at initialisation (only needed when the predicted patch is warped on the device, pred_patch_fc)
+    unsigned char* patch_init;  // N x 41 x 41 row-major
+    double* init_pose;          // N x 14: r_wc(3), R_wc row-major(9), uv(2)
+    int* last_id;               // N: index of the latest inverse-depth feature <= i (-1 if none): XYZ_w actually used (quirk Q3)
     // image (may be shared between filters)
     const unsigned char* image;
     int img_rows, img_cols, img_stride, pad1;

@@ -377,6 +377,159 @@ __global__ void __launch_bounds__(128) k_predict(DevFilter* Fs, CamDev cam, ParD
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// (a4) predicted appearance: Tracking::pred_patch_fc (src/Tracking.cpp:164-278) -- SURVEY 8(f) next row 1.
+// One CTA per feature, one thread per pixel of the 13 x 13 predicted patch.  The 41 x 41 initial patch is warped by the
+// plane-induced homography K (R12 - t12 n^T / d) K^-1 between the initialisation camera and the predicted camera, through the
+// undistort / distort model, and sampled exactly like cv::remap(INTER_LINEAR, BORDER_CONSTANT 0) on CV_32F data: map coordinates
+// cast to float, quantised to 1/32 px with round-half-even, float weights, out-of-range taps = 0.  Geometry in fp64.
+// Reference quirks kept: Q11 (MATLAB -1 in the patch offset), Q12 (translation R*r), Q13 (truncating cv::Range), Q3 (stale XYZ_w
+// for cartesian features).
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void undistort_dev(const CamDev& cam, double ud, double vd, double& uu, double& vu) {  // src/ExtendKF.cpp:266-285
+    const double xd = (ud - cam.Cx) * cam.dx, yd = (vd - cam.Cy) * cam.dy;
+    const double rd = sqrt(xd * xd + yd * yd);
+    const double rd2 = rd * rd;
+    const double D = 1 + cam.k1 * rd2 + cam.k2 * (rd2 * rd2);
+    uu = xd * D / cam.dx + cam.Cx;
+    vu = yd * D / cam.dy + cam.Cy;
+}
+__device__ void inv4_dev(const double* m, double* o) {  // closed-form 4x4 inverse, row-major
+    const double a00 = m[0], a01 = m[1], a02 = m[2], a03 = m[3], a10 = m[4], a11 = m[5], a12 = m[6], a13 = m[7];
+    const double a20 = m[8], a21 = m[9], a22 = m[10], a23 = m[11], a30 = m[12], a31 = m[13], a32 = m[14], a33 = m[15];
+    const double s0 = a00 * a11 - a10 * a01, s1 = a00 * a12 - a10 * a02, s2 = a00 * a13 - a10 * a03;
+    const double s3 = a01 * a12 - a11 * a02, s4 = a01 * a13 - a11 * a03, s5 = a02 * a13 - a12 * a03;
+    const double c5 = a22 * a33 - a32 * a23, c4 = a21 * a33 - a31 * a23, c3 = a21 * a32 - a31 * a22;
+    const double c2 = a20 * a33 - a30 * a23, c1 = a20 * a32 - a30 * a22, c0 = a20 * a31 - a30 * a21;
+    const double id = 1.0 / (s0 * c5 - s1 * c4 + s2 * c3 + s3 * c2 - s4 * c1 + s5 * c0);
+    o[0] = (a11 * c5 - a12 * c4 + a13 * c3) * id;
+    o[1] = (-a01 * c5 + a02 * c4 - a03 * c3) * id;
+    o[2] = (a31 * s5 - a32 * s4 + a33 * s3) * id;
+    o[3] = (-a21 * s5 + a22 * s4 - a23 * s3) * id;
+    o[4] = (-a10 * c5 + a12 * c2 - a13 * c1) * id;
+    o[5] = (a00 * c5 - a02 * c2 + a03 * c1) * id;
+    o[6] = (-a30 * s5 + a32 * s2 - a33 * s1) * id;
+    o[7] = (a20 * s5 - a22 * s2 + a23 * s1) * id;
+    o[8] = (a10 * c4 - a11 * c2 + a13 * c0) * id;
+    o[9] = (-a00 * c4 + a01 * c2 - a03 * c0) * id;
+    o[10] = (a30 * s4 - a31 * s2 + a33 * s0) * id;
+    o[11] = (-a20 * s4 + a21 * s2 - a23 * s0) * id;
+    o[12] = (-a10 * c3 + a11 * c1 - a12 * c0) * id;
+    o[13] = (a00 * c3 - a01 * c1 + a02 * c0) * id;
+    o[14] = (-a30 * s3 + a31 * s1 - a32 * s0) * id;
+    o[15] = (a20 * s3 - a21 * s1 + a22 * s0) * id;
+}
+__device__ __forceinline__ void homog4_dev(const double* R, const double* r, double* H) {  // [R 0;0 1] * [I r;0 1] = [R, R r; 0 1]
+    for (int i = 0; i < 3; i++) {
+        H[4 * i] = R[3 * i];
+        H[4 * i + 1] = R[3 * i + 1];
+        H[4 * i + 2] = R[3 * i + 2];
+        H[4 * i + 3] = R[3 * i] * r[0] + R[3 * i + 1] * r[1] + R[3 * i + 2] * r[2];
+    }
+    H[12] = H[13] = H[14] = 0.0;
+    H[15] = 1.0;
+}
+__device__ __forceinline__ void mat3_mul(const double* A, const double* B, double* C) {
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) C[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+}
+
+__global__ void __launch_bounds__(192) k_pred_patch(DevFilter* Fs, CamDev cam) {
+    DevFilter& F = Fs[blockIdx.y];
+    const int i = blockIdx.x;
+    if (i >= F.N || !F.has_h[i] || F.patch_init == nullptr) return;
+    __shared__ double sHm[9];
+    __shared__ int s_org[3];  // xs, ys, ok
+    __shared__ unsigned char sp[41 * 41];
+    const int tid = threadIdx.x;
+    float* out = F.patch + (size_t)i * kPatchPix;
+    const double h0 = F.h[2 * i], h1 = F.h[2 * i + 1];
+    const bool inside = (h0 > kHalfPatch) && (h0 < (cam.nCols - kHalfPatch)) && (h1 > kHalfPatch) && (h1 < (cam.nRows - kHalfPatch));
+    if (!inside) {  // src/Tracking.cpp:275
+        if (tid < kPatchPix) out[tid] = 0.f;
+        return;
+    }
+    for (int e = tid; e < 41 * 41; e += blockDim.x) sp[e] = F.patch_init[(size_t)i * 1681 + e];
+    const double* ip = F.init_pose + (size_t)i * 14;
+    const double uvf0 = ip[12], uvf1 = ip[13];
+    if (tid == 0) {
+        const double* x = F.x_km1;
+        double Rwc[9], Hpf[16], Hk[16], Hpfi[16], Hkk[16];
+        q2r_dev(x + 3, Rwc);
+        homog4_dev(ip + 3, ip, Hpf);
+        homog4_dev(Rwc, x, Hk);
+        inv4_dev(Hpf, Hpfi);
+        for (int a = 0; a < 4; a++)
+            for (int b = 0; b < 4; b++) {
+                double s = 0;
+                for (int k = 0; k < 4; k++) s += Hpfi[4 * a + k] * Hk[4 * k + b];
+                Hkk[4 * a + b] = s;
+            }
+        const double fz = -cam.f / cam.dx;
+        double n1[3] = {uvf0 - cam.Cx, uvf1 - cam.Cy, fz};
+        double nn = sqrt(n1[0] * n1[0] + n1[1] * n1[1] + n1[2] * n1[2]);
+        double n[3] = {n1[0] / nn, n1[1] / nn, n1[2] / nn};
+        const double n2[4] = {h0 - cam.Cx, h1 - cam.Cy, fz, 1.0};
+        double nt4[4];
+        for (int a = 0; a < 4; a++) nt4[a] = Hkk[4 * a] * n2[0] + Hkk[4 * a + 1] * n2[1] + Hkk[4 * a + 2] * n2[2] + Hkk[4 * a + 3] * n2[3];
+        double nt[3] = {nt4[0] / nt4[3], nt4[1] / nt4[3], nt4[2] / nt4[3]};
+        const double ntn = sqrt(nt[0] * nt[0] + nt[1] * nt[1] + nt[2] * nt[2]);
+        double ns[3] = {n[0] + nt[0] / ntn, n[1] + nt[1] / ntn, n[2] + nt[2] / ntn};
+        const double nsn = sqrt(ns[0] * ns[0] + ns[1] * ns[1] + ns[2] * ns[2]);
+        for (int a = 0; a < 3; a++) n[a] = ns[a] / nsn;
+        // XYZ_w of the feature (Q3: cartesian features reuse the value of the previous inverse-depth feature)
+        double X[3] = {0, 0, 0};
+        const int li = F.last_id[i];
+        if (li >= 0) {
+            const double* y = x + F.foff[li];
+            const double st = sin(y[3]), ct = cos(y[3]), sph = sin(y[4]), cph = cos(y[4]);
+            const double m3[3] = {cph * st, -sph, cph * ct};
+            for (int a = 0; a < 3; a++) X[a] = y[a] + (1.0 / y[5]) * m3[a];
+        }
+        double Xk[4];
+        for (int a = 0; a < 4; a++) Xk[a] = Hpfi[4 * a] * X[0] + Hpfi[4 * a + 1] * X[1] + Hpfi[4 * a + 2] * X[2] + Hpfi[4 * a + 3];
+        const double d = -(n[0] * (Xk[0] / Xk[3]) + n[1] * (Xk[1] / Xk[3]) + n[2] * (Xk[2] / Xk[3]));
+        const double fk = cam.f / cam.dx;  // cam.K << f/d, 0, Cx ; 0, f/d, Cy ; 0 0 1 (src/System.cpp:58)
+        const double K[9] = {fk, 0, cam.Cx, 0, fk, cam.Cy, 0, 0, 1};
+        double Ki[9], M[9], T[9], Hm[9], Hmi[9];
+        inv3_dev(K, Ki);
+        for (int a = 0; a < 3; a++)
+            for (int b = 0; b < 3; b++) M[3 * a + b] = Hkk[4 * a + b] - (Hkk[4 * a + 3] * n[b]) / d;
+        mat3_mul(K, M, T);
+        mat3_mul(T, Ki, Hm);
+        inv3_dev(Hm, Hmi);
+        double uu, vu;
+        undistort_dev(cam, uvf0, uvf1, uu, vu);
+        const double w0 = Hmi[0] * uu + Hmi[1] * vu + Hmi[2], w1 = Hmi[3] * uu + Hmi[4] * vu + Hmi[5], w2 = Hmi[6] * uu + Hmi[7] * vu + Hmi[8];
+        double c2u, c2v;
+        distort_dev(cam, w0 / w2, w1 / w2, c2u, c2v);
+        const int xs = (int)(c2u - kHalfPatch), xe = (int)(c2u + kHalfPatch), ys = (int)(c2v - kHalfPatch), ye = (int)(c2v + kHalfPatch);
+        s_org[0] = xs;
+        s_org[1] = ys;
+        s_org[2] = (xe - xs + 1 == kPatch) && (ye - ys + 1 == kPatch);
+        for (int a = 0; a < 9; a++) sHm[a] = Hm[a];
+    }
+    __syncthreads();
+    if (tid >= kPatchPix) return;
+    if (!s_org[2]) {
+        out[tid] = 0.f;
+        return;
+    }
+    const int r = tid / kPatch, c = tid % kPatch;
+    double uu, vu;
+    undistort_dev(cam, (double)(s_org[0] + c), (double)(s_org[1] + r), uu, vu);
+    const double w0 = sHm[0] * uu + sHm[1] * vu + sHm[2], w1 = sHm[3] * uu + sHm[4] * vu + sHm[5], w2 = sHm[6] * uu + sHm[7] * vu + sHm[8];
+    double c1u, c1v;
+    distort_dev(cam, w0 / w2, w1 / w2, c1u, c1v);
+    const float mx = (float)(c1u - (uvf0 - 20 - 1)), my = (float)(c1v - (uvf1 - 20 - 1));
+    const int sx = __float2int_rn(mx * 32.0f), sy = __float2int_rn(my * 32.0f);
+    const int ix = sx >> 5, iy = sy >> 5;
+    const float fx = (float)(sx & 31) / 32.0f, fy = (float)(sy & 31) / 32.0f;
+    const float w00 = (1.f - fy) * (1.f - fx), w01 = (1.f - fy) * fx, w10 = fy * (1.f - fx), w11 = fy * fx;
+    auto tap = [&](int yy, int xx) -> float { return (xx < 0 || yy < 0 || xx >= 41 || yy >= 41) ? 0.f : (float)sp[yy * 41 + xx]; };
+    out[tid] = tap(iy, ix) * w00 + tap(iy, ix + 1) * w01 + tap(iy + 1, ix) * w10 + tap(iy + 1, ix + 1) * w11;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // (b) active search: Tracking::matching (src/Tracking.cpp:279-351) + Converter::corrcoef_opencv (src/Converter.cpp:188-209).
 // One CTA per feature.  The search window and the predicted 13x13 patch are staged in shared memory; each thread scores
 // candidates with one-pass sums (sum b, sum b^2 exact in integers; sum a*b in fp64); block arg-max keeps the FIRST maximum in

@@ -58,6 +58,7 @@ struct rslam_filter {
     size_t sup_h_cap = 0;
     unsigned long long* d_key = nullptr;  // [0] key, [1] pair counter
     bool have_image = false;
+    bool warp_patches = false;  // run pred_patch_fc on the device before the search
     bool upd_ws = false;
     int hN = 0, hn = 0;  // max over filters of the uploaded N / n
     bool descr_dirty = false;
@@ -294,6 +295,9 @@ int rslam_create(const rslam_camera* cam, const rslam_params* par, int max_featu
     unsigned char *has_h, *ic, *li, *hi;
     float* patch;
     unsigned* masks;
+    unsigned char* patch_init;
+    double* init_pose;
+    int* last_id;
     const size_t psz = (size_t)f->ldp * n;
 #define A(ptr, cnt)                                       \
     if ((rc = dev_alloc(f, &ptr, (size_t)(cnt)*B))) {    \
@@ -303,6 +307,7 @@ int rslam_create(const rslam_camera* cam, const rslam_params* par, int max_featu
     A(P, psz) A(xkk, n) A(xkm1, n) A(h, 2 * N) A(Hc, 14 * N) A(Hf, 12 * N) A(S, 4 * N) A(z, 2 * N) A(hyp_ab, 13 * N) A(hyp_xcam, 7 * N) A(Jn, 32)
     A(ftype, N) A(foff, N) A(tp, N) A(tm, N) A(ic_list, N) A(id_list, N) A(id_pos, N) A(support, N) A(ctl, CTL_SIZE) A(upd_list, N)
     A(has_h, N) A(ic, N) A(li, N) A(hi, N) A(patch, (size_t)N * kPatchPix) A(masks, (size_t)N * f->mwords)
+    A(patch_init, (size_t)N * 1681) A(init_pose, (size_t)N * 14) A(last_id, N)
 #undef A
     if ((rc = dev_alloc(f, &f->dF, (size_t)B))) {
         rslam_destroy(f);
@@ -339,6 +344,9 @@ int rslam_create(const rslam_camera* cam, const rslam_params* par, int max_featu
         D.times_measured = tm + (size_t)N * b;
         D.patch = patch + (size_t)N * kPatchPix * b;
         D.image = nullptr;
+        D.patch_init = patch_init + (size_t)N * 1681 * b;
+        D.init_pose = init_pose + (size_t)N * 14 * b;
+        D.last_id = last_id + (size_t)N * b;
         D.ic_list = ic_list + (size_t)N * b;
         D.id_list = id_list + (size_t)N * b;
         D.id_pos = id_pos + (size_t)N * b;
@@ -412,9 +420,15 @@ int rslam_upload_state(rslam_filter* f, int b, int which, const double* x, const
     const bool shape_changed = (D.n != n) || (D.N != N);
     D.n = n;
     D.N = N;
+    std::vector<int> lastid(N, -1);
+    for (int i = 0, last = -1; i < N; i++) {
+        if (types[i] == 0) last = i;
+        lastid[i] = last;
+    }
     if (N) {
         CK(cudaMemcpyAsync(D.ftype, types.data(), sizeof(int) * N, cudaMemcpyHostToDevice, f->stream));
         CK(cudaMemcpyAsync(D.foff, offs.data(), sizeof(int) * N, cudaMemcpyHostToDevice, f->stream));
+        CK(cudaMemcpyAsync(D.last_id, lastid.data(), sizeof(int) * N, cudaMemcpyHostToDevice, f->stream));
     }
     CK(cudaMemcpyAsync(which ? D.x_km1 : D.x_kk, x, sizeof(double) * n, cudaMemcpyDefault, f->stream));
     if (P) {
@@ -467,6 +481,37 @@ int rslam_upload_patches(rslam_filter* f, int b, const double* patches, int N) {
     std::vector<float> tmp((size_t)N * kPatchPix);
     for (size_t i = 0; i < tmp.size(); i++) tmp[i] = (float)patches[i];  // Converter::toCvMat_f (src/Converter.cpp:83-94)
     CK(cudaMemcpyAsync(f->hF[b].patch, tmp.data(), sizeof(float) * tmp.size(), cudaMemcpyHostToDevice, f->stream));
+    CK(cudaStreamSynchronize(f->stream));
+    return RSLAM_OK;
+}
+
+int rslam_upload_feature_init(rslam_filter* f, int b, const uint8_t* patches41, const double* r_wc, const double* R_wc, const double* uv, int N) {
+    if (!f || b < 0 || b >= f->B || !patches41 || !r_wc || !R_wc || !uv || N < 0 || N > f->Nmax) return fail(RSLAM_ERR_INVALID, "rslam_upload_feature_init: bad arguments");
+    CK(cudaSetDevice(f->device));
+    std::vector<double> pose((size_t)N * 14);
+    for (int i = 0; i < N; i++) {
+        for (int k = 0; k < 3; k++) pose[(size_t)i * 14 + k] = r_wc[3 * i + k];
+        for (int k = 0; k < 9; k++) pose[(size_t)i * 14 + 3 + k] = R_wc[9 * i + k];
+        pose[(size_t)i * 14 + 12] = uv[2 * i];
+        pose[(size_t)i * 14 + 13] = uv[2 * i + 1];
+    }
+    CK(cudaMemcpyAsync(f->hF[b].patch_init, patches41, (size_t)N * 1681, cudaMemcpyHostToDevice, f->stream));
+    CK(cudaMemcpyAsync(f->hF[b].init_pose, pose.data(), sizeof(double) * pose.size(), cudaMemcpyHostToDevice, f->stream));
+    CK(cudaStreamSynchronize(f->stream));
+    return RSLAM_OK;
+}
+
+int rslam_set_patch_warp(rslam_filter* f, int enable) {
+    if (!f) return fail(RSLAM_ERR_INVALID, "null handle");
+    f->warp_patches = enable != 0;
+    f->graph_key = -1;
+    return RSLAM_OK;
+}
+
+int rslam_download_patches(rslam_filter* f, int b, float* patches, int N) {
+    if (!f || b < 0 || b >= f->B || !patches || N < 0 || N > f->Nmax) return fail(RSLAM_ERR_INVALID, "rslam_download_patches: bad arguments");
+    CK(cudaSetDevice(f->device));
+    CK(cudaMemcpyAsync(patches, f->hF[b].patch, sizeof(float) * (size_t)N * kPatchPix, cudaMemcpyDeviceToHost, f->stream));
     CK(cudaStreamSynchronize(f->stream));
     return RSLAM_OK;
 }
@@ -595,6 +640,7 @@ int rslam_search_ic_matches(rslam_filter* f) {
     CK(cudaSetDevice(f->device));
     if (f->hN == 0) return RSLAM_OK;
     LAUNCH(f, k_predict, dim3(cdiv(f->hN, 128), f->B), 128, 0, f->dF, f->camd, f->pard, 0);
+    if (f->warp_patches) LAUNCH(f, k_pred_patch, dim3(f->hN, f->B), 192, 0, f->dF, f->camd);
     if (f->have_image) LAUNCH(f, k_search, dim3(f->hN, f->B), 128, 0, f->dF, f->camd, f->pard);
     return check_launch();
 }
@@ -743,7 +789,7 @@ int rslam_frame(rslam_filter* f, const uint8_t* images, int rows, int cols, int 
         if ((rc = run_frame_stages(f, flags))) return rc;
         return check_launch();
     }
-    const long long key = ((long long)f->hN << 40) ^ ((long long)f->hn << 16) ^ ((long long)f->B << 4) ^ ((flags & 1) << 1) ^ (f->have_image ? 1 : 0);
+    const long long key = ((long long)f->hN << 40) ^ ((long long)f->hn << 16) ^ ((long long)f->B << 4) ^ ((flags & 1) << 1) ^ (f->have_image ? 1 : 0) ^ (f->warp_patches ? 4 : 0);
     if (!f->graph_exec || key != f->graph_key) {
         if (f->graph_exec) {
             cudaGraphExecDestroy(f->graph_exec);

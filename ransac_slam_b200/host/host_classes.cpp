@@ -117,6 +117,26 @@ int ExtendKF::sync_to_device() {
     const int n = x_k_k.rows();
     status_ = rslam_upload_state(dev_, 0, 0, x_k_k.data(), p_k_k.data(), n, p_k_k.rows(), types.data(), N);
     if (status_ == 0 && N) status_ = rslam_upload_patches(dev_, 0, patches.data(), N);
+    // when every feature carries its 41 x 41 initialisation patch (Map::initialize_a_features, src/Map.cpp:286-294) the predicted
+    // appearance is warped on the device (Tracking::pred_patch_fc); otherwise patch_when_matching is used as given
+    bool have_init = N > 0;
+    for (int i = 0; i < N && have_init; i++)
+        have_init = features_info[i].patch_when_initialized.rows() == 41 && features_info[i].patch_when_initialized.cols() == 41;
+    if (status_ == 0 && have_init) {
+        std::vector<uint8_t> p41((size_t)N * 1681);
+        std::vector<double> r(3 * (size_t)N), R(9 * (size_t)N), uv(2 * (size_t)N);
+        for (int i = 0; i < N; i++) {
+            const Feature& ft = features_info[i];
+            for (int a = 0; a < 41; a++)
+                for (int b = 0; b < 41; b++) p41[(size_t)i * 1681 + a * 41 + b] = (uint8_t)ft.patch_when_initialized(a, b);
+            for (int k = 0; k < 3; k++) r[3 * i + k] = ft.r_wc_when_initialized[k];
+            for (int k = 0; k < 9; k++) R[9 * i + k] = ft.R_wc_when_initialized[k];
+            uv[2 * i] = ft.uv_when_initialized[0];
+            uv[2 * i + 1] = ft.uv_when_initialized[1];
+        }
+        status_ = rslam_upload_feature_init(dev_, 0, p41.data(), r.data(), R.data(), uv.data(), N);
+    }
+    if (status_ == 0) status_ = rslam_set_patch_warp(dev_, have_init ? 1 : 0);
     return status_;
 }
 

@@ -247,3 +247,46 @@ def test_full_size_properties_N2000():
     xh, Ph = f.download_state()
     assert np.array_equal(Ph, Ph.T) and np.trace(Ph) <= np.trace(Pl) and np.isfinite(Ph).all()
     assert tr0 > 0
+
+
+def test_patch_warp_matches_oracle_remap():
+    """Tracking::pred_patch_fc on the device (homography warp + cv::remap-compatible sampling) against the oracle, whose remap is
+    pinned bit-exactly to cv2 (tests/golden/cv_fixtures.npz).  Then a search with the warped patches on both sides."""
+    N = 40
+    scene, x, P = synth.random_spd_state(N, seed=111)
+    rng = np.random.default_rng(5)
+    # smooth-ish 41x41 appearance so that the warped patch still correlates with the image content
+    init = rng.integers(0, 256, (N, 41, 41)).astype(np.uint8)
+    o = O.OracleFilter(scene.cam.as9(), std_z=scene.std_z, quirks=O.Q_ALL, sparse=False, fast_corr=True, warp_patches=True)
+    for i in range(N):
+        o.add_feature(0, init[i], None, scene.x0[:3], np.eye(3), scene.uv0[i])
+    o.set_state(x, P, prior=True)
+    g = H.gpu_from(scene, x, P)
+    g.upload_feature_init(init, np.tile(scene.x0[:3], (N, 1)), np.tile(np.eye(3).reshape(1, 9), (N, 1)), scene.uv0)
+    g.set_patch_warp(True)
+    o.search_ic_matches(None)
+    g.search_ic_matches()
+    pg = g.download_patches()
+    fo = o.features()
+    assert fo["has_h"].sum() >= N - 2
+    same = 0
+    for i in np.flatnonzero(fo["has_h"]):
+        po = o.patch_matching(i)
+        assert po.std() > 0
+        d = np.abs(pg[i].astype(np.float64) - po)
+        # identical sampling except where a map coordinate sits within rounding noise of a 1/32-px quantisation boundary
+        assert (d == 0).mean() > 0.97 and d.max() < 12.0, (i, (d == 0).mean(), d.max())
+        same += int((d == 0).all())
+    assert same >= 0.8 * fo["has_h"].sum()
+    # build an image that contains the oracle-predicted appearance at a pasted location and search on both sides
+    img = synth.background(scene.cam).copy()
+    for i in np.flatnonzero(fo["has_h"]):
+        cx, cy = np.rint(fo["h"][i]).astype(int)
+        if 7 <= cx < scene.cam.nCols - 7 and 7 <= cy < scene.cam.nRows - 7:
+            img[cy - 6:cy + 7, cx - 6:cx + 7] = np.clip(np.rint(o.patch_matching(i)), 0, 255).astype(np.uint8)
+    o.search_ic_matches(img)
+    g.set_image(img)
+    g.search_ic_matches()
+    f2o, f2g = o.features(), g.features()
+    assert f2o["ic"].sum() >= N // 2
+    assert (f2o["ic"] == f2g["ic"]).all() and (f2o["z"][f2o["ic"]] == f2g["z"][f2g["ic"]]).all()
