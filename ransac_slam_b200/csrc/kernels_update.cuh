@@ -604,17 +604,19 @@ __global__ void __launch_bounds__(WM * 64) k_trsm_ll(DevFilter* Fs) {
 // sm_100a.  3-stage cp.async pipeline, padded smem (+4 doubles per k-row) so that the fragment loads are bank-conflict free.
 // Two tile shapes: 128 x 128 (8 warps, warp tile 64 x 32) for large problems, 64 x 64 (4 warps, 32 x 32) when the large tiling
 // would leave most SMs idle (the 100-feature configuration).
-constexpr int GBK = 16, GSTAGES = 3, GPAD = 4;
-template <int BM>
+constexpr int GBK = 16, GSTAGES = 4, GPAD = 4;
+template <int BM, int BN>
 struct GemmCfg {
-    static constexpr int kBM = BM, kBN = BM;
-    static constexpr int kThreads = BM == 128 ? 256 : 128;
-    static constexpr int kWM = 2, kWN = BM == 128 ? 4 : 2;
+    static constexpr int kBM = BM, kBN = BN;
+    static constexpr int kWM = 2, kWN = BN / 32;            // warp grid; every warp owns (BM/2) x 32
+    static constexpr int kThreads = kWM * kWN * 32;
     static constexpr int kMT = BM / (8 * kWM), kNT = 4;
-    static constexpr int kLds = BM + GPAD;
-    static constexpr int kSmemBytes = GSTAGES * 2 * GBK * kLds * (int)sizeof(double);
+    static constexpr int kLdA = BM + GPAD, kLdB = BN + GPAD;  // == 8 (mod 32) words per k-row -> conflict-free fragment loads
+    static constexpr int kSmemBytes = GSTAGES * GBK * (kLdA + kLdB) * (int)sizeof(double);
+    // 128 x 64 tiles with 4 warps: two CTAs are resident per SM, so one CTA's prologue / epilogue / barrier bubbles are
+    // covered by the other CTA's DMMA stream (the single 128 x 128 CTA left the tensor pipe ~20 % idle)
+    static constexpr int kMinBlocks = (BM == 128 && BN == 64) ? 2 : 1;
 };
-constexpr int GBM = 128, GBN = 128;
 
 enum GemmMode { GEMM_SYRK_P = 0, GEMM_CHOL_TRAIL = 1 };
 
@@ -655,56 +657,61 @@ __device__ __forceinline__ bool gemm_setup(const DevFilter& F, int mode, int ste
 // In SYRK mode the product is taken over the n+1 rows of W: entries (n, c) of V V^T are (V y)[c] and update the state,
 //   x_k_k[c] = x0[c] + (V y)[c]   (x0 = x_k_km1 for the low-innovation update, x_k_k for the high-innovation one),
 // everything else is the covariance downdate P -= V V^T.
-template <int BM>
-__global__ void __launch_bounds__(GemmCfg<BM>::kThreads, 1) k_gemm_dmma(DevFilter* Fs, int mode, int step) {
-    using Cfg = GemmCfg<BM>;
-    constexpr int BN = Cfg::kBN, LDS = Cfg::kLds, MT = Cfg::kMT, NT = Cfg::kNT, THREADS = Cfg::kThreads;
+template <int BM, int BN>
+__global__ void __launch_bounds__(GemmCfg<BM, BN>::kThreads, GemmCfg<BM, BN>::kMinBlocks) k_gemm_dmma(DevFilter* Fs, int mode, int step) {
+    using Cfg = GemmCfg<BM, BN>;
+    constexpr int LDA = Cfg::kLdA, LDB = Cfg::kLdB, MT = Cfg::kMT, NT = Cfg::kNT, THREADS = Cfg::kThreads;
     const DevFilter& F = Fs[blockIdx.z];
     GemmProb g;
     if (!gemm_setup(F, mode & 0xff, step, g)) return;
     int ti, tj;
     const int tm = (g.M + BM - 1) / BM, tn = (g.N + BN - 1) / BN;
     if (g.lower) {
+        // tile row i needs column tiles 0 .. min(R*(i+1), tn) - 1 with R = BM / BN; rows are enumerated back to back
+        constexpr int RT = BM / BN;
         const long long t = blockIdx.x;
-        if (t >= (long long)tm * (tm + 1) / 2) return;
-        int i = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
-        while ((long long)i * (i + 1) / 2 > t) i--;
-        while ((long long)(i + 1) * (i + 2) / 2 <= t) i++;
+        int i = (int)((sqrt(1.0 + 8.0 * (double)t / RT) - 1.0) * 0.5);
+        if (i < 0) i = 0;
+        while (i > 0 && (long long)RT * i * (i + 1) / 2 > t) i--;
+        while ((long long)RT * (i + 1) * (i + 2) / 2 <= t) i++;
+        if (i >= tm) return;
         ti = i;
-        tj = (int)(t - (long long)i * (i + 1) / 2);
+        tj = (int)(t - (long long)RT * i * (i + 1) / 2);
+        if (tj >= tn) return;
     } else {
         if ((long long)blockIdx.x >= (long long)tm * tn) return;
         ti = blockIdx.x % tm;
         tj = blockIdx.x / tm;
     }
     extern __shared__ __align__(16) double gsm[];
-    double* As = gsm;                          // [stage][GBK][LDS]
-    double* Bs = gsm + GSTAGES * GBK * LDS;    // [stage][GBK][LDS]
+    double* As = gsm;                          // [stage][GBK][LDA]
+    double* Bs = gsm + GSTAGES * GBK * LDA;    // [stage][GBK][LDB]
     const int m0 = ti * BM, n0 = tj * BN;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm0 = (warp % Cfg::kWM) * (MT * 8), wn0 = (warp / Cfg::kWM) * (NT * 8);
     const int nkt = (g.K + GBK - 1) / GBK;
-    constexpr int CHUNKS = GBK * (BM / 2);
+    constexpr int A_CHUNKS = GBK * (BM / 2), B_CHUNKS = GBK * (BN / 2);
+    static_assert(A_CHUNKS % THREADS == 0 && B_CHUNKS % THREADS == 0, "tile loads must divide evenly");
 
     auto load_stage = [&](int stage, int kt) {
         const int k0 = kt * GBK;
 #pragma unroll
-        for (int it = 0; it < CHUNKS / THREADS; it++) {
+        for (int it = 0; it < A_CHUNKS / THREADS; it++) {
             const int ch = tid + it * THREADS;
             const int kc = ch / (BM / 2), r2 = ch % (BM / 2);
             const int row = m0 + 2 * r2, col = k0 + kc;
             const bool v = (row < g.M) && (col < g.K);
             const double* src = v ? (g.A + row + (size_t)col * g.lda) : g.A;
-            cp_async16(&As[(stage * GBK + kc) * LDS + 2 * r2], src, v);
+            cp_async16(&As[(stage * GBK + kc) * LDA + 2 * r2], src, v);
         }
 #pragma unroll
-        for (int it = 0; it < CHUNKS / THREADS; it++) {
+        for (int it = 0; it < B_CHUNKS / THREADS; it++) {
             const int ch = tid + it * THREADS;
-            const int kc = ch / (BM / 2), r2 = ch % (BM / 2);
+            const int kc = ch / (BN / 2), r2 = ch % (BN / 2);
             const int row = n0 + 2 * r2, col = k0 + kc;
             const bool v = (row < g.N) && (col < g.K);
             const double* src = v ? (g.B + row + (size_t)col * g.ldb) : g.B;
-            cp_async16(&Bs[(stage * GBK + kc) * LDS + 2 * r2], src, v);
+            cp_async16(&Bs[(stage * GBK + kc) * LDB + 2 * r2], src, v);
         }
     };
 
@@ -727,16 +734,16 @@ __global__ void __launch_bounds__(GemmCfg<BM>::kThreads, 1) k_gemm_dmma(DevFilte
             if (nk < nkt) load_stage(nk % GSTAGES, nk);
             cp_async_commit();
         }
-        const double* as = As + (kt % GSTAGES) * GBK * LDS;
-        const double* bs = Bs + (kt % GSTAGES) * GBK * LDS;
+        const double* as = As + (kt % GSTAGES) * GBK * LDA;
+        const double* bs = Bs + (kt % GSTAGES) * GBK * LDB;
 #pragma unroll
         for (int ks = 0; ks < GBK / 4; ks++) {
             const int krow = ks * 4 + (lane & 3);
             double af[MT], bf[NT];
 #pragma unroll
-            for (int mt = 0; mt < MT; mt++) af[mt] = as[krow * LDS + wm0 + mt * 8 + (lane >> 2)];
+            for (int mt = 0; mt < MT; mt++) af[mt] = as[krow * LDA + wm0 + mt * 8 + (lane >> 2)];
 #pragma unroll
-            for (int nt = 0; nt < NT; nt++) bf[nt] = bs[krow * LDS + wn0 + nt * 8 + (lane >> 2)];
+            for (int nt = 0; nt < NT; nt++) bf[nt] = bs[krow * LDB + wn0 + nt * 8 + (lane >> 2)];
 #pragma unroll
             for (int mt = 0; mt < MT; mt++)
 #pragma unroll

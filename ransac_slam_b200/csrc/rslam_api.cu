@@ -194,12 +194,13 @@ int run_update(rslam_filter* f, int which) {
             const int rem = kmax - kNB * (s + 1);
             if (rem > 0) {
                 const int tm = cdiv(rem, 128);
-                LAUNCH_N(f, "k_gemm_dmma/chol_trail", k_gemm_dmma<128>, dim3(tm * (tm + 1) / 2, 1, B), 256, GemmCfg<128>::kSmemBytes, f->dF, (int)GEMM_CHOL_TRAIL, s);
+                LAUNCH_N(f, "k_gemm_dmma/chol_trail", (k_gemm_dmma<128, 64>), dim3(tm * (tm + 1), 1, B), (GemmCfg<128, 64>::kThreads), (GemmCfg<128, 64>::kSmemBytes), f->dF,
+                         (int)GEMM_CHOL_TRAIL, s);
             }
         }
     }
-    if (cdiv(n + 1, 96) * B >= 100) {
-        LAUNCH_N(f, "k_trsm_ll", (k_trsm_ll<96, 4>), dim3(cdiv(n + 1, 96), B), 256, (TrsmCfg<96, 4>::kSmemBytes), f->dF);
+    if (cdiv(n + 1, 48) * B >= 200) {  // 48-row CTAs, two resident per SM: one CTA's barriers / diagonal step hide behind the other's DMMA stream
+        LAUNCH_N(f, "k_trsm_ll", (k_trsm_ll<48, 2>), dim3(cdiv(n + 1, 48), B), 128, (TrsmCfg<48, 2>::kSmemBytes), f->dF);
     } else {
         LAUNCH_N(f, "k_trsm_ll", (k_trsm_ll<32, 2>), dim3(cdiv(n + 1, 32), B), 128, (TrsmCfg<32, 2>::kSmemBytes), f->dF);
     }
@@ -207,11 +208,11 @@ int run_update(rslam_filter* f, int which) {
     {
         const int tm = cdiv(n + 1, 128);
         const int smode = (int)GEMM_SYRK_P | (which << 8);
-        if ((long long)tm * (tm + 1) / 2 * B >= 96) {
-            LAUNCH_N(f, "k_gemm_dmma/syrk_P", k_gemm_dmma<128>, dim3(tm * (tm + 1) / 2, 1, B), 256, GemmCfg<128>::kSmemBytes, f->dF, smode, 0);
+        if ((long long)tm * (tm + 1) * B >= 192) {
+            LAUNCH_N(f, "k_gemm_dmma/syrk_P", (k_gemm_dmma<128, 64>), dim3(tm * (tm + 1), 1, B), (GemmCfg<128, 64>::kThreads), (GemmCfg<128, 64>::kSmemBytes), f->dF, smode, 0);
         } else {
             const int ts = cdiv(n + 1, 64);
-            LAUNCH_N(f, "k_gemm_dmma/syrk_P", k_gemm_dmma<64>, dim3(ts * (ts + 1) / 2, 1, B), 128, GemmCfg<64>::kSmemBytes, f->dF, smode, 0);
+            LAUNCH_N(f, "k_gemm_dmma/syrk_P", (k_gemm_dmma<64, 64>), dim3(ts * (ts + 1) / 2, 1, B), (GemmCfg<64, 64>::kThreads), (GemmCfg<64, 64>::kSmemBytes), f->dF, smode, 0);
         }
     }
     LAUNCH(f, k_upd_jnorm, dim3(1, B), 256, 0, f->dF, f->pard);
@@ -280,9 +281,9 @@ int rslam_create(const rslam_camera* cam, const rslam_params* par, int max_featu
     f->pard = ParDev{f->par.std_z, f->par.chi2_095_2, f->par.corr_threshold, f->par.p_spurious_free, f->par.max_ellipse_eig,
                      (f->par.std_a * 1.0) * (f->par.std_a * 1.0), (f->par.std_alpha * 1.0) * (f->par.std_alpha * 1.0), f->par.n_hyp_initial, f->par.quirks};
     CK(cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking));
-    CK(cudaFuncSetAttribute(k_gemm_dmma<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<128>::kSmemBytes));
-    CK(cudaFuncSetAttribute(k_gemm_dmma<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<64>::kSmemBytes));
-    CK(cudaFuncSetAttribute(k_trsm_ll<96, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TrsmCfg<96, 4>::kSmemBytes));
+    CK(cudaFuncSetAttribute(k_gemm_dmma<128, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<128, 64>::kSmemBytes));
+    CK(cudaFuncSetAttribute(k_gemm_dmma<64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<64, 64>::kSmemBytes));
+    CK(cudaFuncSetAttribute(k_trsm_ll<48, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TrsmCfg<48, 2>::kSmemBytes));
     CK(cudaFuncSetAttribute(k_trsm_ll<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TrsmCfg<32, 2>::kSmemBytes));
     CK(cudaFuncSetAttribute(k_chol_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPanelSmemBytes));
     CK(cudaFuncSetAttribute(k_chol_small, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholSmallSmemBytes));
