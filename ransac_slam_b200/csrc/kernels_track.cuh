@@ -104,7 +104,7 @@ __device__ void build_F_Q(const double* x, const ParDev& par, double* Fm /*13x13
         }
 }
 
-__global__ void __launch_bounds__(128) k_ekf_prediction(DevFilter* Fs, ParDev par) {
+__global__ void __launch_bounds__(128) k_ekf_prediction(DevFilter* Fs, ParDev par, int with_begin) {
     DevFilter& F = Fs[blockIdx.y];
     __shared__ double sF[169], sQ[169], sX[13], sP[169], sT[169];
     const int n = F.n;
@@ -135,6 +135,14 @@ __global__ void __launch_bounds__(128) k_ekf_prediction(DevFilter* Fs, ParDev pa
         if (threadIdx.x < 13) F.x_km1[threadIdx.x] = sX[threadIdx.x];
     }
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (with_begin && j < F.N) {  // Map::map_management step 2 (src/Map.cpp:34-55): counters + per-frame flag reset
+        if (F.has_h[j]) F.times_predicted[j] += 1;
+        if (F.li[j] || F.hi[j]) F.times_measured[j] += 1;
+        F.ic[j] = 0;
+        F.li[j] = 0;
+        F.hi[j] = 0;
+        F.has_h[j] = 0;
+    }
     if (j >= 13 && j < n) {
         F.x_km1[j] = F.x_kk[j];
         double v[13], o[13];
@@ -309,8 +317,19 @@ __global__ void __launch_bounds__(128) k_predict(DevFilter* Fs, CamDev cam, ParD
         }
     }
     if (!need_S) return;
-    // S = H P H^T over the 7 + fs structurally non-zero columns; T = H * P first (left to right)
+    // S = H P H^T over the 7 + fs structurally non-zero columns; T = H * P first (left to right).
+    // All 13 x 6 + 6 x 7 loads have compile-time trip counts (columns beyond fs are predicated to 0) so that they are issued as
+    // one batch: on the single-filter path this kernel is pure memory latency.
     const double* P = F.P;
+    double Pfc[6][7];  // P[off+k, j]   (feature rows, camera columns)
+    double Pff[6][6];  // P[off+k, off+j]
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+#pragma unroll
+        for (int j = 0; j < 7; j++) Pfc[k][j] = (k < fs) ? P[(off + k) + (size_t)j * ld] : 0.0;
+#pragma unroll
+        for (int j = 0; j < 6; j++) Pff[k][j] = (k < fs && j < fs) ? P[(off + k) + (size_t)(off + j) * ld] : 0.0;
+    }
     double T[2][13];
 #pragma unroll
     for (int j = 0; j < 7; j++) {
@@ -321,27 +340,27 @@ __global__ void __launch_bounds__(128) k_predict(DevFilter* Fs, CamDev cam, ParD
             s0 += Hc[k] * p;
             s1 += Hc[7 + k] * p;
         }
-        for (int k = 0; k < fs; k++) {
-            const double p = P[(off + k) + (size_t)j * ld];
-            s0 += Hf[k] * p;
-            s1 += Hf[6 + k] * p;
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            s0 += Hf[k] * Pfc[k][j];
+            s1 += Hf[6 + k] * Pfc[k][j];
         }
         T[0][j] = s0;
         T[1][j] = s1;
     }
-    for (int j = 0; j < fs; j++) {
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
         double s0 = 0, s1 = 0;
-        const double* pc = P + (size_t)(off + j) * ld;
 #pragma unroll
         for (int k = 0; k < 7; k++) {
-            const double p = pc[k];
+            const double p = Pfc[j][k];  // P[k, off+j] == P[off+j, k] (exactly symmetric storage)
             s0 += Hc[k] * p;
             s1 += Hc[7 + k] * p;
         }
-        for (int k = 0; k < fs; k++) {
-            const double p = pc[off + k];
-            s0 += Hf[k] * p;
-            s1 += Hf[6 + k] * p;
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            s0 += Hf[k] * Pff[k][j];
+            s1 += Hf[6 + k] * Pff[k][j];
         }
         T[0][7 + j] = s0;
         T[1][7 + j] = s1;
@@ -354,7 +373,8 @@ __global__ void __launch_bounds__(128) k_predict(DevFilter* Fs, CamDev cam, ParD
             double s = 0;
 #pragma unroll
             for (int j = 0; j < 7; j++) s += T[a][j] * Hc[b * 7 + j];
-            for (int j = 0; j < fs; j++) s += T[a][7 + j] * Hf[b * 6 + j];
+#pragma unroll
+            for (int j = 0; j < 6; j++) s += T[a][7 + j] * Hf[b * 6 + j];
             S[a * 2 + b] = s;
         }
     if (mode == 0) {
@@ -729,6 +749,7 @@ __global__ void __launch_bounds__(256) k_ransac_compact(DevFilter* Fs) {
         F.ctl[CTL_MID] = s_base[1];
         F.ctl[CTL_NCART] = s_base[2];
     }
+    for (int i = threadIdx.x; i < F.N; i += blockDim.x) F.support[i] = 0;  // accumulated with atomics by k_ransac_support
 }
 
 // c.2 one thread per distinct 1-point hypothesis t (match p = ic_list[t]): partial EKF state update restricted to the camera
@@ -923,11 +944,13 @@ __global__ void __launch_bounds__(256, 4) k_ransac_support(DevFilter* Fs, CamDev
     }
 }
 
+__device__ __forceinline__ void gather_inliers(DevFilter& F, int which, int* s_scan, int* s_base);  // kernels_update.cuh
+
 // c.4 replay of the reference's sequential, adaptive control flow (src/Tracking.cpp:403-415, 506-537) over the uniform draws,
 //     then write-back of the winner's low_innovation_inlier flags.  One CTA per filter; warp 0 walks the draws 32 at a time:
 //     a chunk without a new record (support > best so far) only has to be checked against the current budget n_hyp, so the
 //     scalar loop body runs only for the (rare) record-setting hypotheses.
-__global__ void __launch_bounds__(256) k_ransac_select(DevFilter* Fs, ParDev par) {
+__global__ void __launch_bounds__(256) k_ransac_select(DevFilter* Fs, ParDev par, int gather_li) {
     DevFilter& F = Fs[blockIdx.y];
     __shared__ int s_state[8];  // 1 max, 2 n_hyp, 3 winner i, 5 hyp_run, 6 status
     __shared__ int s_sup[2048];
@@ -1037,6 +1060,12 @@ __global__ void __launch_bounds__(256) k_ransac_select(DevFilter* Fs, ParDev par
         F.ctl[CTL_NHYP] = s_state[2];
         F.ctl[CTL_WINNER] = win;
         F.ctl[CTL_WINNER_T] = wt;
+    }
+    if (gather_li) {  // fused first step of ekf_update_li_inliers: ordered inlier list + innovation (saves a launch on the latency path)
+        __shared__ int s_scan[256];
+        __shared__ int s_base;
+        __syncthreads();
+        gather_inliers(F, 0, s_scan, &s_base);
     }
 }
 

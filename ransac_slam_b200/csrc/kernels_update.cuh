@@ -19,12 +19,10 @@
 namespace rslam {
 
 // ---- U1: ordered list of the inlier set + innovation ----------------------------------------------------------------
-// which = 0: low_innovation_inlier, prior state x_k_km1 (:559-596); which = 1: high_innovation_inlier, state x_k_k (:640-678)
-__global__ void __launch_bounds__(256) k_upd_gather(DevFilter* Fs, int which) {
-    DevFilter& F = Fs[blockIdx.y];
-    __shared__ int s_scan[256];
-    __shared__ int s_base;
-    if (threadIdx.x == 0) s_base = 0;
+// which = 0: low_innovation_inlier, prior state x_k_km1 (:559-596); which = 1: high_innovation_inlier, state x_k_k (:640-678).
+// CTA-collective (256 threads).  With an empty low-innovation set the reference copies the prior (src/ExtendKF.cpp:635-638).
+__device__ __forceinline__ void gather_inliers(DevFilter& F, int which, int* s_scan /*[256]*/, int* s_base) {
+    if (threadIdx.x == 0) *s_base = 0;
     __syncthreads();
     const unsigned char* flag = which == 0 ? F.li : F.hi;
     for (int base = 0; base < F.N; base += 256) {
@@ -40,20 +38,29 @@ __global__ void __launch_bounds__(256) k_upd_gather(DevFilter* Fs, int which) {
             __syncthreads();
         }
         if (a) {
-            const int t = s_base + s_scan[threadIdx.x] - 1;
+            const int t = *s_base + s_scan[threadIdx.x] - 1;
             F.upd_list[t] = i;
             // innovation z - h rides along as row n of W
             F.W[F.n + (size_t)(2 * t) * F.ldw] = F.z[2 * i] - F.h[2 * i];
             F.W[F.n + (size_t)(2 * t + 1) * F.ldw] = F.z[2 * i + 1] - F.h[2 * i + 1];
         }
         __syncthreads();
-        if (threadIdx.x == 255) s_base += s_scan[255];
+        if (threadIdx.x == 255) *s_base += s_scan[255];
         __syncthreads();
     }
+    const int m = *s_base;
     if (threadIdx.x == 0) {
-        F.ctl[CTL_M] = s_base;
-        F.ctl[CTL_K] = 2 * s_base;
+        F.ctl[CTL_M] = m;
+        F.ctl[CTL_K] = 2 * m;
     }
+    if (which == 0 && m == 0)
+        for (int r = threadIdx.x; r < F.n; r += blockDim.x) F.x_kk[r] = F.x_km1[r];
+}
+
+__global__ void __launch_bounds__(256) k_upd_gather(DevFilter* Fs, int which) {
+    __shared__ int s_scan[256];
+    __shared__ int s_base;
+    gather_inliers(Fs[blockIdx.y], which, s_scan, &s_base);
 }
 
 // ---- U2: W = P H^T.  Thread per state row r, CTA handles a chunk of measurements. ---------------------------------------
@@ -149,45 +156,51 @@ __global__ void __launch_bounds__(256) k_upd_S(DevFilter* Fs) {
 // On this part fp64 sqrt / divide / dependent FMA chains cost hundreds of cycles, so the panel code is organised to keep the
 // per-column serial chain minimal (one rsqrt + one multiply + one barrier) and to do everything else as wide, independent work.
 
-// Right-looking Cholesky of the NB x NB block in smem (lower part valid, identity padding beyond w).  16 x 16 thread grid, thread
-// (ty,tx) owns elements (i,c) with i = ty (mod 16), c = tx (mod 16).  Per column j: every thread recomputes rd = rsqrt(a_jj)
-// itself (no barrier to broadcast it) and applies the rank-1 update straight from the UNSCALED column j,
-//     a_ic -= a_ij * a_cj * rd^2 ,
-// while column j-1 is scaled to l = a * rd_{j-1} by its owners (nobody reads it any more).  One barrier per column.
-// (A register-resident variant was measured slower: the loop is instruction-issue bound, not shared-memory bound.)
+// Right-looking Cholesky of the NB x NB block in smem (lower part valid, identity padding beyond w).  The loop is bound by
+// instruction issue and by the per-column serial chain (barrier -> a_jj -> rsqrt -> update), not by flops.  16 x 16 thread grid
+// ANCHORED at the trailing block: at column j thread (ty,tx) updates (i,c) = (j+1+ty+16a, j+1+tx+16b) for the slices b <= a that
+// are still alive, so the instruction count follows the shrinking trailing matrix (4.8 slices per column on average instead of
+// 16 with fixed ownership).  Every thread recomputes rd = rsqrt(a_jj) itself (no broadcast barrier) and updates from the UNSCALED
+// column j,  a_ic -= (a_ij rd^2) a_cj ;  column j-1 is scaled to l = a rd_{j-1} one step later, when nobody reads it any more.
+// One barrier per column.  (Measured alternatives per 64 block: fixed-ownership grid 46 k cycles, register-resident 71 k,
+// row-owner threads 88 k.)
 __device__ __forceinline__ void smem_potrf(double (*sL)[kNB + 1], double* sRd, int w) {
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     if (threadIdx.x < kNB) sRd[threadIdx.x] = 1.0;
     double rd_prev = 1.0;
     for (int j = 0; j <= w; j++) {
         __syncthreads();
-        if (j > 0 && tx == ((j - 1) & 15)) {  // scale the previous column (rows >= j-1)
-#pragma unroll
-            for (int a = 0; a < 4; a++) {
-                const int i = ty + 16 * a;
-                if (i >= j - 1 && i < w) sL[i][j - 1] *= rd_prev;
-            }
-            if (ty == 0) sRd[j - 1] = rd_prev;
+        if (j > 0) {
+            const int i = threadIdx.x;
+            if (i >= j - 1 && i < w) sL[i][j - 1] *= rd_prev;  // final column j-1 of L
+            if (i == 0) sRd[j - 1] = rd_prev;
         }
         if (j == w) break;
         const double rd = rsqrt(sL[j][j]);
         const double r2 = rd * rd;
-        // rows i = ty + 16a > j and columns c = tx + 16b in (j, i]: skip whole a / b slices that cannot be active
-        const int a0 = (j >= ty) ? ((j - ty) >> 4) + 1 : 0;   // first a with i > j
-        if (a0 < 4) {
-            double lc[4];
+        const int nb = (w - 1 - j + 15) >> 4;  // alive 16-wide slices of the trailing block (uniform)
+        double lc[4];
 #pragma unroll
-            for (int bq = 0; bq < 4; bq++) lc[bq] = sL[tx + 16 * bq][j];
+        for (int bq = 0; bq < 4; bq++) {
+            const int c = j + 1 + tx + 16 * bq;
+            lc[bq] = (bq < nb && c < w) ? sL[c][j] : 0.0;
+        }
 #pragma unroll
-            for (int a = 0; a < 4; a++) {
-                const int i = ty + 16 * a;
-                if (a < a0 || i >= w) continue;
-                const double lia = sL[i][j] * r2;
+        for (int a = 0; a < 4; a++) {
+            if (a >= nb) break;
+            const int i = j + 1 + ty + 16 * a;
+            const bool iv = i < w;
+            const double lia = iv ? sL[i][j] * r2 : 0.0;
+            double v[4];
 #pragma unroll
-                for (int bq = 0; bq < 4; bq++) {
-                    const int c = tx + 16 * bq;
-                    if (c > j && c <= i) sL[i][c] -= lia * lc[bq];
-                }
+            for (int bq = 0; bq < 4; bq++) {
+                const int c = j + 1 + tx + 16 * bq;
+                if (bq <= a) v[bq] = (iv && c <= i) ? sL[i][c] : 0.0;
+            }
+#pragma unroll
+            for (int bq = 0; bq < 4; bq++) {
+                const int c = j + 1 + tx + 16 * bq;
+                if (bq <= a && iv && c <= i) sL[i][c] = fma(-lia, lc[bq], v[bq]);
             }
         }
         rd_prev = rd;
@@ -389,12 +402,13 @@ __global__ void __launch_bounds__(256) k_chol_small(DevFilter* Fs) {
         smem_potrf(sL, sRd, w);
         PH(1);
         smem_trinv(sL, sRd, sX, sT);
+        PH(2);
         for (int e = threadIdx.x; e < kNB * kNB; e += blockDim.x) {
             const int i = e % kNB, c = e / kNB;
             if (i < w && c < w) S[(j0 + i) + (size_t)(j0 + c) * ld] = (i >= c) ? sL[i][c] : 0.0;
         }
         store_linv(sX, F.Linv + (size_t)(j0 / kNB) * kNB * kNB);
-        PH(2);
+        PH(4);
         if (rem <= 0) break;
         smem_panel_mul(sPan, sX, rem);
         PH(3);
@@ -780,13 +794,7 @@ __global__ void __launch_bounds__(GemmCfg<BM, BN>::kThreads, GemmCfg<BM, BN>::kM
     }
 }
 
-// ---- U7: x+ = x + V y is fused into the SYRK kernel (row n of V V^T); with no measurements the prior is copied ----------------
-__global__ void __launch_bounds__(128) k_upd_x_copy(DevFilter* Fs) {  // low-innovation update with an empty inlier set (:635-638)
-    DevFilter& F = Fs[blockIdx.y];
-    if (F.ctl[CTL_K] > 0) return;
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r < F.n) F.x_kk[r] = F.x_km1[r];
-}
+// ---- U7: x+ = x + V y is fused into the SYRK kernel (row n of V V^T); the empty-set copy of the prior happens in gather_inliers ----
 
 // ---- U9: quaternion normalisation and its Jacobian applied to P (src/ExtendKF.cpp:611-634).  One CTA per filter. -----------
 __global__ void __launch_bounds__(256) k_upd_jnorm(DevFilter* Fs, ParDev par) {

@@ -176,14 +176,14 @@ int check_launch() {
     return 0;
 }
 
-int run_update(rslam_filter* f, int which) {
+int run_update(rslam_filter* f, int which, bool gathered = false) {
     int rc = ensure_update_ws(f);
     if (rc) return rc;
     const int B = f->B, N = f->hN, n = f->hn;
     if (N == 0) return 0;
     const int kmax = 2 * N;
     const int nsteps = cdiv(kmax, kNB);
-    LAUNCH(f, k_upd_gather, dim3(1, B), 256, 0, f->dF, which);
+    if (!gathered) LAUNCH(f, k_upd_gather, dim3(1, B), 256, 0, f->dF, which);
     LAUNCH(f, k_upd_W, dim3(cdiv(n, 256), cdiv(N, kWChunk), B), 256, 0, f->dF);
     LAUNCH(f, k_upd_S, dim3(cdiv(N, 16), cdiv(N, 16), B), 256, 0, f->dF);
     if (kmax <= kCholSmallMaxK) {
@@ -204,7 +204,6 @@ int run_update(rslam_filter* f, int which) {
     } else {
         LAUNCH_N(f, "k_trsm_ll", (k_trsm_ll<32, 2>), dim3(cdiv(n + 1, 32), B), 128, (TrsmCfg<32, 2>::kSmemBytes), f->dF);
     }
-    if (which == 0) LAUNCH(f, k_upd_x_copy, dim3(cdiv(n, 128), B), 128, 0, f->dF);
     {
         const int tm = cdiv(n + 1, 128);
         const int smode = (int)GEMM_SYRK_P | (which << 8);
@@ -219,16 +218,15 @@ int run_update(rslam_filter* f, int which) {
     return check_launch();
 }
 
-int run_ransac_core(rslam_filter* f, bool select) {
+int run_ransac_core(rslam_filter* f, bool select, bool gather_li = false) {
     const int B = f->B, N = f->hN;
     if (N == 0) return 0;
     LAUNCH(f, k_ransac_compact, dim3(1, B), 256, 0, f->dF);
     LAUNCH(f, k_ransac_hyp, dim3(cdiv(N, 128), B), 128, 0, f->dF);
-    CK(cudaMemsetAsync(f->d_support_all, 0, sizeof(int) * (size_t)f->Nmax * B, f->stream));
     if (select) {
         LAUNCH(f, k_ransac_support, dim3(cdiv(N, SJT), cdiv(N, SHB), B), 256, 0, f->dF, f->camd, f->pard, (const int*)nullptr, 0, N, 0, N, (const int*)nullptr,
                (int*)nullptr, (unsigned long long*)nullptr);
-        LAUNCH(f, k_ransac_select, dim3(1, B), 256, 0, f->dF, f->pard);
+        LAUNCH(f, k_ransac_select, dim3(1, B), 256, 0, f->dF, f->pard, gather_li ? 1 : 0);
     }
     return check_launch();
 }
@@ -632,7 +630,7 @@ int rslam_begin_frame(rslam_filter* f) {
 int rslam_ekf_prediction(rslam_filter* f) {
     if (!f) return fail(RSLAM_ERR_INVALID, "null handle");
     CK(cudaSetDevice(f->device));
-    LAUNCH(f, k_ekf_prediction, dim3(cdiv(f->hn > 13 ? f->hn : 13, 128), f->B), 128, 0, f->dF, f->pard);
+    LAUNCH(f, k_ekf_prediction, dim3(cdiv(f->hn > 13 ? f->hn : 13, 128), f->B), 128, 0, f->dF, f->pard, 0);
     return check_launch();
 }
 
@@ -748,13 +746,13 @@ static int resolve_u01(rslam_filter* f, const double* u01, int n_u01, const doub
 // the fixed launch sequence of one frame (src/System.cpp:111-129); inputs already bound by k_set_inputs
 static int run_frame_stages(rslam_filter* f, int flags) {
     int rc;
-    if (flags & 1) {
-        if ((rc = rslam_begin_frame(f))) return rc;
-        if ((rc = rslam_ekf_prediction(f))) return rc;
+    if (flags & 1) {  // begin_frame folded into the prediction launch (n >= N always)
+        LAUNCH(f, k_ekf_prediction, dim3(cdiv(f->hn > 13 ? f->hn : 13, 128), f->B), 128, 0, f->dF, f->pard, 1);
     }
     if ((rc = rslam_search_ic_matches(f))) return rc;
-    if ((rc = run_ransac_core(f, true))) return rc;
-    if ((rc = run_update(f, 0))) return rc;
+    if ((rc = ensure_update_ws(f))) return rc;
+    if ((rc = run_ransac_core(f, true, true))) return rc;
+    if ((rc = run_update(f, 0, true))) return rc;
     if ((rc = rslam_rescue_hi(f))) return rc;
     if ((rc = run_update(f, 1))) return rc;
     return 0;
