@@ -158,7 +158,7 @@ def algorithmic_work(kernel, N, n, st):
             return "tensor", sum(float(n) * n * k for k in ks)
         if kernel.endswith("trsm_trail"):
             return "tensor", sum(float(n) * k * k for k in ks)
-        if kernel.endswith("chol_trail"):
+        if kernel.endswith("chol_outer") or kernel.endswith("chol_inner"):
             return "tensor", sum(k**3 / 3.0 for k in ks)
         return "tensor", sum(float(n) * n * k + float(n) * k * k + k**3 / 3.0 for k in ks)
     if kernel == "k_ekf_prediction":

@@ -216,9 +216,29 @@ def bench_c5(args, world, rank, local):
     ms = B.run_frames_resident(g, d_images, d_u01, range(W, W + K), False, flush, stream)
     B.barrier(world)
     ms = B.max_over_ranks(ms, world)
+    # instrumented pass (events around every launch, no graph): where the batch frame goes
+    g.profile(True)
+    B.run_frames_resident(g, d_images, d_u01, [W + K - 1], False, flush, stream)
+    prof = g.profile_read()
+    g.profile(False)
+    ft = [g.features(b=b) for b in range(0, Bl, max(1, Bl // 16))]
+    m_hi = float(np.mean([f["hi"].sum() for f in ft]))
+    m_li = float(np.mean([f["li"].sum() for f in ft]))
+    tot = sum(v[1] for v in prof.values())
+    breakdown = {k: dict(launches=v[0], ms=v[1], share=v[1] / tot) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
     g.close()
+    # HBM roofline of the batch frame: every filter's P (n x ldp fp64) is read and written once per non-empty update (the SYRK
+    # downdate), and the 7 + 6 m columns of P that W = P H^T gathers are read once more; everything else is < 5 % of that
+    ldp = (n + 15) // 16 * 16
+    upd = (1 if m_li > 0 else 0) + (1 if m_hi > 0 else 0)
+    bytes_per_filter = upd * 2.0 * n * ldp * 8 + 8.0 * n * (7 * upd + 6 * (m_li + m_hi))
+    pk = B.peaks()
+    ach = Bl * bytes_per_filter / (ms / K * 1e-3) / 1e9
     return dict(workload=f"C5: {Btot} independent 100-feature filters, batch split over ranks, no inter-GPU traffic", n_gpus=world, scaling="strong",
                 value=Btot * K / (ms * 1e-3), unit="filter-frames/s", ms_per_batch_frame=ms / K, filters_per_gpu=Bl,
+                frame_stats=dict(m_li=m_li, m_hi=m_hi), kernels=breakdown,
+                roofline=dict(bound="hbm", unit="GB/s", achieved=ach, peak=pk["hbm_gbs"], frac=ach / pk["hbm_gbs"], bytes_per_filter_frame=bytes_per_filter,
+                              note="whole batch frame against HBM: P read+written once per non-empty update + the P columns gathered by W = P H^T; peak " + pk["source"]),
                 note="working set (P 12.5 GB per 4096 filters) exceeds L2; no flush needed")
 
 

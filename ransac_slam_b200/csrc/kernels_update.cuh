@@ -632,7 +632,12 @@ struct GemmCfg {
     static constexpr int kMinBlocks = (BM == 128 && BN == 64) ? 2 : 1;
 };
 
-enum GemmMode { GEMM_SYRK_P = 0, GEMM_CHOL_TRAIL = 1 };
+// Cholesky trailing updates are two-level: after the 64-wide panel `step` only the columns up to the end of its 256-wide outer
+// block are updated (GEMM_CHOL_INNER, K = 64, a thin M x <=192 rectangle); after the last panel of an outer block the rest of the
+// matrix gets one K = 256 update (GEMM_CHOL_OUTER).  Same flops as a K = 64 update after every panel, but 4x fewer passes over the
+// trailing matrix and DMMA tiles with a 4x longer k-loop.
+constexpr int kOB = 4;  // panels per outer block
+enum GemmMode { GEMM_SYRK_P = 0, GEMM_CHOL_INNER = 1, GEMM_CHOL_OUTER = 2 };
 
 struct GemmProb {
     const double* A;
@@ -655,16 +660,26 @@ __device__ __forceinline__ bool gemm_setup(const DevFilter& F, int mode, int ste
         g.lower = g.mirror = true;
         return true;
     }
-    const int o = kNB * (step + 1);
-    if (kk <= o) return false;
-    g.A = g.B = F.Sm + o + (size_t)(o - kNB) * F.lds;
-    g.lda = g.ldb = F.lds;
-    g.C = F.Sm + o + (size_t)o * F.lds;
-    g.ldc = F.lds;
-    g.M = g.N = kk - o;
-    g.K = kNB;
-    g.lower = true;
+    g.lda = g.ldb = g.ldc = F.lds;
     g.mirror = false;
+    if (mode == GEMM_CHOL_INNER) {  // step = panel index
+        const int o = kNB * (step + 1), oend = kNB * kOB * (step / kOB + 1);
+        if (kk <= o || oend <= o) return false;
+        g.A = g.B = F.Sm + o + (size_t)(o - kNB) * F.lds;
+        g.C = F.Sm + o + (size_t)o * F.lds;
+        g.M = kk - o;
+        g.N = min(kk, oend) - o;
+        g.K = kNB;
+        g.lower = false;  // thin rectangle; the few entries above the diagonal are never read
+        return true;
+    }
+    const int o = kNB * kOB * (step + 1);  // step = outer block index
+    if (kk <= o) return false;
+    g.A = g.B = F.Sm + o + (size_t)(o - kNB * kOB) * F.lds;
+    g.C = F.Sm + o + (size_t)o * F.lds;
+    g.M = g.N = kk - o;
+    g.K = kNB * kOB;
+    g.lower = true;
     return true;
 }
 

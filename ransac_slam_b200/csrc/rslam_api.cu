@@ -191,11 +191,16 @@ int run_update(rslam_filter* f, int which, bool gathered = false) {
     } else {
         for (int s = 0; s < nsteps; s++) {
             LAUNCH(f, k_chol_panel, dim3(nsteps - s, B), 256, kPanelSmemBytes, f->dF, s);
-            const int rem = kmax - kNB * (s + 1);
-            if (rem > 0) {
-                const int tm = cdiv(rem, 128);
-                LAUNCH_N(f, "k_gemm_dmma/chol_trail", (k_gemm_dmma<128, 64>), dim3(tm * (tm + 1), 1, B), (GemmCfg<128, 64>::kThreads), (GemmCfg<128, 64>::kSmemBytes), f->dF,
-                         (int)GEMM_CHOL_TRAIL, s);
+            const int o = kNB * (s + 1), oend = kNB * kOB * (s / kOB + 1);
+            if (kmax <= o) break;
+            if (oend > o) {  // inner: the rest of this 256-wide outer block only
+                const int tm = cdiv(kmax - o, 128), tn = cdiv((kmax < oend ? kmax : oend) - o, 64);
+                LAUNCH_N(f, "k_gemm_dmma/chol_inner", (k_gemm_dmma<128, 64>), dim3(tm * tn, 1, B), (GemmCfg<128, 64>::kThreads), (GemmCfg<128, 64>::kSmemBytes), f->dF,
+                         (int)GEMM_CHOL_INNER, s);
+            } else {  // outer: everything beyond the block, K = 256
+                const int tm = cdiv(kmax - o, 128);
+                LAUNCH_N(f, "k_gemm_dmma/chol_outer", (k_gemm_dmma<128, 64>), dim3(tm * (tm + 1), 1, B), (GemmCfg<128, 64>::kThreads), (GemmCfg<128, 64>::kSmemBytes), f->dF,
+                         (int)GEMM_CHOL_OUTER, s / kOB);
             }
         }
     }

@@ -56,6 +56,29 @@ def main():
         for _ in range(frames):
             key, _, pairs = g.support_sweep(hyp, want_mask=False)
         print("c4 done", capi.decode_key(key), pairs)
+    elif wl == "c5":
+        Bl = int(os.environ.get("RSLAM_C5_FILTERS", "1024"))
+        scene, seq = B.make_c2(1234, frames)
+        g = capi.Filter(scene.cam.as9(), 100, batch=Bl)
+        g.set_graph(graph)
+        n = scene.x0.size
+        xd = torch.from_numpy(scene.x0).to(dev)
+        Pd = torch.from_numpy(np.ascontiguousarray(scene.P0)).to(dev)
+        for b in range(Bl):
+            g.upload_state_device(xd.data_ptr(), Pd.data_ptr(), n, n, 100, b=b)
+            g.upload_patches(scene.templates.astype(np.float64), b=b)
+        for k in range(frames):
+            g.frame(seq.images[k][None].repeat(Bl, 0), seq.u01[k][None].repeat(Bl, 0))
+        g.sync()
+        print("c5 done", g.launches)
+    elif wl == "cublas":  # the fp64 GEMM the DMMA tiles are compared with (library probe, not product code)
+        nn = 6144
+        a = torch.randn(nn, nn, dtype=torch.float64, device=dev)
+        b = torch.randn(nn, nn, dtype=torch.float64, device=dev)
+        for _ in range(frames):
+            c = a @ b
+        torch.cuda.synchronize()
+        print("cublas done", float(c[0, 0]))
     else:
         raise SystemExit("unknown workload")
 

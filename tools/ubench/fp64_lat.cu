@@ -52,7 +52,7 @@ __global__ void k_lat(double* out, long long* cyc, int iters) {
 }
 int main() {
     double* out; long long* cyc;
-    cudaMalloc(&out, 1 << 20); cudaMalloc(&cyc, 64);
+    cudaMalloc(&out, 8 << 20); cudaMalloc(&cyc, 64);
     for (int threads : {32, 256, 1024}) {
         for (int blocks : {1, 148 * 2}) {
             const int iters = 2000;
