@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "librslam_b200.so")
+LIB_PATH = os.environ.get("RSLAM_LIB") or os.path.join(_HERE, "lib", "librslam_b200.so")  # RSLAM_LIB: A/B builds of the same CUDA library during tuning
 
 Q1 = 0x1
 Q4 = 0x2

@@ -557,16 +557,24 @@ __global__ void __launch_bounds__(192) k_pred_patch(DevFilter* Fs, CamDev cam) {
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kMaxHalfSearch = 20;                           // ceil(2*sqrt(S_ii)) with S_ii < 100
 constexpr int kWinMax = 2 * kMaxHalfSearch + 1 + 2 * kHalfPatch;  // 53
+constexpr int kSearchThreads = 64;
+constexpr int kStrip = 4;  // vertically adjacent candidates scored by one thread
 
-__global__ void __launch_bounds__(128) k_search(DevFilter* Fs, CamDev cam, ParDev par) {
+// Scoring is register-tiled: a thread owns a strip of kStrip vertically adjacent candidates (same x), walks the 13 patch columns
+// and for each loads the 16 window pixels the strip touches once; every predicted-patch value is then used for kStrip candidates.
+// The window is converted to fp64 once when it is staged (an int->double conversion per candidate pixel saturated the XU pipe);
+// sum b and sum b^2 are exact integer-valued doubles built with a sliding column sum.  Per candidate pixel this is ~0.56 shared
+// loads and ~1.7 DFMA instead of 2 loads + 1 conversion + 1 DFMA + 2 IMAD.
+__global__ void __launch_bounds__(kSearchThreads) k_search(DevFilter* Fs, CamDev cam, ParDev par) {
     DevFilter& F = Fs[blockIdx.y];
     const int i = blockIdx.x;
     if (i >= F.N) return;
     if (!F.has_h[i] || F.image == nullptr) return;
-    __shared__ unsigned char win[kWinMax * kWinMax + 8];
+    __shared__ double win[(kWinMax + kStrip - 1) * kWinMax];  // rows padded to whole strips
     __shared__ double pa[kPatchPix];  // predicted patch minus its mean
-    __shared__ double red_c[4], red_firstc[4];
-    __shared__ int red_i[4], red_first[4];
+    __shared__ double s_part[kPatch];
+    __shared__ double red_c[2], red_firstc[2];
+    __shared__ int red_i[2], red_first[2];
     __shared__ double s_stats[2];
     const double h0 = F.h[2 * i], h1 = F.h[2 * i + 1];
     const double S00 = F.S[4 * i], S01 = F.S[4 * i + 1], S10 = F.S[4 * i + 2], S11 = F.S[4 * i + 3];
@@ -579,69 +587,115 @@ __global__ void __launch_bounds__(128) k_search(DevFilter* Fs, CamDev cam, ParDe
     if (hsx > kMaxHalfSearch || hsy > kMaxHalfSearch) return;  // cannot happen while lmax < 100
     const int cx = (int)round(h0), cy = (int)round(h1);
     const int x_lo = cx - hsx, y_lo = cy - hsy;
-    const int ww = 2 * hsx + 1 + 2 * kHalfPatch, wh = 2 * hsy + 1 + 2 * kHalfPatch;
+    const int ncx = 2 * hsx + 1, ncy = 2 * hsy + 1;
+    const int nsy = (ncy + kStrip - 1) / kStrip;
+    const int ww = ncx + 2 * kHalfPatch, wh = nsy * kStrip + 2 * kHalfPatch;  // rows padded to whole strips (zeros)
     const int wx0 = x_lo - kHalfPatch, wy0 = y_lo - kHalfPatch;
     for (int e = threadIdx.x; e < ww * wh; e += blockDim.x) {
         const int wy = e / ww, wx = e % ww;
         const int gx = wx0 + wx, gy = wy0 + wy;
         unsigned char v = 0;
         if (gx >= 0 && gx < F.img_cols && gy >= 0 && gy < F.img_rows) v = F.image[(size_t)gy * F.img_stride + gx];
-        win[e] = v;
+        win[e] = (double)v;
     }
     for (int e = threadIdx.x; e < kPatchPix; e += blockDim.x) pa[e] = (double)F.patch[(size_t)i * kPatchPix + e];
     __syncthreads();
+    // mean and centred energy of the predicted patch: per-row partial sums, then a fixed-order sum of the 13 partials
+    if (threadIdx.x < kPatch) {
+        double sa = 0;
+        for (int c = 0; c < kPatch; c++) sa += pa[threadIdx.x * kPatch + c];
+        s_part[threadIdx.x] = sa;
+    }
+    __syncthreads();
     if (threadIdx.x == 0) {
         double sa = 0;
-        for (int e = 0; e < kPatchPix; e++) sa += pa[e];
+        for (int r = 0; r < kPatch; r++) sa += s_part[r];
         s_stats[0] = sa * (1.0 / kPatchPix);
     }
     __syncthreads();
     const double mean_a = s_stats[0];
     for (int e = threadIdx.x; e < kPatchPix; e += blockDim.x) pa[e] -= mean_a;
     __syncthreads();
+    if (threadIdx.x < kPatch) {
+        double va = 0;
+        for (int c = 0; c < kPatch; c++) va += pa[threadIdx.x * kPatch + c] * pa[threadIdx.x * kPatch + c];
+        s_part[threadIdx.x] = va;
+    }
+    __syncthreads();
     if (threadIdx.x == 0) {
         double va = 0;
-        for (int e = 0; e < kPatchPix; e++) va += pa[e] * pa[e];
+        for (int r = 0; r < kPatch; r++) va += s_part[r];
         s_stats[1] = va;  // sum (a - mean)^2, exactly 0 for a constant (e.g. zeroed) patch
     }
     __syncthreads();
     const double var_a = s_stats[1];
     const double idet = 1.0 / (S00 * S11 - S01 * S10);
     const double i00 = S11 * idet, i01 = -S01 * idet, i10 = -S10 * idet, i11 = S00 * idet;
-    const int ncx = 2 * hsx + 1, ncy = 2 * hsy + 1;
     double best_c = -INFINITY;   // best finite score seen by this thread
     int best_idx = 0x7fffffff;   // its visiting-order index jx*ncy + iy
     int first_idx = 0x7fffffff;  // first accepted candidate seen by this thread
     double first_c = 0.0;
-    for (int cand = threadIdx.x; cand < ncx * ncy; cand += blockDim.x) {
-        const int jx = cand / ncy, iy = cand % ncy;  // reference visiting order: x outer, y inner
-        const int j = x_lo + jx, ii = y_lo + iy;
-        const double nu0 = j - h0, nu1 = ii - h1;
-        const double t0 = nu0 * i00 + nu1 * i10, t1 = nu0 * i01 + nu1 * i11;
-        if (!((t0 * nu0 + t1 * nu1) < par.chi2)) continue;
-        if (!((j > kHalfPatch) && (j < (cam.nCols - kHalfPatch)) && (ii > kHalfPatch) && (ii < (cam.nRows - kHalfPatch)))) continue;
-        int sb = 0, sbb = 0;
-        double sab = 0;
-        const unsigned char* wp = &win[iy * ww + jx];
-#pragma unroll 1
-        for (int r = 0; r < kPatch; r++) {
+    for (int strip = threadIdx.x; strip < ncx * nsy; strip += blockDim.x) {
+        const int jx = strip % ncx, iy0 = (strip / ncx) * kStrip;
+        const int j = x_lo + jx;
+        bool ok[kStrip];
+        bool any = false;
 #pragma unroll
-            for (int c = 0; c < kPatch; c++) {
-                const int b = wp[r * ww + c];
-                sb += b;
-                sbb += b * b;
-                sab = fma(pa[r * kPatch + c], (double)b, sab);  // sum (a - mean_a) * b == sum (a - mean_a)(b - mean_b)
+        for (int t = 0; t < kStrip; t++) {
+            const int iy = iy0 + t, ii = y_lo + iy;
+            const double nu0 = j - h0, nu1 = ii - h1;
+            const double t0 = nu0 * i00 + nu1 * i10, t1 = nu0 * i01 + nu1 * i11;
+            ok[t] = iy < ncy && ((t0 * nu0 + t1 * nu1) < par.chi2) && (j > kHalfPatch) && (j < (cam.nCols - kHalfPatch)) && (ii > kHalfPatch) &&
+                    (ii < (cam.nRows - kHalfPatch));
+            any |= ok[t];
+        }
+        if (!any) continue;
+        double sab[kStrip], sb[kStrip], sbb[kStrip];
+#pragma unroll
+        for (int t = 0; t < kStrip; t++) sab[t] = sb[t] = sbb[t] = 0.0;
+        const double* wp = &win[iy0 * ww + jx];
+#pragma unroll 1
+        for (int c = 0; c < kPatch; c++) {
+            double wv[kPatch + kStrip - 1];
+#pragma unroll
+            for (int r = 0; r < kPatch + kStrip - 1; r++) wv[r] = wp[r * ww + c];
+            // column sums of b and b^2 for the first candidate, then slide down
+            double cs = 0.0, cq = 0.0;
+#pragma unroll
+            for (int r = 0; r < kPatch; r++) {
+                cs += wv[r];
+                cq = fma(wv[r], wv[r], cq);
+            }
+            sb[0] += cs;
+            sbb[0] += cq;
+#pragma unroll
+            for (int t = 1; t < kStrip; t++) {
+                cs += wv[t + kPatch - 1] - wv[t - 1];
+                cq += wv[t + kPatch - 1] * wv[t + kPatch - 1] - wv[t - 1] * wv[t - 1];
+                sb[t] += cs;
+                sbb[t] += cq;
+            }
+#pragma unroll
+            for (int r = 0; r < kPatch; r++) {
+                const double a = pa[r * kPatch + c];
+#pragma unroll
+                for (int t = 0; t < kStrip; t++) sab[t] = fma(a, wv[r + t], sab[t]);  // sum (a - mean_a) * b == sum (a - mean_a)(b - mean_b)
             }
         }
-        const double var_b = (double)((long long)kPatchPix * sbb - (long long)sb * sb) / kPatchPix;
-        const double corr = sab / sqrt(var_a * var_b);
-        if (cand < first_idx) {
-            first_idx = cand;
-            first_c = corr;
-        }
-        if (corr == corr && (corr > best_c)) {  // NaN never wins; strict '>' keeps the earlier index (cand increases per thread)
-            best_c = corr;
-            best_idx = cand;
+#pragma unroll
+        for (int t = 0; t < kStrip; t++) {
+            if (!ok[t]) continue;
+            const int cand = jx * ncy + iy0 + t;  // reference visiting order: x outer, y inner
+            const double var_b = ((double)kPatchPix * sbb[t] - sb[t] * sb[t]) / kPatchPix;  // exact: integer-valued operands < 2^53
+            const double corr = sab[t] / sqrt(var_a * var_b);
+            if (cand < first_idx) {
+                first_idx = cand;
+                first_c = corr;
+            }
+            if (corr == corr && (corr > best_c || (corr == best_c && cand < best_idx))) {  // NaN never wins; ties keep the earlier index
+                best_c = corr;
+                best_idx = cand;
+            }
         }
     }
     // block reduce: maximum finite corr, ties -> smaller visiting index ; and the globally first accepted candidate
@@ -670,7 +724,7 @@ __global__ void __launch_bounds__(128) k_search(DevFilter* Fs, CamDev cam, ParDe
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int k = 1; k < 4; k++) {
+        for (int k = 1; k < kSearchThreads / 32; k++) {
             if (red_c[k] > best_c || (red_c[k] == best_c && red_i[k] < best_idx)) {
                 best_c = red_c[k];
                 best_idx = red_i[k];

@@ -613,6 +613,142 @@ __global__ void __launch_bounds__(WM * 64) k_trsm_ll(DevFilter* Fs) {
     }
 }
 
+// ---- U5s: TRSM for SMALL innovation dimension (k <= 256).  The left-looking kernel above re-reads its own V rows from L2 for every
+// column block and waits on each of those round trips (26 % tensor-pipe utilisation, long-scoreboard bound, on the batched
+// configuration).  Here the CTA's 32 rows of W are loaded ONCE into shared memory and turned into V in place; the only streamed
+// operand is L (off-diagonal blocks, then the inverse of the diagonal block), through a 4-stage cp.async ring flattened over the
+// whole (column block, k-chunk) sequence, so every load is issued several chunks before it is needed.
+constexpr int TS_R = 32, TS_THREADS = 128, TS_LDA = TS_R + 4, TS_LDB = kNB + 4, TS_STAGES = 4, TS_BK = 16;
+inline int trsm_small_smem_bytes(int kmax) { return (((kmax + kNB - 1) / kNB * kNB) * TS_LDA + TS_STAGES * TS_BK * TS_LDB) * (int)sizeof(double); }
+
+__global__ void __launch_bounds__(TS_THREADS, 2) k_trsm_small(DevFilter* Fs, int krows) {
+    DevFilter& F = Fs[blockIdx.y];
+    const int kk = F.ctl[CTL_K];
+    if (kk <= 0) return;
+    const int M = F.n + 1;
+    const int r0 = blockIdx.x * TS_R;
+    if (r0 >= M) return;
+    extern __shared__ __align__(16) double tsm2[];
+    double* Vs = tsm2;                    // [krows][TS_LDA]  k-major: W rows on entry, V rows on exit
+    double* Bs = tsm2 + krows * TS_LDA;   // [stage][TS_BK][TS_LDB]
+    double* W = F.W;
+    const double* Sm = F.Sm;
+    const int ldw = F.ldw, lds = F.lds;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm0 = (warp & 1) * 16, wn0 = (warp >> 1) * 32;  // warp grid 2 x 2, warp tile 16 x 32
+    const int nb = (kk + kNB - 1) / kNB;
+    const int total = 2 * nb * (nb + 1);  // sum_j (4 j + 4) chunks
+
+    for (int ch = tid; ch < nb * kNB * (TS_R / 2); ch += TS_THREADS) {
+        const int kc = ch / (TS_R / 2), r2 = ch % (TS_R / 2);
+        const int row = r0 + 2 * r2;
+        const bool v = row < M && kc < kk;
+        cp_async16(&Vs[kc * TS_LDA + 2 * r2], v ? (W + row + (size_t)kc * ldw) : W, v);
+    }
+    int lj = 0, lc = 0;  // loader cursor (column block, chunk within it)
+    auto load_next = [&](int stage) {
+        double* bs = Bs + stage * TS_BK * TS_LDB;
+        const int c0 = lj * kNB;
+        if (lc < 4 * lj) {  // off-diagonal: Bs[k][col] = L[c0 + col, 16 lc + k]
+            const int k0 = lc * TS_BK;
+#pragma unroll
+            for (int it = 0; it < TS_BK * (kNB / 2) / TS_THREADS; it++) {
+                const int ch = tid + it * TS_THREADS;
+                const int kc = ch / (kNB / 2), r2 = ch % (kNB / 2);
+                const int row = c0 + 2 * r2;
+                const bool v = row < kk;
+                cp_async16(&bs[kc * TS_LDB + 2 * r2], v ? (Sm + row + (size_t)(k0 + kc) * lds) : Sm, v);
+            }
+        } else {  // diagonal: Bs[k][col] = inv(L_jj)[col, 16 d + k]
+            const int d = lc - 4 * lj;
+            const double* Li = F.Linv + (size_t)lj * kNB * kNB + (size_t)d * TS_BK * kNB;
+#pragma unroll
+            for (int it = 0; it < TS_BK * (kNB / 2) / TS_THREADS; it++) {
+                const int ch = tid + it * TS_THREADS;
+                const int kc = ch / (kNB / 2), r2 = ch % (kNB / 2);
+                cp_async16(&bs[kc * TS_LDB + 2 * r2], Li + 2 * r2 + (size_t)kc * kNB, true);
+            }
+        }
+        if (++lc == 4 * lj + 4) {
+            lc = 0;
+            lj++;
+        }
+    };
+#pragma unroll
+    for (int s = 0; s < TS_STAGES - 1; s++) {
+        if (s < total) load_next(s);
+        cp_async_commit();
+    }
+    double acc[2][4][2];
+    int j = 0, c = 0;
+    for (int q = 0; q < total; q++) {
+        const int c0 = j * kNB;
+        if (c == 0 || c == 4 * j) {
+#pragma unroll
+            for (int a = 0; a < 2; a++)
+#pragma unroll
+                for (int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+        }
+        cp_async_wait<TS_STAGES - 2>();
+        __syncthreads();
+        {
+            const int nq = q + TS_STAGES - 1;
+            if (nq < total) load_next(nq % TS_STAGES);
+            cp_async_commit();
+        }
+        const bool diag = c >= 4 * j;
+        const double* as = Vs + (diag ? (c0 + (c - 4 * j) * TS_BK) : c * TS_BK) * TS_LDA;
+        const double* bs = Bs + (q % TS_STAGES) * TS_BK * TS_LDB;
+#pragma unroll
+        for (int ks = 0; ks < TS_BK / 4; ks++) {
+            const int krow = ks * 4 + (lane & 3);
+            double af[2], bf[4];
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++) af[mt] = as[krow * TS_LDA + wm0 + mt * 8 + (lane >> 2)];
+#pragma unroll
+            for (int nt = 0; nt < 4; nt++) bf[nt] = bs[krow * TS_LDB + wn0 + nt * 8 + (lane >> 2)];
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                for (int nt = 0; nt < 4; nt++) dmma8x8x4(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+        }
+        if (!diag && c == 4 * j - 1) {
+            // T = W_j - acc, in place (each thread touches only its own elements; the accumulation never reads rows >= c0)
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                for (int nt = 0; nt < 4; nt++)
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                        const int rl = wm0 + mt * 8 + (lane >> 2), cl = wn0 + nt * 8 + 2 * (lane & 3) + e;
+                        Vs[(c0 + cl) * TS_LDA + rl] -= acc[mt][nt][e];
+                    }
+        } else if (diag && c == 4 * j + 3) {
+            // V_j = T inv(L_jj)^T : everybody must be done reading T before it is overwritten
+            __syncthreads();
+            const int w = min(kNB, kk - c0);
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++) {
+                const int rl = wm0 + mt * 8 + (lane >> 2);
+                const int row = r0 + rl;
+#pragma unroll
+                for (int nt = 0; nt < 4; nt++)
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                        const int cl = wn0 + nt * 8 + 2 * (lane & 3) + e;
+                        Vs[(c0 + cl) * TS_LDA + rl] = acc[mt][nt][e];
+                        if (row < M && cl < w) W[row + (size_t)(c0 + cl) * ldw] = acc[mt][nt][e];
+                    }
+            }
+        }
+        if (++c == 4 * j + 4) {
+            c = 0;
+            j++;
+        }
+    }
+    cp_async_wait<0>();
+}
+
 // ---- fp64 tensor-core GEMM:  C -= A * B^T  (A: M x K, B: N x K, C: M x N, all column-major) ------------------------------
 // DMMA m8n8k4 (mma.sync.aligned.m8n8k4.row.col.f64): tcgen05 has no fp64 kind, so mma.sync DMMA is the fp64 tensor path on
 // sm_100a.  3-stage cp.async pipeline, padded smem (+4 doubles per k-row) so that the fragment loads are bank-conflict free.
@@ -807,6 +943,152 @@ __global__ void __launch_bounds__(GemmCfg<BM, BN>::kThreads, GemmCfg<BM, BN>::kM
             }
         }
     }
+}
+
+// ---- U6s: covariance downdate for SMALL innovation dimension (k <= 256: the 100-feature and batched-filter configurations) -----
+// With K this small a 64 x 64 tile is a handful of k-steps, so the one-tile-per-CTA GEMM above spends most of its life in the
+// prologue (first loads) and the epilogue (read-modify-write of the P tile from HBM) -- 35 % tensor-pipe utilisation on the
+// 4096-filter batch.  Here a CTA owns a SEGMENT of one 64-row tile row of P:
+//   * its 64 x K block of V (the A operand) is loaded once and stays in shared memory for all tiles of the segment,
+//   * the tiles of the segment are dealt alternately to TWO independent warp groups (4 warps each, one warp per SM sub-partition,
+//     warp tile 32 x 32); each group streams its B operand through its own 4-stage cp.async ring, FLATTENED over
+//     (tile, k-chunk) so that the pipeline never drains, and synchronises on its own named barrier -- the groups drift apart, and
+//     one group's barrier / fragment-load bubbles are covered by the other group's DMMA stream (what two co-resident CTAs would
+//     do, without paying for the resident A twice),
+//   * the P tile is fetched into registers at the first k-chunk of its tile and consumed in the epilogue, which hides its HBM
+//     latency behind the tile's DMMA work.
+// seg_len = 1 gives one CTA per tile (single filter: maximum parallelism, minimum latency); seg_len = tiles-per-row gives one CTA
+// per tile row (large batches: minimum traffic).  Same row-n convention as k_gemm_dmma: row n of V V^T is the state correction.
+#ifndef RSLAM_SR_STAGES
+#define RSLAM_SR_STAGES 4
+#endif
+constexpr int SR_BM = 64, SR_THREADS = 256, SR_LD = SR_BM + 4, SR_STAGES = RSLAM_SR_STAGES, SR_BK = 16, SR_KMAX = 256;
+inline int syrk_rows_smem_bytes(int kmax) { return (((kmax + SR_BK - 1) / SR_BK * SR_BK) * SR_LD + 2 * SR_STAGES * SR_BK * SR_LD) * (int)sizeof(double); }
+
+__device__ __forceinline__ void group_barrier(int g) { asm volatile("bar.sync %0, 128;\n" ::"r"(1 + g) : "memory"); }
+
+__global__ void __launch_bounds__(SR_THREADS, 1) k_syrk_rows(DevFilter* Fs, int which, int seg_len, int kpad) {
+    const DevFilter& F = Fs[blockIdx.z];
+    const int kk = F.ctl[CTL_K];
+    if (kk <= 0) return;
+    const int n = F.n, M = n + 1;
+    const int tm = (M + SR_BM - 1) / SR_BM;
+    // blockIdx.x -> (tile row ti, segment): long rows first
+    int t = blockIdx.x, ti = tm - 1;
+    for (;; ti--) {
+        if (ti < 0) return;
+        const int ns = (ti + seg_len) / seg_len;  // ceil((ti + 1) / seg_len)
+        if (t < ns) break;
+        t -= ns;
+    }
+    const int tj0 = t * seg_len, tj1 = min(ti + 1, tj0 + seg_len);
+    extern __shared__ __align__(16) double rsm[];
+    const int tid = threadIdx.x, grp = tid >> 7, gt = tid & 127, lane = tid & 31, gw = (tid >> 5) & 3;
+    double* As = rsm;                                                         // [kpad][SR_LD]   the CTA's 64 rows of V, k-major
+    double* Bs = rsm + kpad * SR_LD + grp * (SR_STAGES * SR_BK * SR_LD);      // this group's ring [stage][SR_BK][SR_LD]
+    const double* W = F.W;
+    const int ldw = F.ldw, ldp = F.ldp;
+    double* P = F.P;
+    const int wm0 = (gw & 1) * 32, wn0 = (gw >> 1) * 32;  // warp grid 2 x 2 inside the group, warp tile 32 x 32
+    const int m0 = ti * SR_BM;
+    const int nkt = (kk + SR_BK - 1) / SR_BK;
+    const int ntile = (tj1 - tj0 - grp + 1) / 2;  // this group's tiles: tj0 + grp, tj0 + grp + 2, ...
+    const int total = ntile * nkt;
+    const double* x0 = which ? F.x_kk : F.x_km1;
+
+    // A: all of K, once, by the whole CTA
+    for (int ch = tid; ch < nkt * SR_BK * (SR_BM / 2); ch += SR_THREADS) {
+        const int kc = ch / (SR_BM / 2), r2 = ch % (SR_BM / 2);
+        const int row = m0 + 2 * r2;
+        const bool v = row < M && kc < kk;
+        cp_async16(&As[kc * SR_LD + 2 * r2], v ? (W + row + (size_t)kc * ldw) : W, v);
+    }
+    auto load_B = [&](int q) {
+        const int tile = q / nkt, kt = q - tile * nkt;
+        const int n0 = (tj0 + grp + 2 * tile) * SR_BM, k0 = kt * SR_BK;
+        double* bs = Bs + (q % SR_STAGES) * SR_BK * SR_LD;
+#pragma unroll
+        for (int it = 0; it < SR_BK * (SR_BM / 2) / 128; it++) {
+            const int ch = gt + it * 128;
+            const int kc = ch / (SR_BM / 2), r2 = ch % (SR_BM / 2);
+            const int row = n0 + 2 * r2, col = k0 + kc;
+            const bool v = row < M && col < kk;
+            cp_async16(&bs[kc * SR_LD + 2 * r2], v ? (W + row + (size_t)col * ldw) : W, v);
+        }
+    };
+#pragma unroll
+    for (int s = 0; s < SR_STAGES - 1; s++) {
+        if (s < total) load_B(s);
+        cp_async_commit();
+    }
+    // the resident A block was loaded by both groups: one CTA-wide barrier, after that the groups run on their own
+    cp_async_wait<SR_STAGES - 2>();
+    __syncthreads();
+    double acc[4][4][2], cpre[4][4][2];
+    for (int q = 0; q < total; q++) {
+        const int tile = q / nkt, kt = q - tile * nkt;
+        const int n0 = (tj0 + grp + 2 * tile) * SR_BM;
+        if (kt == 0) {
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    acc[a][b][0] = acc[a][b][1] = 0.0;
+                    const int row = m0 + wm0 + a * 8 + (lane >> 2);
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                        const int cc = n0 + wn0 + b * 8 + 2 * (lane & 3) + e;
+                        cpre[a][b][e] = (row < n && cc <= row) ? P[row + (size_t)cc * ldp] : 0.0;
+                    }
+                }
+        }
+        if (q > 0) {
+            cp_async_wait<SR_STAGES - 2>();
+            group_barrier(grp);
+        }
+        {
+            const int nq = q + SR_STAGES - 1;
+            if (nq < total) load_B(nq);
+            cp_async_commit();
+        }
+        const double* as = As + kt * SR_BK * SR_LD;
+        const double* bs = Bs + (q % SR_STAGES) * SR_BK * SR_LD;
+#pragma unroll
+        for (int ks = 0; ks < SR_BK / 4; ks++) {
+            const int krow = ks * 4 + (lane & 3);
+            double af[4], bf[4];
+#pragma unroll
+            for (int mt = 0; mt < 4; mt++) af[mt] = as[krow * SR_LD + wm0 + mt * 8 + (lane >> 2)];
+#pragma unroll
+            for (int nt = 0; nt < 4; nt++) bf[nt] = bs[krow * SR_LD + wn0 + nt * 8 + (lane >> 2)];
+#pragma unroll
+            for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+                for (int nt = 0; nt < 4; nt++) dmma8x8x4(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+        }
+        if (kt == nkt - 1) {  // epilogue of this tile: P -= acc (lower part, mirrored), row n -> state correction
+#pragma unroll
+            for (int mt = 0; mt < 4; mt++) {
+                const int row = m0 + wm0 + mt * 8 + (lane >> 2);
+                if (row >= M) continue;
+#pragma unroll
+                for (int nt = 0; nt < 4; nt++)
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                        const int cc = n0 + wn0 + nt * 8 + 2 * (lane & 3) + e;
+                        if (cc > row || cc >= n) continue;
+                        if (row == n) {
+                            F.x_kk[cc] = x0[cc] + acc[mt][nt][e];
+                            continue;
+                        }
+                        const double v = cpre[mt][nt][e] - acc[mt][nt][e];
+                        P[row + (size_t)cc * ldp] = v;
+                        if (row != cc) P[cc + (size_t)row * ldp] = v;
+                    }
+            }
+        }
+    }
+    cp_async_wait<0>();
 }
 
 // ---- U7: x+ = x + V y is fused into the SYRK kernel (row n of V V^T); the empty-set copy of the prior happens in gather_inliers ----

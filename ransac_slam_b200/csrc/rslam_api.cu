@@ -204,12 +204,23 @@ int run_update(rslam_filter* f, int which, bool gathered = false) {
             }
         }
     }
-    if (cdiv(n + 1, 48) * B >= 200) {  // 48-row CTAs, two resident per SM: one CTA's barriers / diagonal step hide behind the other's DMMA stream
+    if (kmax <= SR_KMAX) {  // small systems: W rows resident in smem, L streamed once
+        LAUNCH(f, k_trsm_small, dim3(cdiv(n + 1, TS_R), B), TS_THREADS, trsm_small_smem_bytes(kmax), f->dF, round_up(kmax, kNB));
+    } else if (cdiv(n + 1, 48) * B >= 200) {  // 48-row CTAs, two resident per SM: one CTA's barriers / diagonal step hide behind the other's DMMA stream
         LAUNCH_N(f, "k_trsm_ll", (k_trsm_ll<48, 2>), dim3(cdiv(n + 1, 48), B), 128, (TrsmCfg<48, 2>::kSmemBytes), f->dF);
     } else {
         LAUNCH_N(f, "k_trsm_ll", (k_trsm_ll<32, 2>), dim3(cdiv(n + 1, 32), B), 128, (TrsmCfg<32, 2>::kSmemBytes), f->dF);
     }
-    {
+    if (kmax <= SR_KMAX) {
+        // small innovation dimension: row-segment SYRK (A resident, flattened B pipeline, P tile prefetched).  Segment length: whole
+        // tile rows when the batch alone fills the machine, single tiles for one filter (latency).
+        const int tm = cdiv(n + 1, SR_BM);
+        int seg = tm;
+        auto ctas = [&](int L) { long long c = 0; for (int i = 0; i < tm; i++) c += (i + L) / L; return c * B; };
+        while (seg > 1 && ctas(seg) < 2 * 148) seg = (seg + 1) / 2;
+        const int kpad = round_up(kmax, SR_BK);
+        LAUNCH_N(f, "k_syrk_rows", k_syrk_rows, dim3((unsigned)(ctas(seg) / B), 1, B), SR_THREADS, syrk_rows_smem_bytes(kmax), f->dF, which, seg, kpad);
+    } else {
         const int tm = cdiv(n + 1, 128);
         const int smode = (int)GEMM_SYRK_P | (which << 8);
         if ((long long)tm * (tm + 1) * B >= 192) {
@@ -290,6 +301,8 @@ int rslam_create(const rslam_camera* cam, const rslam_params* par, int max_featu
     CK(cudaFuncSetAttribute(k_trsm_ll<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TrsmCfg<32, 2>::kSmemBytes));
     CK(cudaFuncSetAttribute(k_chol_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPanelSmemBytes));
     CK(cudaFuncSetAttribute(k_chol_small, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholSmallSmemBytes));
+    CK(cudaFuncSetAttribute(k_trsm_small, cudaFuncAttributeMaxDynamicSharedMemorySize, trsm_small_smem_bytes(SR_KMAX)));
+    CK(cudaFuncSetAttribute(k_syrk_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, syrk_rows_smem_bytes(SR_KMAX)));
 
     const int B = batch, N = max_features, n = f->nmax;
     f->hF.assign(B, DevFilter{});
@@ -645,7 +658,7 @@ int rslam_search_ic_matches(rslam_filter* f) {
     if (f->hN == 0) return RSLAM_OK;
     LAUNCH(f, k_predict, dim3(cdiv(f->hN, 128), f->B), 128, 0, f->dF, f->camd, f->pard, 0);
     if (f->warp_patches) LAUNCH(f, k_pred_patch, dim3(f->hN, f->B), 192, 0, f->dF, f->camd);
-    if (f->have_image) LAUNCH(f, k_search, dim3(f->hN, f->B), 128, 0, f->dF, f->camd, f->pard);
+    if (f->have_image) LAUNCH(f, k_search, dim3(f->hN, f->B), kSearchThreads, 0, f->dF, f->camd, f->pard);
     return check_launch();
 }
 
