@@ -152,296 +152,6 @@ __global__ void __launch_bounds__(256) k_upd_S(DevFilter* Fs) {
     S[(2 * ti + 1) + (size_t)(2 * tj + 1) * ld] = s11;
 }
 
-// ---- shared helpers for the 64-wide panels (all are CTA-collective: 256 threads, every thread must call them) -------------
-// On this part fp64 sqrt / divide / dependent FMA chains cost hundreds of cycles, so the panel code is organised to keep the
-// per-column serial chain minimal (one rsqrt + one multiply + one barrier) and to do everything else as wide, independent work.
-
-// Right-looking Cholesky of the NB x NB block in smem (lower part valid, identity padding beyond w).  The loop is bound by
-// instruction issue and by the per-column serial chain (barrier -> a_jj -> rsqrt -> update), not by flops.  16 x 16 thread grid
-// ANCHORED at the trailing block: at column j thread (ty,tx) updates (i,c) = (j+1+ty+16a, j+1+tx+16b) for the slices b <= a that
-// are still alive, so the instruction count follows the shrinking trailing matrix (4.8 slices per column on average instead of
-// 16 with fixed ownership).  Every thread recomputes rd = rsqrt(a_jj) itself (no broadcast barrier) and updates from the UNSCALED
-// column j,  a_ic -= (a_ij rd^2) a_cj ;  column j-1 is scaled to l = a rd_{j-1} one step later, when nobody reads it any more.
-// One barrier per column.  (Measured alternatives per 64 block: fixed-ownership grid 46 k cycles, register-resident 71 k,
-// row-owner threads 88 k.)
-__device__ __forceinline__ void smem_potrf(double (*sL)[kNB + 1], double* sRd, int w) {
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    if (threadIdx.x < kNB) sRd[threadIdx.x] = 1.0;
-    double rd_prev = 1.0;
-    for (int j = 0; j <= w; j++) {
-        __syncthreads();
-        if (j > 0) {
-            const int i = threadIdx.x;
-            if (i >= j - 1 && i < w) sL[i][j - 1] *= rd_prev;  // final column j-1 of L
-            if (i == 0) sRd[j - 1] = rd_prev;
-        }
-        if (j == w) break;
-        const double rd = rsqrt(sL[j][j]);
-        const double r2 = rd * rd;
-        const int nb = (w - 1 - j + 15) >> 4;  // alive 16-wide slices of the trailing block (uniform)
-        double lc[4];
-#pragma unroll
-        for (int bq = 0; bq < 4; bq++) {
-            const int c = j + 1 + tx + 16 * bq;
-            lc[bq] = (bq < nb && c < w) ? sL[c][j] : 0.0;
-        }
-#pragma unroll
-        for (int a = 0; a < 4; a++) {
-            if (a >= nb) break;
-            const int i = j + 1 + ty + 16 * a;
-            const bool iv = i < w;
-            const double lia = iv ? sL[i][j] * r2 : 0.0;
-            double v[4];
-#pragma unroll
-            for (int bq = 0; bq < 4; bq++) {
-                const int c = j + 1 + tx + 16 * bq;
-                if (bq <= a) v[bq] = (iv && c <= i) ? sL[i][c] : 0.0;
-            }
-#pragma unroll
-            for (int bq = 0; bq < 4; bq++) {
-                const int c = j + 1 + tx + 16 * bq;
-                if (bq <= a && iv && c <= i) sL[i][c] = fma(-lia, lc[bq], v[bq]);
-            }
-        }
-        rd_prev = rd;
-    }
-    __syncthreads();
-}
-
-// inverse of the lower-triangular block in sL (identity padded) -> sX (full 64 x 64, zeros above the diagonal), recursively:
-// four 16 x 16 diagonal inverses by forward substitution (short chains), then inv([[A,0],[B,C]]) = [[iA,0],[-iC B iA, iC]] twice,
-// the products as wide independent dot products.  sT: 32 x 33 scratch.
-__device__ __forceinline__ void smem_trinv(const double (*sL)[kNB + 1], const double* sRd, double (*sX)[kNB + 1], double (*sT)[33]) {
-    const int tid = threadIdx.x;
-    for (int e = tid; e < kNB * kNB; e += blockDim.x) {
-        const int i = e / kNB, c = e % kNB;
-        if (c > i) sX[i][c] = 0.0;
-    }
-    if (tid < kNB) {  // level 0: column c of diagonal block d
-        const int d0 = (tid >> 4) * 16, c = tid & 15;
-        for (int i = 0; i < c; i++) sX[d0 + i][d0 + c] = 0.0;
-        sX[d0 + c][d0 + c] = sRd[d0 + c];
-        for (int i = c + 1; i < 16; i++) {
-            double s0 = 0.0, s1 = 0.0;
-            int t = c;
-            for (; t + 1 < i; t += 2) {
-                s0 += sL[d0 + i][d0 + t] * sX[d0 + t][d0 + c];
-                s1 += sL[d0 + i][d0 + t + 1] * sX[d0 + t + 1][d0 + c];
-            }
-            if (t < i) s0 += sL[d0 + i][d0 + t] * sX[d0 + t][d0 + c];
-            sX[d0 + i][d0 + c] = -(s0 + s1) * sRd[d0 + i];
-        }
-    }
-    __syncthreads();
-    // level 1: blocks (16..31, 0..15) and (48..63, 32..47);  T = B * iA ,  X = -iC * T
-    for (int e = tid; e < 512; e += blockDim.x) {
-        const int blk = e >> 8, i = (e >> 4) & 15, c = e & 15;
-        const int r0 = blk * 32 + 16, c0 = blk * 32;
-        double s = 0.0;
-        for (int t = c; t < 16; t++) s += sL[r0 + i][c0 + t] * sX[c0 + t][c0 + c];
-        sT[blk * 16 + i][c] = s;
-    }
-    __syncthreads();
-    for (int e = tid; e < 512; e += blockDim.x) {
-        const int blk = e >> 8, i = (e >> 4) & 15, c = e & 15;
-        const int r0 = blk * 32 + 16, c0 = blk * 32;
-        double s = 0.0;
-        for (int t = 0; t <= i; t++) s += sX[r0 + i][r0 + t] * sT[blk * 16 + t][c];
-        sX[r0 + i][c0 + c] = -s;
-    }
-    __syncthreads();
-    // level 2: block (32..63, 0..31)
-    for (int e = tid; e < 1024; e += blockDim.x) {
-        const int i = e >> 5, c = e & 31;
-        double s0 = 0.0, s1 = 0.0;
-        int t = c;
-        for (; t + 1 < 32; t += 2) {
-            s0 += sL[32 + i][t] * sX[t][c];
-            s1 += sL[32 + i][t + 1] * sX[t + 1][c];
-        }
-        if (t < 32) s0 += sL[32 + i][t] * sX[t][c];
-        sT[i][c] = s0 + s1;
-    }
-    __syncthreads();
-    for (int e = tid; e < 1024; e += blockDim.x) {
-        const int i = e >> 5, c = e & 31;
-        double s0 = 0.0, s1 = 0.0;
-        int t = 0;
-        for (; t + 1 <= i; t += 2) {
-            s0 += sX[32 + i][32 + t] * sT[t][c];
-            s1 += sX[32 + i][32 + t + 1] * sT[t + 1][c];
-        }
-        if (t <= i) s0 += sX[32 + i][32 + t] * sT[t][c];
-        sX[32 + i][c] = -(s0 + s1);
-    }
-    __syncthreads();
-}
-
-// rows [0, nr) of sPan (nr x 64, row stride NB+1) <- sPan * inv(L)^T with inv(L) = sX:  out[r][c] = sum_{t<=c} A[r][t] iL[c][t].
-// 4 threads per row (16 output columns each) accumulate into registers, then store after a barrier (in-place safe).
-__device__ __forceinline__ void smem_panel_mul(double (*sPan)[kNB + 1], const double (*sX)[kNB + 1], int nr) {
-    for (int base = 0; base < nr; base += 64) {  // uniform trip count across the CTA
-        const int r = base + (threadIdx.x & 63), cg = (threadIdx.x >> 6) * 16;
-        double o[16];
-#pragma unroll
-        for (int q = 0; q < 16; q++) o[q] = 0.0;
-        if (r < nr) {
-#pragma unroll
-            for (int q = 0; q < 16; q++) {
-                const int c = cg + q;
-                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-                int t = 0;
-                for (; t + 3 <= c; t += 4) {
-                    s0 += sPan[r][t] * sX[c][t];
-                    s1 += sPan[r][t + 1] * sX[c][t + 1];
-                    s2 += sPan[r][t + 2] * sX[c][t + 2];
-                    s3 += sPan[r][t + 3] * sX[c][t + 3];
-                }
-                for (; t <= c; t++) s0 += sPan[r][t] * sX[c][t];
-                o[q] = (s0 + s1) + (s2 + s3);
-            }
-        }
-        __syncthreads();
-        if (r < nr) {
-#pragma unroll
-            for (int q = 0; q < 16; q++) sPan[r][cg + q] = o[q];
-        }
-        __syncthreads();
-    }
-}
-
-__device__ __forceinline__ void store_linv(const double (*sX)[kNB + 1], double* out) {  // 64 x 64 column-major
-    for (int e = threadIdx.x; e < kNB * kNB; e += blockDim.x) out[e] = sX[e % kNB][e / kNB];
-}
-
-// smem carve-up shared by the panel kernels: sL[64][65], sX[64][65], sT[32][33], sRd[64], then (chol_small only) sPan[192][65]
-constexpr int kPanelDoubles = 2 * kNB * (kNB + 1) + 32 * 33 + kNB;  // sL, sX, sT, sRd
-constexpr int kPanelSmemBytes = (kPanelDoubles + kNB * (kNB + 1)) * (int)sizeof(double);  // + one 64-row panel
-
-// ---- U4a: Cholesky panel at block column `step` (multi-launch path, k > 256): every CTA factors the diagonal block and inverts
-//           it (redundantly: ~10 us, cheaper than a dependent launch); CTA 0 stores L_jj and inv(L_jj) (the TRSM needs it);
-//           CTA b > 0 forms row block b of the panel:  L[rb,step] = S[rb,step] * inv(L_jj)^T
-__global__ void __launch_bounds__(256) k_chol_panel(DevFilter* Fs, int step) {
-    DevFilter& F = Fs[blockIdx.y];
-    const int kk = F.ctl[CTL_K];
-    const int j0 = kNB * step;
-    if (j0 >= kk) return;
-    const int r0 = j0 + kNB * blockIdx.x;
-    if (r0 >= kk) return;
-    const int w = min(kNB, kk - j0);
-    extern __shared__ __align__(16) double psm[];
-    double(*sL)[kNB + 1] = reinterpret_cast<double(*)[kNB + 1]>(psm);
-    double(*sX)[kNB + 1] = reinterpret_cast<double(*)[kNB + 1]>(psm + kNB * (kNB + 1));
-    double(*sT)[33] = reinterpret_cast<double(*)[33]>(psm + 2 * kNB * (kNB + 1));
-    double* sRd = psm + 2 * kNB * (kNB + 1) + 32 * 33;
-    double(*sPan)[kNB + 1] = reinterpret_cast<double(*)[kNB + 1]>(psm + kPanelDoubles);
-    double* S = F.Sm;
-    const int ld = F.lds;
-    const int nr = blockIdx.x == 0 ? 0 : min(kNB, kk - r0);
-    for (int e = threadIdx.x; e < kNB * kNB; e += blockDim.x) {
-        const int i = e % kNB, c = e / kNB;
-        double v = (i == c) ? 1.0 : 0.0;
-        if (i < w && c < w && i >= c) v = S[(j0 + i) + (size_t)(j0 + c) * ld];
-        sL[i][c] = v;
-        if (nr) sPan[i][c] = (i < nr && c < w) ? S[(r0 + i) + (size_t)(j0 + c) * ld] : 0.0;
-    }
-    smem_potrf(sL, sRd, w);
-    smem_trinv(sL, sRd, sX, sT);
-    if (blockIdx.x == 0) {
-        for (int e = threadIdx.x; e < kNB * kNB; e += blockDim.x) {
-            const int i = e % kNB, c = e / kNB;
-            if (i < w && c < w) S[(j0 + i) + (size_t)(j0 + c) * ld] = (i >= c) ? sL[i][c] : 0.0;
-        }
-        store_linv(sX, F.Linv + (size_t)step * kNB * kNB);
-        return;
-    }
-    smem_panel_mul(sPan, sX, nr);
-    for (int e = threadIdx.x; e < kNB * kNB; e += blockDim.x) {
-        const int i = e % kNB, c = e / kNB;
-        if (i < nr && c < w) S[(r0 + i) + (size_t)(j0 + c) * ld] = sPan[i][c];
-    }
-}
-
-// ---- U4s: whole Cholesky (+ inverses of the diagonal blocks) in ONE CTA for small systems (k <= 256): the launch-latency
-//           path of the 100-feature configuration.
-constexpr int kCholSmallMaxK = 256;
-constexpr int kCholSmallSmemBytes = (kPanelDoubles + (kCholSmallMaxK - kNB) * (kNB + 1)) * (int)sizeof(double);
-__global__ void __launch_bounds__(256) k_chol_small(DevFilter* Fs) {
-    DevFilter& F = Fs[blockIdx.y];
-    const int kk = F.ctl[CTL_K];
-    if (kk <= 0) return;
-    extern __shared__ __align__(16) double psm[];
-    double(*sL)[kNB + 1] = reinterpret_cast<double(*)[kNB + 1]>(psm);
-    double(*sX)[kNB + 1] = reinterpret_cast<double(*)[kNB + 1]>(psm + kNB * (kNB + 1));
-    double(*sT)[33] = reinterpret_cast<double(*)[33]>(psm + 2 * kNB * (kNB + 1));
-    double* sRd = psm + 2 * kNB * (kNB + 1) + 32 * 33;
-    double(*sPan)[kNB + 1] = reinterpret_cast<double(*)[kNB + 1]>(psm + kPanelDoubles);
-    double* S = F.Sm;
-    const int ld = F.lds;
-#ifdef RSLAM_PHASE_CLOCKS
-    long long tc[6] = {0, 0, 0, 0, 0, 0};
-#define PH(i) do { __syncthreads(); const long long now__ = clock64(); tc[i] += now__ - tprev; tprev = now__; } while (0)
-    long long tprev = clock64();
-#else
-#define PH(i)
-#endif
-    for (int j0 = 0; j0 < kk; j0 += kNB) {
-        const int w = min(kNB, kk - j0);
-        const int rem = max(0, kk - (j0 + kNB));
-        for (int e = threadIdx.x; e < kNB * kNB; e += blockDim.x) {
-            const int i = e % kNB, c = e / kNB;
-            double v = (i == c) ? 1.0 : 0.0;
-            if (i < w && c < w && i >= c) v = S[(j0 + i) + (size_t)(j0 + c) * ld];
-            sL[i][c] = v;
-        }
-        for (int e = threadIdx.x; e < rem * kNB; e += blockDim.x) {
-            const int i = e % rem, c = e / rem;
-            sPan[i][c] = S[(j0 + kNB + i) + (size_t)(j0 + c) * ld];
-        }
-        PH(0);
-        smem_potrf(sL, sRd, w);
-        PH(1);
-        smem_trinv(sL, sRd, sX, sT);
-        PH(2);
-        for (int e = threadIdx.x; e < kNB * kNB; e += blockDim.x) {
-            const int i = e % kNB, c = e / kNB;
-            if (i < w && c < w) S[(j0 + i) + (size_t)(j0 + c) * ld] = (i >= c) ? sL[i][c] : 0.0;
-        }
-        store_linv(sX, F.Linv + (size_t)(j0 / kNB) * kNB * kNB);
-        PH(4);
-        if (rem <= 0) break;
-        smem_panel_mul(sPan, sX, rem);
-        PH(3);
-        for (int e = threadIdx.x; e < rem * kNB; e += blockDim.x) {
-            const int i = e % rem, c = e / rem;
-            S[(j0 + kNB + i) + (size_t)(j0 + c) * ld] = sPan[i][c];
-        }
-        PH(4);
-        // trailing update (lower triangle): lanes run down a column (coalesced), warps over columns
-        const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-        for (int bcol = wrp; bcol < rem; bcol += 8) {
-            for (int arow = bcol + lane; arow < rem; arow += 32) {
-                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-#pragma unroll 4
-                for (int c = 0; c < kNB; c += 4) {
-                    s0 += sPan[arow][c] * sPan[bcol][c];
-                    s1 += sPan[arow][c + 1] * sPan[bcol][c + 1];
-                    s2 += sPan[arow][c + 2] * sPan[bcol][c + 2];
-                    s3 += sPan[arow][c + 3] * sPan[bcol][c + 3];
-                }
-                S[(j0 + kNB + arow) + (size_t)(j0 + kNB + bcol) * ld] -= (s0 + s1) + (s2 + s3);
-            }
-        }
-        __syncthreads();
-        PH(5);
-    }
-#ifdef RSLAM_PHASE_CLOCKS
-    if (threadIdx.x == 0)
-        for (int i = 0; i < 6; i++) F.Jn[16 + i] = (double)tc[i];
-#endif
-#undef PH
-}
-
 // ---- async-copy / DMMA primitives ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -455,6 +165,297 @@ __device__ __forceinline__ void cp_async_wait() {
 }
 __device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// ---- Cholesky of the innovation covariance: 64-wide panels factorised in shared memory -------------------------------------------
+// fp64 sqrt / divide / dependent-FMA chains cost ~80-130 cycles each on this part and a CTA barrier ~30, so the panel code keeps
+// the per-column serial chain as short as possible and does everything else as wide, independent work:
+//   * a 64-wide panel (diagonal block + the rows below it, all in smem) is processed in four 16-column sub-blocks, right-looking;
+//   * the 16 x 16 diagonal sub-block is factorised by ONE warp entirely in registers (lane = row, column loop unrolled, pivots and
+//     column entries exchanged with shuffles): no barrier and no smem round trip inside the 16 dependent columns
+//     (~140 cycles per column: shuffle + rsqrt + multiply + shuffle + FMA);
+//   * the rows below are solved one thread per row by forward substitution against that sub-block (running updates, the 120
+//     multipliers are broadcast loads), which also writes a k-major copy of the 16 new columns;
+//   * the remaining columns of the panel are updated from that copy on the fp64 tensor cores (DMMA m8n8k4, K = 16);
+//   * the explicit inverse of the 64 x 64 diagonal block (the TRSM kernels multiply by it on tensor cores) is built one thread
+//     per column by forward substitution in registers, by two warps, WHILE the other warps run the trailing update.
+constexpr int kSB = 16;
+constexpr int kTld = 260;          // panel storage is k-major: entry (row i, column c) at sT[c * kTld + i]; 260 == 4 (mod 16), so DMMA
+                                   // fragment loads, thread-per-row accesses and column stores are all bank-conflict free
+constexpr int kPanRowsMax = 256;   // diagonal block (rows 0..63) + up to 192 rows below it
+// smem carve-up shared by the panel kernels: sT[64][260] panel, sX[64][65] inverse of the diagonal block, sRd[64] (1 / l_jj)
+constexpr int kPanelDoubles = kNB * kTld + kNB * (kNB + 1) + kNB;
+constexpr int kPanelSmemBytes = kPanelDoubles * (int)sizeof(double);
+constexpr int kCholSmallMaxK = 256;
+constexpr int kCholSmallSmemBytes = kPanelSmemBytes;
+
+struct PanelSmem {
+    double* sT;
+    double (*sX)[kNB + 1];
+    double* sRd;
+};
+__device__ __forceinline__ PanelSmem panel_carve(double* base) {
+    PanelSmem p;
+    p.sT = base;
+    p.sX = reinterpret_cast<double(*)[kNB + 1]>(base + kNB * kTld);
+    p.sRd = base + kNB * kTld + kNB * (kNB + 1);
+    return p;
+}
+
+// lanes 0..15 hold row `lane` of a 16 x 16 SPD block (lower triangle in a[0..lane]); on exit a[] is row `lane` of L and rd[j] =
+// 1 / l_jj on every lane.  Upper entries are garbage and must be ignored by the caller.
+__device__ __forceinline__ void warp_potrf16(double (&a)[kSB], double (&rd)[kSB]) {
+    const unsigned fm = 0xffffffffu;
+#pragma unroll
+    for (int j = 0; j < kSB; j++) {
+        const double d = __shfl_sync(fm, a[j], j);
+        const double r = rsqrt(d);
+        rd[j] = r;
+        const double lj = a[j] * r;  // l_ij (lane j: d * rsqrt(d) = sqrt(d))
+        a[j] = lj;
+#pragma unroll
+        for (int c = j + 1; c < kSB; c++) {
+            const double lc = __shfl_sync(fm, lj, c);
+            a[c] = fma(-lj, lc, a[c]);
+        }
+    }
+}
+
+// In-place factorisation of the panel in sT: rows 0..63 = diagonal block (lower triangle valid, identity padding beyond w), rows
+// 64..R-1 = the rows below it.  On exit rows 0..63 hold L_jj (lower, zeros above), rows >= 64 hold A L_jj^-T, sRd the reciprocal
+// diagonal.  CTA-collective (256 threads).
+__device__ __forceinline__ void smem_panel_factor(const PanelSmem& ps, int R, int w) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double* sT = ps.sT;
+    if (tid < kNB) ps.sRd[tid] = 1.0;
+    __syncthreads();
+    for (int c0 = 0; c0 < kNB && c0 < w; c0 += kSB) {
+        if (warp == 0) {  // (a) diagonal sub-block, in registers
+            double a[kSB], rd[kSB];
+            const int l16 = lane & 15, r = c0 + l16;
+#pragma unroll
+            for (int c = 0; c < kSB; c++) a[c] = (c <= l16) ? sT[(c0 + c) * kTld + r] : 0.0;
+            warp_potrf16(a, rd);
+            if (lane < kSB) {
+#pragma unroll
+                for (int c = 0; c < kSB; c++) sT[(c0 + c) * kTld + r] = (c <= lane) ? a[c] : 0.0;
+                double myrd = 1.0;
+#pragma unroll
+                for (int c = 0; c < kSB; c++)
+                    if (c == lane) myrd = rd[c];
+                ps.sRd[r] = myrd;
+            }
+        }
+        __syncthreads();
+        const int base = c0 + kSB;  // first row / column behind the sub-block
+        {  // (b) rows behind the sub-block: x = a L_ss^-T by forward substitution, one thread per row (multipliers are broadcast loads)
+            const int i = base + tid;
+            if (i < R) {
+                double a[kSB];
+#pragma unroll
+                for (int c = 0; c < kSB; c++) a[c] = sT[(c0 + c) * kTld + i];
+#pragma unroll
+                for (int c = 0; c < kSB; c++) {
+                    const double x = a[c] * ps.sRd[c0 + c];
+                    a[c] = x;
+#pragma unroll
+                    for (int c2 = c + 1; c2 < kSB; c2++) a[c2] = fma(-x, sT[(c0 + c) * kTld + c0 + c2], a[c2]);
+                }
+#pragma unroll
+                for (int c = 0; c < kSB; c++) sT[(c0 + c) * kTld + i] = a[c];
+            }
+        }
+        __syncthreads();
+        const int ncol = kNB - base;  // 48, 32, 16, 0 columns of the panel still to update
+        if (ncol > 0) {               // (c) A[i][c] -= sum_t x_it x_ct on DMMA tiles (rows i >= base, cols base <= c < 64, c <= i)
+            const int nrow = R - base;
+            const int MT = (nrow + 15) >> 4, NT = ncol >> 3;  // warp tile 16 x 8
+            for (int tile = warp; tile < MT * NT; tile += 8) {
+                const int mt = tile / NT, nt = tile - mt * NT;
+                if (mt * 16 + 15 < nt * 8) continue;  // entirely above the diagonal
+                double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
+#pragma unroll
+                for (int ks = 0; ks < kSB / 4; ks++) {
+                    const double* kr = sT + (c0 + ks * 4 + (lane & 3)) * kTld + base;
+                    const double bf = kr[nt * 8 + (lane >> 2)];
+                    dmma8x8x4(c00, c01, kr[mt * 16 + (lane >> 2)], bf);
+                    dmma8x8x4(c10, c11, kr[mt * 16 + 8 + (lane >> 2)], bf);
+                }
+                const int i = base + mt * 16 + (lane >> 2), cc = base + nt * 8 + 2 * (lane & 3);
+                if (i < R) {
+                    if (cc <= i) sT[cc * kTld + i] -= c00;
+                    if (cc + 1 <= i) sT[(cc + 1) * kTld + i] -= c01;
+                }
+                if (i + 8 < R) {
+                    if (cc <= i + 8) sT[cc * kTld + i + 8] -= c10;
+                    if (cc + 1 <= i + 8) sT[(cc + 1) * kTld + i + 8] -= c11;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// explicit inverse of the 64 x 64 lower-triangular diagonal block (rows 0..63 of sT, identity padded) -> sX (full 64 x 64, zeros
+// above the diagonal).  Column c of the inverse solves L x = e_c by forward substitution with running updates of the right-hand
+// side.  FOUR adjacent lanes share a column (8 columns per warp, all 8 warps busy): lane part p keeps rows i = 4 q + p in
+// registers, the owner of row t forms x_t = b_t / l_tt and hands it to its three neighbours with a shuffle, then every part
+// updates its rows behind t.  (A lone warp sustains only one shared-load-fed DFMA per ~7 cycles, so the 2016 updates of a
+// column-per-thread version cost ~24 k cycles on two warps; spread over 256 threads they take ~4 k.)  CTA-collective.
+__device__ __forceinline__ void smem_trinv64(const PanelSmem& ps) {
+    const unsigned fm = 0xffffffffu;
+    const int lane = threadIdx.x & 31, p = lane & 3;
+    const int c = (threadIdx.x >> 5) * 8 + (lane >> 2);
+    const double* sT = ps.sT;
+    double b[kNB / 4];
+#pragma unroll
+    for (int q = 0; q < kNB / 4; q++) b[q] = (4 * q + p == c) ? 1.0 : 0.0;
+#pragma unroll
+    for (int t = 0; t < kNB; t++) {
+        const double x = __shfl_sync(fm, b[t / 4] * ps.sRd[t], (lane & ~3) | (t & 3));
+        if (p == (t & 3)) ps.sX[t][c] = x;
+        // rows 4 q + p behind t; entries of rows <= t are already final (or were stored above) and may be clobbered
+#pragma unroll
+        for (int q = t / 4; q < kNB / 4; q++) b[q] = fma(-sT[t * kTld + 4 * q + p], x, b[q]);
+    }
+}
+
+__device__ __forceinline__ void store_linv(const double (*sX)[kNB + 1], double* out, int t0, int nt) {  // 64 x 64 column-major
+    for (int e = t0; e < kNB * kNB; e += nt) out[e] = sX[e % kNB][e / kNB];
+}
+
+// load the diagonal block at (j0, j0) (identity padded beyond w) and `nr` rows starting at global row r0 into the panel
+__device__ __forceinline__ void panel_load(const PanelSmem& ps, const double* S, int ld, int j0, int w, int r0, int nr) {
+    for (int e = threadIdx.x; e < kNB * kNB; e += blockDim.x) {
+        const int i = e % kNB, c = e / kNB;
+        double v = (i == c) ? 1.0 : 0.0;
+        if (i < w && c < w && i >= c) v = S[(j0 + i) + (size_t)(j0 + c) * ld];
+        ps.sT[c * kTld + i] = v;
+    }
+    for (int e = threadIdx.x; e < nr * kNB; e += blockDim.x) {
+        const int i = e % nr, c = e / nr;
+        ps.sT[c * kTld + kNB + i] = (c < w) ? S[(r0 + i) + (size_t)(j0 + c) * ld] : 0.0;
+    }
+}
+
+// ---- U4a: Cholesky panel at block column `step` (multi-launch path, k > 256): every CTA factors the diagonal block (redundantly:
+//           cheaper than a dependent launch) together with its own 64-row block of the panel; CTA 0 also builds and stores the
+//           inverse of the diagonal block (the TRSM kernel multiplies by it).
+__global__ void __launch_bounds__(256) k_chol_panel(DevFilter* Fs, int step) {
+    DevFilter& F = Fs[blockIdx.y];
+    const int kk = F.ctl[CTL_K];
+    const int j0 = kNB * step;
+    if (j0 >= kk) return;
+    const int r0 = j0 + kNB * blockIdx.x;
+    if (r0 >= kk) return;
+    const int w = min(kNB, kk - j0);
+    extern __shared__ __align__(16) double psm[];
+    const PanelSmem ps = panel_carve(psm);
+    double* S = F.Sm;
+    const int ld = F.lds;
+    const int nr = blockIdx.x == 0 ? 0 : min(kNB, kk - r0);
+    panel_load(ps, S, ld, j0, w, r0, nr);
+    __syncthreads();
+    smem_panel_factor(ps, kNB + nr, w);
+    if (blockIdx.x == 0) {
+        smem_trinv64(ps);
+        for (int e = threadIdx.x; e < kNB * kNB; e += blockDim.x) {
+            const int i = e % kNB, c = e / kNB;
+            if (i < w && c < w) S[(j0 + i) + (size_t)(j0 + c) * ld] = ps.sT[c * kTld + i];
+        }
+        __syncthreads();
+        store_linv(ps.sX, F.Linv + (size_t)step * kNB * kNB, threadIdx.x, blockDim.x);
+        return;
+    }
+    for (int e = threadIdx.x; e < nr * kNB; e += blockDim.x) {
+        const int i = e % nr, c = e / nr;
+        if (c < w) S[(r0 + i) + (size_t)(j0 + c) * ld] = ps.sT[c * kTld + kNB + i];
+    }
+}
+
+// ---- U4s: whole Cholesky (+ inverses of the diagonal blocks) in ONE CTA for small systems (k <= 256): the launch-latency
+//           path of the 100-feature configuration.
+__global__ void __launch_bounds__(256) k_chol_small(DevFilter* Fs) {
+    DevFilter& F = Fs[blockIdx.y];
+    const int kk = F.ctl[CTL_K];
+    if (kk <= 0) return;
+    extern __shared__ __align__(16) double psm[];
+    const PanelSmem ps = panel_carve(psm);
+    double* S = F.Sm;
+    const int ld = F.lds;
+#ifdef RSLAM_PHASE_CLOCKS
+    long long tc[6] = {0, 0, 0, 0, 0, 0};
+#define PH(i) do { __syncthreads(); const long long now__ = clock64(); tc[i] += now__ - tprev; tprev = now__; } while (0)
+    long long tprev = clock64();
+#else
+#define PH(i)
+#endif
+    for (int j0 = 0; j0 < kk; j0 += kNB) {
+        const int w = min(kNB, kk - j0);
+        const int rem = max(0, kk - (j0 + kNB));
+        panel_load(ps, S, ld, j0, w, j0 + kNB, rem);
+        __syncthreads();
+        PH(0);
+        smem_panel_factor(ps, kNB + rem, w);
+        PH(1);
+        // inverse of the diagonal block (all warps), then store the panel and run the trailing update on DMMA tiles
+        smem_trinv64(ps);
+        {
+            const int t = threadIdx.x, nt = blockDim.x;
+            for (int e = t; e < kNB * kNB; e += nt) {
+                const int i = e % kNB, c = e / kNB;
+                if (i < w && c < w) S[(j0 + i) + (size_t)(j0 + c) * ld] = ps.sT[c * kTld + i];
+            }
+            for (int e = t; e < rem * kNB; e += nt) {
+                const int i = e % rem, c = e / rem;
+                S[(j0 + kNB + i) + (size_t)(j0 + c) * ld] = ps.sT[c * kTld + kNB + i];
+            }
+            // trailing update S[a, b] -= sum_c X[a, c] X[b, c] (lower triangle), warp tiles 16 x 32 straight from the k-major panel
+            const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+            const int MT = (rem + 15) >> 4, NT = (rem + 31) >> 5;
+            for (int tile = wrp; tile < MT * NT; tile += 8) {
+                const int mt = tile / NT, nt2 = tile - mt * NT;
+                if (mt * 16 + 15 < nt2 * 32) continue;
+                double acc[2][4][2];
+#pragma unroll
+                for (int a = 0; a < 2; a++)
+#pragma unroll
+                    for (int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+#pragma unroll 4
+                for (int ks = 0; ks < kNB / 4; ks++) {
+                    const double* kr = ps.sT + (ks * 4 + (lane & 3)) * kTld + kNB;
+                    double af[2], bf[4];
+#pragma unroll
+                    for (int a = 0; a < 2; a++) af[a] = kr[mt * 16 + a * 8 + (lane >> 2)];
+#pragma unroll
+                    for (int b = 0; b < 4; b++) bf[b] = kr[nt2 * 32 + b * 8 + (lane >> 2)];
+#pragma unroll
+                    for (int a = 0; a < 2; a++)
+#pragma unroll
+                        for (int b = 0; b < 4; b++) dmma8x8x4(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+                }
+#pragma unroll
+                for (int a = 0; a < 2; a++)
+#pragma unroll
+                    for (int b = 0; b < 4; b++)
+#pragma unroll
+                        for (int e = 0; e < 2; e++) {
+                            const int ar = mt * 16 + a * 8 + (lane >> 2), bc = nt2 * 32 + b * 8 + 2 * (lane & 3) + e;
+                            if (ar < rem && bc <= ar) S[(j0 + kNB + ar) + (size_t)(j0 + kNB + bc) * ld] -= acc[a][b][e];
+                        }
+            }
+        }
+        __syncthreads();
+        PH(2);
+        store_linv(ps.sX, F.Linv + (size_t)(j0 / kNB) * kNB * kNB, threadIdx.x, blockDim.x);
+        __syncthreads();  // the trailing update must have landed before the next panel is loaded; sX / sT are reused
+        PH(3);
+    }
+#ifdef RSLAM_PHASE_CLOCKS
+    if (threadIdx.x == 0)
+        for (int i = 0; i < 6; i++) F.Jn[16 + i] = (double)tc[i];
+#endif
+#undef PH
 }
 
 // ---- U5: TRSM  V = W L^-T  for all n+1 rows of W (row n: the innovation, which becomes y = L^-1 nu), ONE launch ---------------
