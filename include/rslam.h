@@ -157,6 +157,30 @@ int rslam_support_sweep(rslam_filter* f, const int* hyp_match_idx, int n_hyp, in
 /* inlier mask of one hypothesis id after a sweep that covered it (for the rank that owns the all-reduced winner) */
 int rslam_sweep_mask(rslam_filter* f, int match_idx, uint8_t* mask);
 
+/* --- map management with the covariance resident on the device (src/Map.cpp) -------------------------- */
+/* All of these act on x_k_k / p_k_k of filter b, like the reference between two frames (src/System.cpp:111).  Each rewrites the
+ * covariance once, out of place, into a spare buffer owned by the handle and swaps the two (16 n^2 bytes of HBM traffic). */
+/* features_info.erase + Map::delete_a_feature (src/Map.cpp:27-28, 69-104) for feature `index` (0-based), consistently. */
+int rslam_map_delete_feature(rslam_filter* f, int b, int index);
+/* Map::map_management step 1 (src/Map.cpp:19-32): delete every feature with times_measured < 0.5 * times_predicted and
+ * times_predicted > 5.  reference_indexing != 0 reproduces the reference's loop exactly: delete_a_feature receives the loop counter,
+ * which runs ahead of the iterator after the first erase, so from the second deletion of a pass on the state block of a LATER
+ * feature is removed; RSLAM_ERR_REFERENCE_UB is returned where the reference would index past the end.  0 = consistent deletion. */
+int rslam_map_delete_features(rslam_filter* f, int b, int reference_indexing, int* n_deleted);
+/* Map::inversedepth_2_cartesian (src/Map.cpp:105-196): converts the FIRST inverse-depth feature whose linearity index is below 0.1
+ * (at most one per call, like the reference); *converted_index = its index or -1. */
+int rslam_map_inversedepth_to_cartesian(rslam_filter* f, int b, int* converted_index);
+/* step 4 of Map::initialize_a_features (src/Map.cpp:268-311) for the corner uv[2] (distorted pixel): ExtendKF::hinv
+ * (src/ExtendKF.cpp:236-265), Map::add_a_feature_covariance_inverse_depth (src/Map.cpp:339-400) and the new features_info record
+ * (41x41 patch cut from the image currently bound to the filter, pose and pixel at initialisation). */
+int rslam_map_add_feature(rslam_filter* f, int b, const double* uv, int* new_index);
+/* feature types of filter b (0 inverse depth, 1 cartesian), types[N] */
+int rslam_feature_types(rslam_filter* f, int b, int* types);
+/* overwrite times_predicted / times_measured of filter b (restoring a saved map; tests) */
+int rslam_set_counters(rslam_filter* f, int b, const int* times_predicted, const int* times_measured);
+/* record stored at initialisation for feature i: patch41[1681] (row-major), pose14 = r_wc(3), R_wc row-major(9), uv(2) */
+int rslam_download_feature_init(rslam_filter* f, int b, int i, uint8_t* patch41, double* pose14);
+
 #ifdef __cplusplus
 }
 #endif

@@ -61,6 +61,13 @@ def lib():
         _lib.orc_undistort.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         _lib.orc_lu_inverse.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         _lib.orc_dgemm.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        _lib.orc_map_delete_pass.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        _lib.orc_map_delete_feature.argtypes = [C.c_void_p, C.c_int]
+        _lib.orc_map_inversedepth_to_cartesian.argtypes = [C.c_void_p]
+        _lib.orc_map_add_feature.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+        _lib.orc_set_counters.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.orc_get_types.argtypes = [C.c_void_p, C.c_void_p]
+        _lib.orc_get_feature_init.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     return _lib
 
 
@@ -185,6 +192,45 @@ class OracleFilter:
         out = np.zeros_like(uv)
         self.L.orc_undistort(self.h, _p(uv), uv.shape[0], _p(out))
         return out
+
+    # ---- Map management (src/Map.cpp) ----
+    def map_delete_pass(self, reference_indexing=True):
+        """Map::map_management step 1 (src/Map.cpp:19-32); returns (status, n_deleted); status -4 = the reference reads out of range"""
+        nd = C.c_int(0)
+        rc = self.L.orc_map_delete_pass(self.h, int(reference_indexing), C.byref(nd))
+        return rc, nd.value
+
+    def map_delete_feature(self, index):
+        return self.L.orc_map_delete_feature(self.h, int(index))
+
+    def map_inversedepth_to_cartesian(self):
+        """Map::inversedepth_2_cartesian (src/Map.cpp:105-196); returns the converted feature index or -1"""
+        return self.L.orc_map_inversedepth_to_cartesian(self.h)
+
+    def map_add_feature(self, uv, image=None):
+        """hinv + add_a_feature_covariance_inverse_depth + features_info.push_back (src/Map.cpp:268-311, 339-400)"""
+        uv = _f64(uv)
+        if image is None:
+            return self.L.orc_map_add_feature(self.h, _p(uv), None, 0, 0, 0)
+        img = np.ascontiguousarray(image, dtype=np.uint8)
+        return self.L.orc_map_add_feature(self.h, _p(uv), _p(img), img.shape[0], img.shape[1], img.shape[1])
+
+    def set_counters(self, times_predicted, times_measured):
+        tp = np.ascontiguousarray(times_predicted, dtype=np.int32)
+        tm = np.ascontiguousarray(times_measured, dtype=np.int32)
+        self.L.orc_set_counters(self.h, _p(tp), _p(tm))
+
+    def types(self):
+        t = np.zeros(self.N, dtype=np.int32)
+        if self.N:
+            self.L.orc_get_types(self.h, _p(t))
+        return t
+
+    def feature_init(self, i):
+        patch = np.zeros((41, 41), dtype=np.uint8)
+        pose = np.zeros(14)
+        self.L.orc_get_feature_init(self.h, int(i), _p(patch), _p(pose))
+        return patch, pose
 
     def frame(self, image, u01, predict=True):
         """One TrackRunning pass (src/System.cpp:111-129) without Map feature add/delete."""

@@ -1019,6 +1019,224 @@ static void map_reset_flags(Filter& F) {
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Map management (src/Map.cpp) -- SURVEY 8f row 3
+// ---------------------------------------------------------------------------------------------------------
+// Map::delete_a_feature (src/Map.cpp:69-104).  feature_id is 1-based and the type is read from features_info[feature_id-1] as it
+// stands at call time (map_management has already erased the record, src/Map.cpp:27-28).  Returns -4 where the reference reads out
+// of range.
+static int delete_a_feature(Filter& F, int feature_id) {
+    if (feature_id - 1 < 0 || feature_id - 1 >= (int)F.fi.size()) return -4;
+    int parToDelete = F.fi[feature_id - 1].type == 1 ? 3 : 6;
+    int indexFromWichDelete = 14 - 1;
+    for (int i = 0; i < feature_id - 1; i++) indexFromWichDelete += F.fi[i].type == 0 ? 6 : 3;
+    const int n = F.x_k_k.rows();
+    int delete_surplus = n - (indexFromWichDelete + parToDelete);
+    if (delete_surplus < 0) return -4;
+    Mat x_temp(n - parToDelete, 1);
+    Mat p_temp(n - parToDelete, n - parToDelete);
+    for (int i = 0; i < indexFromWichDelete; i++) x_temp[i] = F.x_k_k[i];
+    for (int i = 0; i < delete_surplus; i++) x_temp[indexFromWichDelete + i] = F.x_k_k[n - delete_surplus + i];
+    F.x_k_k = x_temp;
+    const int a = indexFromWichDelete, d = delete_surplus;
+    p_temp.set_block(0, 0, F.p_k_k.block(0, 0, a, a));
+    p_temp.set_block(0, a, F.p_k_k.block(0, n - d, a, d));
+    p_temp.set_block(a, 0, F.p_k_k.block(n - d, 0, d, a));
+    p_temp.set_block(a, a, F.p_k_k.block(n - d, n - d, d, d));
+    F.p_k_k = p_temp;
+    return 0;
+}
+
+// Map::map_management step 1 (src/Map.cpp:19-32).  reference_indexing: pass the loop counter i to delete_a_feature exactly like the
+// reference (it runs ahead of the iterator after the first erase); otherwise delete the state block of the erased record.
+static int map_delete_pass(Filter& F, bool reference_indexing, int* n_deleted) {
+    int i = 1, deleted = 0;
+    for (size_t pos = 0; pos < F.fi.size(); i++) {
+        const Feature& ft = F.fi[pos];
+        if (ft.times_measured < ft.times_predicted * 0.5 && ft.times_predicted > 5) {
+            if (reference_indexing) {
+                F.fi.erase(F.fi.begin() + pos);
+                int rc = delete_a_feature(F, i);
+                if (rc) return rc;
+            } else {
+                // consistent variant: delete_a_feature reads the type at [id-1], so call it with the record's own id, then erase
+                int rc = delete_a_feature(F, (int)pos + 1);
+                if (rc) return rc;
+                F.fi.erase(F.fi.begin() + pos);
+            }
+            deleted++;
+        } else {
+            pos++;
+        }
+    }
+    if (n_deleted) *n_deleted = deleted;
+    return state_dim(F) == F.x_k_k.rows() ? 0 : -4;
+}
+
+// Map::inversedepth_2_cartesian (src/Map.cpp:105-196): converts the first inverse-depth feature whose linearity index is below 0.1
+// (dense J_all * P * J_all^T like the reference); returns its index or -1.
+static int inversedepth_2_cartesian_map(Filter& F) {
+    const double linearity_index_threshold = 0.1;
+    Mat X = F.x_k_k, P = F.p_k_k;
+    for (size_t i = 0; i < F.fi.size(); i++) {
+        if (F.fi[i].type != 0) continue;
+        int ip = state_offset(F, (int)i);
+        double std_rho = std::sqrt(P(ip + 5, ip + 5));
+        double rho = X[ip + 5];
+        double std_d = std_rho / (rho * rho);
+        double theta = X[ip + 3], phi = X[ip + 4];
+        double mi[3] = {std::cos(phi) * std::sin(theta), -std::sin(phi), std::cos(phi) * std::cos(theta)};
+        double X_out[3];
+        inversedepth2cartesian(&X.a[ip], X_out);
+        double a = 0, n1 = 0, n2 = 0;
+        for (int k = 0; k < 3; k++) {
+            a += (X_out[k] - X[ip + k]) * (X_out[k] - X[k]);
+            n1 += (X_out[k] - X[ip + k]) * (X_out[k] - X[ip + k]);
+            n2 += (X_out[k] - X[k]) * (X_out[k] - X[k]);
+        }
+        double d_c2p = std::sqrt(n2);
+        double cos_alpha = a / (std::sqrt(n1) * std::sqrt(n2));
+        double linearity_index = 4 * std_d * cos_alpha / d_c2p;
+        if (linearity_index < linearity_index_threshold) {
+            const int size_X_old = X.rows();
+            Mat Xe(size_X_old - 3, 1);
+            for (int k = 0; k < ip; k++) Xe[k] = X[k];
+            for (int k = 0; k < 3; k++) Xe[ip + k] = X_out[k];
+            for (int k = ip + 6; k < size_X_old; k++) Xe[k - 3] = X[k];
+            F.x_k_k = Xe;
+            double dmt[3] = {std::cos(phi) * std::cos(theta), 0, -std::cos(phi) * std::sin(theta)};
+            double dmp[3] = {-std::sin(phi) * std::sin(theta), -std::cos(phi), -std::sin(phi) * std::cos(theta)};
+            Mat J_all(size_X_old - 3, size_X_old);
+            for (int k = 0; k < ip; k++) J_all(k, k) = 1.0;
+            for (int r = 0; r < 3; r++) {
+                J_all(ip + r, ip + r) = 1.0;
+                J_all(ip + r, ip + 3) = (1 / rho) * dmt[r];
+                J_all(ip + r, ip + 4) = (1 / rho) * dmp[r];
+                J_all(ip + r, ip + 5) = -mi[r] / (rho * rho);
+            }
+            for (int k = ip + 6; k < size_X_old; k++) J_all(k - 3, k) = 1.0;
+            F.p_k_k = mul_nt(J_all * P, J_all);
+            F.fi[i].type = 1;
+            return (int)i;
+        }
+    }
+    return -1;
+}
+
+// ExtendKF::hinv (src/ExtendKF.cpp:236-265)
+static void hinv(const Filter& F, const double* uvd, const double* Xv, double initial_rho, double* newFeature) {
+    const Cam& cam = F.cam;
+    double fku = cam.K(0, 0), fkv = cam.K(1, 1), U0 = cam.K(0, 2), V0 = cam.K(1, 2);
+    Mat uvdm(2, 1);
+    uvdm[0] = uvd[0];
+    uvdm[1] = uvd[1];
+    Mat uv = undistort_fm(cam, uvdm);
+    double h_LR[3] = {-(U0 - uv[0]) / fku, -(V0 - uv[1]) / fkv, 1};
+    Mat R = q2r(Xv + 3);
+    double n[3];
+    for (int r = 0; r < 3; r++) n[r] = R(r, 0) * h_LR[0] + R(r, 1) * h_LR[1] + R(r, 2) * h_LR[2];
+    newFeature[0] = Xv[0];
+    newFeature[1] = Xv[1];
+    newFeature[2] = Xv[2];
+    newFeature[3] = std::atan2(n[0], n[2]);
+    newFeature[4] = std::atan2(-n[1], std::sqrt(n[0] * n[0] + n[2] * n[2]));
+    newFeature[5] = initial_rho;
+}
+
+// Map::add_a_feature_covariance_inverse_depth (src/Map.cpp:339-400)
+static Mat add_a_feature_covariance_inverse_depth(const Filter& F, const Mat& P, const double* uvd, const double* Xv) {
+    const Cam& cam = F.cam;
+    double fku = cam.K(0, 0), fkv = cam.K(1, 1), U0 = cam.K(0, 2), V0 = cam.K(1, 2);
+    Mat R_wc = q2r(Xv + 3);
+    Mat uvdm(2, 1);
+    uvdm[0] = uvd[0];
+    uvdm[1] = uvd[1];
+    Mat uvu = undistort_fm(cam, uvdm);
+    double XYZ_c[3] = {-(U0 - uvu[0]) / fku, -(V0 - uvu[1]) / fkv, 1};
+    double XYZ_w[3];
+    for (int r = 0; r < 3; r++) XYZ_w[r] = R_wc(r, 0) * XYZ_c[0] + R_wc(r, 1) * XYZ_c[1] + R_wc(r, 2) * XYZ_c[2];
+    double X_w = XYZ_w[0], Y_w = XYZ_w[1], Z_w = XYZ_w[2];
+    Mat dgw_dqwr = dRq_times_a_by_dq(Xv + 3, XYZ_c);
+    Mat dtheta_dgw(1, 3), dphi_dgw(1, 3);
+    dtheta_dgw[0] = Z_w / (X_w * X_w + Z_w * Z_w);
+    dtheta_dgw[1] = 0;
+    dtheta_dgw[2] = -X_w / (X_w * X_w + Z_w * Z_w);
+    dphi_dgw[0] = (X_w * Y_w) / ((X_w * X_w + Y_w * Y_w + Z_w * Z_w) * std::sqrt(X_w * X_w + Z_w * Z_w));
+    dphi_dgw[1] = -std::sqrt(X_w * X_w + Z_w * Z_w) / (X_w * X_w + Y_w * Y_w + Z_w * Z_w);
+    dphi_dgw[2] = (Z_w * Y_w) / ((X_w * X_w + Y_w * Y_w + Z_w * Z_w) * std::sqrt(X_w * X_w + Z_w * Z_w));
+    Mat dy_dxv(6, 13);
+    for (int k = 0; k < 3; k++) dy_dxv(k, k) = 1.0;
+    dy_dxv.set_block(3, 3, dtheta_dgw * dgw_dqwr);
+    dy_dxv.set_block(4, 3, dphi_dgw * dgw_dqwr);
+    Mat dyprima_dgw(5, 3);
+    dyprima_dgw.set_block(3, 0, dtheta_dgw);
+    dyprima_dgw.set_block(4, 0, dphi_dgw);
+    Mat dgc_dhu(3, 2);
+    dgc_dhu(0, 0) = 1 / fku;
+    dgc_dhu(1, 1) = 1 / fkv;
+    Mat dhu_dhd = jacob_undistor_fm(cam, uvd);
+    Mat dyprima_dhd = dyprima_dgw * R_wc * dgc_dhu * dhu_dhd;
+    Mat dy_dhd(6, 3);
+    dy_dhd.set_block(0, 0, dyprima_dhd);
+    dy_dhd(5, 2) = 1;
+    Mat Padd(3, 3);
+    Padd(0, 0) = Padd(1, 1) = std::pow(F.std_z, 2);
+    Padd(2, 2) = std::pow(1, 2);
+    const int P_len = P.rows();
+    Mat P_xv = P.block(0, 0, 13, 13);
+    Mat P_yxv = P.block(13, 0, P_len - 13, 13);
+    Mat P_y = P.block(13, 13, P_len - 13, P_len - 13);
+    Mat P_xvy = P.block(0, 13, 13, P_len - 13);
+    Mat P_RES1 = mul_nt(P_xv, dy_dxv);
+    Mat P_RES2 = mul_nt(P_yxv, dy_dxv);
+    Mat P_RES3 = mul_nt(dy_dxv * P_xv, dy_dxv) + mul_nt(dy_dhd * Padd, dy_dhd);
+    Mat P_RES(P_len + 6, P_len + 6);
+    P_RES.set_block(0, 0, P_xv);
+    P_RES.set_block(0, 13, P_xvy);
+    P_RES.set_block(0, P_len, P_RES1);
+    P_RES.set_block(13, 0, P_yxv);
+    P_RES.set_block(13, 13, P_y);
+    P_RES.set_block(13, P_len, P_RES2);
+    P_RES.set_block(P_len, 0, dy_dxv * P_xv);
+    P_RES.set_block(P_len, 13, dy_dxv * P_xvy);
+    P_RES.set_block(P_len, P_len, P_RES3);
+    return P_RES;
+}
+
+// step 4 of Map::initialize_a_features (src/Map.cpp:268-311) for a given corner uv: state, covariance and the feature record
+static int map_add_feature(Filter& F, const double* uv, const uint8_t* image, int rows, int cols, int stride) {
+    const int initial_rho = 1;
+    Mat X_RES = F.x_k_k, P_RES = F.p_k_k;
+    double Xv[13];
+    for (int k = 0; k < 13; k++) Xv[k] = F.x_k_k[k];
+    double newFeature[6];
+    hinv(F, uv, Xv, initial_rho, newFeature);
+    Mat Xn(X_RES.rows() + 6, 1);
+    for (int k = 0; k < X_RES.rows(); k++) Xn[k] = X_RES[k];
+    for (int k = 0; k < 6; k++) Xn[X_RES.rows() + k] = newFeature[k];
+    F.p_k_k = add_a_feature_covariance_inverse_depth(F, P_RES, uv, Xv);
+    F.x_k_k = Xn;
+    Feature nf;
+    nf.patch_when_initialized = Mat(41, 41);
+    const int u0 = (int)(uv[0] - 20), v0 = (int)(uv[1] - 20);  // cv::Range(double) truncates (src/Map.cpp:286)
+    for (int r = 0; r < 41; r++)
+        for (int c = 0; c < 41; c++) {
+            int gy = v0 + r, gx = u0 + c;
+            nf.patch_when_initialized(r, c) = (image && gx >= 0 && gx < cols && gy >= 0 && gy < rows) ? image[(size_t)gy * stride + gx] : 0;
+        }
+    nf.patch_when_matching = Mat(13, 13);
+    nf.patch_template = Mat(13, 13);
+    for (int k = 0; k < 3; k++) nf.r_wc_when_initialized[k] = Xn[k];
+    nf.R_wc_when_initialized = q2r(&Xn.a[3]);
+    nf.uv_when_initialized[0] = uv[0];
+    nf.uv_when_initialized[1] = uv[1];
+    nf.type = 0;
+    nf.R = Mat::Identity(2);
+    F.fi.push_back(nf);
+    return (int)F.fi.size() - 1;
+}
+
 }  // namespace orc
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1235,5 +1453,42 @@ void orc_lu_inverse(const double* A_colmajor, int n, double* out_colmajor) {
 }
 void orc_dgemm(int tA, int tB, int M, int N, int K, const double* A, int lda, const double* B, int ldb, double* C, int ldc) {
     dgemm(tA != 0, tB != 0, M, N, K, A, lda, B, ldb, C, ldc);
+}
+
+// --- map management -------------------------------------------------------------------------------------------------------
+int orc_map_delete_pass(void* h, int reference_indexing, int* n_deleted) { return map_delete_pass(*(Filter*)h, reference_indexing != 0, n_deleted); }
+int orc_map_delete_feature(void* h, int index) {
+    Filter& F = *(Filter*)h;
+    if (index < 0 || index >= (int)F.fi.size()) return -1;
+    int rc = delete_a_feature(F, index + 1);
+    if (rc) return rc;
+    F.fi.erase(F.fi.begin() + index);
+    return 0;
+}
+int orc_map_inversedepth_to_cartesian(void* h) { return inversedepth_2_cartesian_map(*(Filter*)h); }
+int orc_map_add_feature(void* h, const double* uv, const uint8_t* image, int rows, int cols, int stride) {
+    return map_add_feature(*(Filter*)h, uv, image, rows, cols, stride);
+}
+void orc_set_counters(void* h, const int* times_predicted, const int* times_measured) {
+    Filter& F = *(Filter*)h;
+    for (size_t i = 0; i < F.fi.size(); i++) {
+        F.fi[i].times_predicted = times_predicted[i];
+        F.fi[i].times_measured = times_measured[i];
+    }
+}
+void orc_get_types(void* h, int* types) {
+    Filter& F = *(Filter*)h;
+    for (size_t i = 0; i < F.fi.size(); i++) types[i] = F.fi[i].type;
+}
+void orc_get_feature_init(void* h, int i, uint8_t* patch41, double* pose14) {
+    Filter& F = *(Filter*)h;
+    const Feature& ft = F.fi[i];
+    for (int r = 0; r < 41; r++)
+        for (int c = 0; c < 41; c++) patch41[r * 41 + c] = (uint8_t)ft.patch_when_initialized(r, c);
+    for (int k = 0; k < 3; k++) pose14[k] = ft.r_wc_when_initialized[k];
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) pose14[3 + 3 * r + c] = ft.R_wc_when_initialized(r, c);
+    pose14[12] = ft.uv_when_initialized[0];
+    pose14[13] = ft.uv_when_initialized[1];
 }
 }

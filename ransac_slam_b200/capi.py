@@ -90,6 +90,13 @@ def load():
     L.rslam_profile_read.argtypes = [vp, C.c_char_p, C.c_size_t]
     L.rslam_support_sweep.argtypes = [vp, vp, ci, ci, ci, ci, ci, vp, vp, vp]
     L.rslam_sweep_mask.argtypes = [vp, ci, vp]
+    L.rslam_map_delete_feature.argtypes = [vp, ci, ci]
+    L.rslam_map_delete_features.argtypes = [vp, ci, ci, vp]
+    L.rslam_map_inversedepth_to_cartesian.argtypes = [vp, ci, vp]
+    L.rslam_map_add_feature.argtypes = [vp, ci, vp, vp]
+    L.rslam_feature_types.argtypes = [vp, ci, vp]
+    L.rslam_set_counters.argtypes = [vp, ci, vp, vp]
+    L.rslam_download_feature_init.argtypes = [vp, ci, ci, vp, vp]
     _lib = L
     return L
 
@@ -275,6 +282,47 @@ class Filter:
             self._keep.append(u)
         self._ck(self.L.rslam_frame(self.h, ip, rows, cols, stride, int(share), up, n_u01, 1 if predict else 0))
 
+    # ---- Map management (src/Map.cpp), covariance resident on the device ----
+    def map_delete_feature(self, index, b=0):
+        self._ck(self.L.rslam_map_delete_feature(self.h, b, int(index)))
+
+    def map_delete_features(self, reference_indexing=True, b=0):
+        """returns (status, n_deleted); status RSLAM_ERR_REFERENCE_UB (-4) where the reference indexes out of range"""
+        nd = C.c_int(0)
+        rc = self.L.rslam_map_delete_features(self.h, b, int(reference_indexing), C.byref(nd))
+        if rc not in (0, -4):
+            self._ck(rc)
+        return rc, nd.value
+
+    def map_inversedepth_to_cartesian(self, b=0):
+        idx = C.c_int(-1)
+        self._ck(self.L.rslam_map_inversedepth_to_cartesian(self.h, b, C.byref(idx)))
+        return idx.value
+
+    def map_add_feature(self, uv, b=0):
+        uv = np.ascontiguousarray(uv, dtype=np.float64)
+        idx = C.c_int(-1)
+        self._ck(self.L.rslam_map_add_feature(self.h, b, _p(uv), C.byref(idx)))
+        return idx.value
+
+    def types(self, b=0):
+        N = self.L.rslam_num_features(self.h, b)
+        t = np.zeros(N, dtype=np.int32)
+        if N:
+            self._ck(self.L.rslam_feature_types(self.h, b, _p(t)))
+        return t
+
+    def set_counters(self, times_predicted, times_measured, b=0):
+        tp = np.ascontiguousarray(times_predicted, dtype=np.int32)
+        tm = np.ascontiguousarray(times_measured, dtype=np.int32)
+        self._ck(self.L.rslam_set_counters(self.h, b, _p(tp), _p(tm)))
+
+    def feature_init(self, i, b=0):
+        patch = np.zeros((41, 41), dtype=np.uint8)
+        pose = np.zeros(14)
+        self._ck(self.L.rslam_download_feature_init(self.h, b, int(i), _p(patch), _p(pose)))
+        return patch, pose
+
     def set_graph(self, enable):
         self._ck(self.L.rslam_set_graph(self.h, int(enable)))
 
@@ -292,6 +340,14 @@ class Filter:
 
     def sync(self):
         self._ck(self.L.rslam_sync(self.h))
+
+    @property
+    def N(self):
+        return self.L.rslam_num_features(self.h, 0)
+
+    @property
+    def n(self):
+        return self.L.rslam_state_dim(self.h, 0)
 
     @property
     def stream(self):

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "kernels_map.cuh"
 #include "kernels_track.cuh"
 #include "kernels_update.cuh"
 
@@ -43,6 +44,13 @@ struct rslam_filter {
     cudaStream_t stream = nullptr;
     long long launches = 0;
     std::vector<DevFilter> hF;  // host mirror of the device descriptors
+    std::vector<std::vector<int>> htype;  // host mirror of the feature types (the map-management entry points edit the feature list)
+    // map surgery scratch (allocated on first use): one spare covariance / state vector that is swapped with the filter's own
+    double* map_P = nullptr;
+    double* map_x = nullptr;
+    double* map_coef = nullptr;
+    int* map_res = nullptr;
+    unsigned char* map_tmp = nullptr;  // staging for erasing one entry of the per-feature arrays
     DevFilter* dF = nullptr;
     std::vector<void*> allocs;
     // shared buffers
@@ -306,6 +314,7 @@ int rslam_create(const rslam_camera* cam, const rslam_params* par, int max_featu
 
     const int B = batch, N = max_features, n = f->nmax;
     f->hF.assign(B, DevFilter{});
+    f->htype.assign(B, std::vector<int>());
     int rc = 0;
     double *P, *xkk, *xkm1, *h, *Hc, *Hf, *S, *z, *hyp_ab, *hyp_xcam, *Jn;
     int *ftype, *foff, *tp, *tm, *ic_list, *id_list, *id_pos, *support, *ctl, *upd_list;
@@ -434,6 +443,7 @@ int rslam_upload_state(rslam_filter* f, int b, int which, const double* x, const
     }
     if (off != n) return fail(RSLAM_ERR_INVALID, "rslam_upload_state: n = %d does not match 13 + sum(feature sizes) = %d", n, off);
     DevFilter& D = f->hF[b];
+    f->htype[b] = types;
     const bool shape_changed = (D.n != n) || (D.N != N);
     D.n = n;
     D.N = N;
@@ -977,4 +987,259 @@ int rslam_sweep_mask(rslam_filter* f, int match_idx, uint8_t* mask) {
     return RSLAM_OK;
 }
 
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Map management on the device (src/Map.cpp): the covariance stays in HBM while features are deleted, converted and added
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+
+int ensure_map_ws(rslam_filter* f) {
+    if (f->map_P) return 0;
+    int rc;
+    if ((rc = dev_alloc(f, &f->map_P, (size_t)f->ldp * f->nmax))) return rc;
+    if ((rc = dev_alloc(f, &f->map_x, (size_t)f->nmax))) return rc;
+    if ((rc = dev_alloc(f, &f->map_coef, (size_t)kMapScratch))) return rc;
+    if ((rc = dev_alloc(f, &f->map_res, (size_t)4))) return rc;
+    if ((rc = dev_alloc(f, &f->map_tmp, (size_t)f->Nmax * 1681))) return rc;
+    return 0;
+}
+
+// recompute offsets / last inverse-depth index from the host type list and push them with the descriptor
+int map_sync_layout(rslam_filter* f, int b) {
+    DevFilter& D = f->hF[b];
+    const std::vector<int>& types = f->htype[b];
+    const int N = (int)types.size();
+    std::vector<int> offs(N), lastid(N);
+    int off = 13, last = -1;
+    for (int i = 0; i < N; i++) {
+        offs[i] = off;
+        off += types[i] == 0 ? 6 : 3;
+        if (types[i] == 0) last = i;
+        lastid[i] = last;
+    }
+    D.N = N;
+    if (N) {
+        CK(cudaMemcpyAsync(D.ftype, types.data(), sizeof(int) * N, cudaMemcpyHostToDevice, f->stream));
+        CK(cudaMemcpyAsync(D.foff, offs.data(), sizeof(int) * N, cudaMemcpyHostToDevice, f->stream));
+        CK(cudaMemcpyAsync(D.last_id, lastid.data(), sizeof(int) * N, cudaMemcpyHostToDevice, f->stream));
+    }
+    f->hN = 0;
+    f->hn = 0;
+    for (int k = 0; k < f->B; k++) {
+        f->hN = f->hF[k].N > f->hN ? f->hF[k].N : f->hN;
+        f->hn = f->hF[k].n > f->hn ? f->hF[k].n : f->hn;
+    }
+    CK(cudaStreamSynchronize(f->stream));  // offs / lastid are stack vectors
+    return push_descr(f);
+}
+
+// run P' = T P T^T + E, x' = T x into the spare buffers and swap them in
+int map_apply(rslam_filter* f, int b, const MapXform& xf) {
+    DevFilter& D = f->hF[b];
+    LAUNCH(f, k_map_xform, dim3(cdiv(xf.n_new, 256), xf.n_new), 256, 0, f->dF, b, xf, (const double*)f->map_coef, f->map_P, f->map_x);
+    std::swap(D.P, f->map_P);
+    std::swap(D.x_kk, f->map_x);
+    D.n = xf.n_new;
+    int rc = check_launch();
+    if (rc) return rc;
+    return push_descr(f);  // the next kernel must see the swapped buffers
+}
+
+// erase entry p of a per-feature device array (count entries of elem bytes), through the staging buffer
+int erase_entry(rslam_filter* f, void* base, size_t elem, int count, int p) {
+    const size_t tail = (size_t)(count - 1 - p) * elem;
+    if (tail == 0) return 0;
+    unsigned char* bp = (unsigned char*)base;
+    CK(cudaMemcpyAsync(f->map_tmp, bp + (size_t)(p + 1) * elem, tail, cudaMemcpyDeviceToDevice, f->stream));
+    CK(cudaMemcpyAsync(bp + (size_t)p * elem, f->map_tmp, tail, cudaMemcpyDeviceToDevice, f->stream));
+    return 0;
+}
+
+// features_info.erase(it) (src/Map.cpp:27): drop the record, not the state
+int map_erase_info(rslam_filter* f, int b, int p) {
+    DevFilter& D = f->hF[b];
+    const int N = D.N;
+    int rc;
+    if ((rc = erase_entry(f, D.times_predicted, sizeof(int), N, p))) return rc;
+    if ((rc = erase_entry(f, D.times_measured, sizeof(int), N, p))) return rc;
+    if ((rc = erase_entry(f, D.patch, sizeof(float) * kPatchPix, N, p))) return rc;
+    if ((rc = erase_entry(f, D.patch_init, 1681, N, p))) return rc;
+    if ((rc = erase_entry(f, D.init_pose, sizeof(double) * 14, N, p))) return rc;
+    f->htype[b].erase(f->htype[b].begin() + p);
+    D.N = N - 1;
+    return 0;
+}
+
+// body of Map::delete_a_feature (src/Map.cpp:69-104): remove `size` rows / columns at state offset `off`
+int map_remove_block(rslam_filter* f, int b, int off, int size) {
+    DevFilter& D = f->hF[b];
+    MapXform xf{};
+    xf.mode = 0;
+    xf.n_old = D.n;
+    xf.n_new = D.n - size;
+    xf.cut_at = off;
+    xf.cut_cnt = size;
+    xf.sp_at = xf.n_new;
+    xf.sp_cnt = 0;
+    return map_apply(f, b, xf);
+}
+
+}  // namespace
+
+extern "C" {
+
+int rslam_map_delete_feature(rslam_filter* f, int b, int index) {
+    if (!f || b < 0 || b >= f->B || index < 0 || index >= f->hF[b].N) return fail(RSLAM_ERR_INVALID, "rslam_map_delete_feature: bad arguments");
+    CK(cudaSetDevice(f->device));
+    int rc = ensure_map_ws(f);
+    if (rc) return rc;
+    int off = 13;
+    for (int i = 0; i < index; i++) off += f->htype[b][i] == 0 ? 6 : 3;
+    const int size = f->htype[b][index] == 0 ? 6 : 3;
+    if ((rc = map_remove_block(f, b, off, size))) return rc;
+    if ((rc = map_erase_info(f, b, index))) return rc;
+    return map_sync_layout(f, b);
+}
+
+int rslam_map_delete_features(rslam_filter* f, int b, int reference_indexing, int* n_deleted) {
+    if (!f || b < 0 || b >= f->B) return fail(RSLAM_ERR_INVALID, "rslam_map_delete_features: bad arguments");
+    CK(cudaSetDevice(f->device));
+    int rc = ensure_map_ws(f);
+    if (rc) return rc;
+    DevFilter& D = f->hF[b];
+    const int N0 = D.N;
+    if (n_deleted) *n_deleted = 0;
+    if (N0 == 0) return RSLAM_OK;
+    std::vector<int> tp(N0), tm(N0);
+    CK(cudaMemcpyAsync(tp.data(), D.times_predicted, sizeof(int) * N0, cudaMemcpyDeviceToHost, f->stream));
+    CK(cudaMemcpyAsync(tm.data(), D.times_measured, sizeof(int) * N0, cudaMemcpyDeviceToHost, f->stream));
+    CK(cudaStreamSynchronize(f->stream));
+    // src/Map.cpp:19-32.  `i` counts loop iterations (1-based) and is what delete_a_feature receives; after the first erase it runs
+    // ahead of the iterator, so the reference removes the STATE block of a later feature than the record it erased, and reads the
+    // type of the record that slid into position i-1.  reference_indexing != 0 reproduces exactly that; 0 deletes consistently.
+    int pos = 0, deleted = 0;
+    for (int i = 1; pos < (int)f->htype[b].size(); i++) {
+        if (tm[pos] < tp[pos] * 0.5 && tp[pos] > 5) {
+            const int erased_type = f->htype[b][pos];
+            tp.erase(tp.begin() + pos);
+            tm.erase(tm.begin() + pos);
+            if ((rc = map_erase_info(f, b, pos))) return rc;
+            const std::vector<int>& ty = f->htype[b];  // features_info AFTER the erase, which is what delete_a_feature reads
+            int size, off = 13;
+            if (reference_indexing) {
+                if (i - 1 >= (int)ty.size()) {
+                    map_sync_layout(f, b);
+                    return fail(RSLAM_ERR_REFERENCE_UB, "map_management: delete_a_feature(%d) indexes past the end of features_info (src/Map.cpp:73)", i);
+                }
+                size = ty[i - 1] == 0 ? 6 : 3;
+                for (int k = 0; k < i - 1; k++) off += ty[k] == 0 ? 6 : 3;
+            } else {
+                size = erased_type == 0 ? 6 : 3;
+                for (int k = 0; k < pos; k++) off += ty[k] == 0 ? 6 : 3;
+            }
+            if (off + size > D.n) {
+                map_sync_layout(f, b);
+                return fail(RSLAM_ERR_REFERENCE_UB, "map_management: delete_a_feature(%d) removes rows past the end of the state (src/Map.cpp:88-101)", i);
+            }
+            if ((rc = map_remove_block(f, b, off, size))) return rc;
+            deleted++;
+        } else {
+            pos++;
+        }
+    }
+    if (n_deleted) *n_deleted = deleted;
+    if ((rc = map_sync_layout(f, b))) return rc;
+    int total = 13;
+    for (int t : f->htype[b]) total += t == 0 ? 6 : 3;
+    if (total != D.n) return fail(RSLAM_ERR_REFERENCE_UB, "map_management: state dimension %d no longer matches features_info (%d): the reference would assert", D.n, total);
+    return RSLAM_OK;
+}
+
+int rslam_map_inversedepth_to_cartesian(rslam_filter* f, int b, int* converted_index) {
+    if (!f || b < 0 || b >= f->B) return fail(RSLAM_ERR_INVALID, "rslam_map_inversedepth_to_cartesian: bad arguments");
+    CK(cudaSetDevice(f->device));
+    int rc = ensure_map_ws(f);
+    if (rc) return rc;
+    DevFilter& D = f->hF[b];
+    if (converted_index) *converted_index = -1;
+    if (D.N == 0) return RSLAM_OK;
+    const int none = 0x7fffffff;
+    CK(cudaMemcpyAsync(f->map_res, &none, sizeof(int), cudaMemcpyHostToDevice, f->stream));
+    LAUNCH(f, k_map_linearity, cdiv(D.N, 128), 128, 0, f->dF, b, 0.1, f->map_res);
+    int idx = none;
+    CK(cudaMemcpyAsync(&idx, f->map_res, sizeof(int), cudaMemcpyDeviceToHost, f->stream));
+    CK(cudaStreamSynchronize(f->stream));
+    if (idx == none) return RSLAM_OK;
+    int ip = 13;
+    for (int i = 0; i < idx; i++) ip += f->htype[b][i] == 0 ? 6 : 3;
+    LAUNCH(f, k_map_prep_convert, 1, 32, 0, f->dF, b, ip, f->map_coef);
+    MapXform xf{};
+    xf.mode = 1;
+    xf.n_old = D.n;
+    xf.n_new = D.n - 3;
+    xf.cut_at = ip;
+    xf.cut_cnt = 6;
+    xf.sp_at = ip;
+    xf.sp_cnt = 3;
+    xf.src_at = ip;
+    xf.src_cnt = 6;
+    if ((rc = map_apply(f, b, xf))) return rc;
+    f->htype[b][idx] = 1;
+    if (converted_index) *converted_index = idx;
+    return map_sync_layout(f, b);
+}
+
+int rslam_map_add_feature(rslam_filter* f, int b, const double* uv, int* new_index) {
+    if (!f || b < 0 || b >= f->B || !uv) return fail(RSLAM_ERR_INVALID, "rslam_map_add_feature: bad arguments");
+    DevFilter& D = f->hF[b];
+    if (D.N + 1 > f->Nmax || D.n + 6 > f->nmax) return fail(RSLAM_ERR_CAPACITY, "rslam_map_add_feature: the handle was created for at most %d features", f->Nmax);
+    CK(cudaSetDevice(f->device));
+    int rc = ensure_map_ws(f);
+    if (rc) return rc;
+    // initial_rho = 1, std_rho = 1, std_pxl = std_z (src/Map.cpp:216-219)
+    LAUNCH(f, k_map_prep_add, 8, 256, 0, f->dF, b, f->camd, uv[0], uv[1], 1.0, f->par.std_z, 1.0, f->map_coef);
+    MapXform xf{};
+    xf.mode = 2;
+    xf.n_old = D.n;
+    xf.n_new = D.n + 6;
+    xf.cut_at = D.n;
+    xf.cut_cnt = 0;
+    xf.sp_at = D.n;
+    xf.sp_cnt = 6;
+    xf.src_at = 0;
+    xf.src_cnt = 13;
+    if ((rc = map_apply(f, b, xf))) return rc;
+    f->htype[b].push_back(0);
+    if (new_index) *new_index = D.N;
+    return map_sync_layout(f, b);
+}
+
+}  // extern "C"
+
+extern "C" {
+int rslam_feature_types(rslam_filter* f, int b, int* types) {
+    if (!f || b < 0 || b >= f->B || !types) return fail(RSLAM_ERR_INVALID, "rslam_feature_types: bad arguments");
+    for (size_t i = 0; i < f->htype[b].size(); i++) types[i] = f->htype[b][i];
+    return RSLAM_OK;
+}
+int rslam_set_counters(rslam_filter* f, int b, const int* times_predicted, const int* times_measured) {
+    if (!f || b < 0 || b >= f->B || !times_predicted || !times_measured) return fail(RSLAM_ERR_INVALID, "rslam_set_counters: bad arguments");
+    CK(cudaSetDevice(f->device));
+    const int N = f->hF[b].N;
+    if (N) {
+        CK(cudaMemcpyAsync(f->hF[b].times_predicted, times_predicted, sizeof(int) * N, cudaMemcpyDefault, f->stream));
+        CK(cudaMemcpyAsync(f->hF[b].times_measured, times_measured, sizeof(int) * N, cudaMemcpyDefault, f->stream));
+        CK(cudaStreamSynchronize(f->stream));
+    }
+    return RSLAM_OK;
+}
+int rslam_download_feature_init(rslam_filter* f, int b, int i, uint8_t* patch41, double* pose14) {
+    if (!f || b < 0 || b >= f->B || i < 0 || i >= f->hF[b].N) return fail(RSLAM_ERR_INVALID, "rslam_download_feature_init: bad arguments");
+    CK(cudaSetDevice(f->device));
+    if (patch41) CK(cudaMemcpyAsync(patch41, f->hF[b].patch_init + (size_t)i * 1681, 1681, cudaMemcpyDeviceToHost, f->stream));
+    if (pose14) CK(cudaMemcpyAsync(pose14, f->hF[b].init_pose + (size_t)i * 14, sizeof(double) * 14, cudaMemcpyDeviceToHost, f->stream));
+    CK(cudaStreamSynchronize(f->stream));
+    return RSLAM_OK;
+}
 }  // extern "C"

@@ -1,0 +1,160 @@
+"""GPU parity of the Map state surgery through the C ABI against the oracle's restatement of src/Map.cpp:
+delete (clean and with the reference's run-ahead indexing), inverse-depth -> cartesian conversion, feature initialisation, and a
+full frame on the modified map; plus size-independent properties at N = 2000."""
+import numpy as np
+import pytest
+
+from oracle import oracle_py as O
+from ransac_slam_b200 import synth
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(N, seed, max_features=None):
+    scene, x, P = synth.random_spd_state(N, seed=seed)
+    o = H.oracle_from(scene, x, P, prior=False)
+    g = H.gpu_from(scene, x, P, prior=False, max_features=max_features or N + 4)
+    return scene, x, P, o, g
+
+
+def _same_state(o, g, exact=False):
+    xo, Po = o.get_state()
+    xg, Pg = g.download_state()
+    assert xg.shape == xo.shape and Pg.shape == Po.shape
+    if exact:
+        assert np.array_equal(xg, xo) and np.array_equal(Pg, Po)
+    else:
+        H.assert_x_close(xg, xo)
+        H.assert_P_close(Pg, Po)
+    assert list(g.types()) == list(o.types())
+
+
+def test_delete_feature_bit_exact():
+    scene, x, P, o, g = _pair(12, 3)
+    for idx in (4, 0, 9):
+        assert o.map_delete_feature(idx) == 0
+        g.map_delete_feature(idx)
+        _same_state(o, g, exact=True)
+    assert g.N == 9
+
+
+@pytest.mark.parametrize("reference_indexing", [True, False])
+def test_delete_pass_matches_oracle(reference_indexing):
+    scene, x, P, o, g = _pair(10, 5)
+    tp = np.full(10, 10, np.int32)
+    tm = np.full(10, 9, np.int32)
+    tm[[2, 5]] = 1
+    o.set_counters(tp, tm)
+    g.set_counters(tp, tm)
+    rco, ndo = o.map_delete_pass(reference_indexing)
+    rcg, ndg = g.map_delete_features(reference_indexing)
+    assert (rco, ndo) == (rcg, ndg) == (0, 2)
+    _same_state(o, g, exact=True)
+    # the surviving records moved with their features: counters line up with the oracle's
+    assert list(g.features()["times_measured"]) == [9] * 8
+
+
+def test_delete_pass_reference_ub_is_reported():
+    scene, x, P, o, g = _pair(6, 7)
+    tp = np.full(6, 10, np.int32)
+    tm = np.full(6, 9, np.int32)
+    tm[5] = 0
+    g.set_counters(tp, tm)
+    rc, _ = g.map_delete_features(True)
+    assert rc == -4
+
+
+def test_inversedepth_to_cartesian_matches_oracle():
+    scene, x, P = synth.random_spd_state(10, seed=11)
+    for i in (3, 7):
+        ip = 13 + 6 * i
+        s = 1e-3 / np.sqrt(P[ip + 5, ip + 5])
+        P[ip + 5, :] *= s
+        P[:, ip + 5] *= s
+    o = H.oracle_from(scene, x, P, prior=False)
+    g = H.gpu_from(scene, x, P, prior=False)
+    for expect in (3, 7, -1):
+        assert o.map_inversedepth_to_cartesian() == expect
+        assert g.map_inversedepth_to_cartesian() == expect
+        _same_state(o, g)
+    # untouched entries are copies, not recomputations
+    xg, Pg = g.download_state()
+    assert np.array_equal(Pg[:13 + 18, :13 + 18], P[:13 + 18, :13 + 18])
+
+
+def test_add_feature_matches_oracle():
+    scene, x, P, o, g = _pair(8, 13)
+    img = synth.background(scene.cam, seed=3)
+    g.set_image(img)
+    for uv in ([201.0, 77.0], [64.0, 150.0]):
+        io = o.map_add_feature(np.array(uv), img)
+        ig = g.map_add_feature(np.array(uv))
+        assert io == ig
+        _same_state(o, g)
+        po, qo = o.feature_init(io)
+        pg, qg = g.feature_init(ig)
+        assert np.array_equal(po, pg)
+        np.testing.assert_allclose(qg, qo, rtol=1e-14)
+    xg, Pg = g.download_state()
+    assert np.array_equal(Pg[:x.size, :x.size], P) and np.array_equal(Pg, Pg.T)
+
+
+def test_frame_after_surgery_matches_oracle():
+    """delete + convert + add, then a full measurement-update frame on the new map: every later stage sees consistent offsets"""
+    scene, x, P = synth.random_spd_state(24, seed=21)
+    ip = 13 + 6 * 5
+    s = 1e-3 / np.sqrt(P[ip + 5, ip + 5])
+    P[ip + 5, :] *= s
+    P[:, ip + 5] *= s
+    seq = synth.make_sequence(scene, T=1, seed=26, t0=3)
+    o = H.oracle_from(scene, x, P, prior=False, sparse=False)
+    g = H.gpu_from(scene, x, P, prior=False, max_features=26)
+    g.set_image(seq.images[0])
+    assert o.map_delete_feature(9) == 0
+    g.map_delete_feature(9)
+    assert o.map_inversedepth_to_cartesian() == g.map_inversedepth_to_cartesian() == 5
+    assert o.map_add_feature(np.array([100.0, 100.0]), seq.images[0]) == g.map_add_feature(np.array([100.0, 100.0])) == 23
+    _same_state(o, g)
+    # the measurement update runs from the prior: copy x_k_k / p_k_k into it on both sides
+    xo, Po = o.get_state()
+    o.set_state(xo, Po, prior=True)
+    xg, Pg = g.download_state()
+    g.upload_state(xg, Pg, feat_types=g.types(), prior=True)
+    tmpl = np.delete(scene.templates, 9, axis=0)
+    tmpl = np.concatenate([tmpl, np.zeros((1, 13, 13), tmpl.dtype)])
+    g.upload_patches(tmpl.astype(np.float64))
+    # cartesian matches in RANSAC are undefined in the reference (Q2): check the stages before it
+    o.search_ic_matches(seq.images[0])
+    g.search_ic_matches()
+    fo, fg = o.features(), g.features()
+    assert (fo["has_h"] == fg["has_h"]).all() and (fo["ic"] == fg["ic"]).all()
+    np.testing.assert_allclose(fg["h"][fg["has_h"]], fo["h"][fo["has_h"]], rtol=1e-9)
+    np.testing.assert_allclose(fg["S"][fg["has_h"]], fo["S"][fo["has_h"]], rtol=1e-9, atol=1e-12)  # atol: exact zeros in the oracle
+    assert (fg["z"][fg["ic"]] == fo["z"][fo["ic"]]).all()
+
+
+def test_large_map_properties():
+    """N = 2000 (P = 1.15 GB): delete and add are exact copies outside the touched block and keep P symmetric"""
+    import torch
+
+    from ransac_slam_b200 import capi
+
+    N = 2000
+    cam = synth.scaled_camera(4)
+    scene = synth.make_scene(N=N, seed=1234, cam=cam, margin=30, min_sep=18, assemble_P=False, motion_scale=0.25)
+    dev = torch.device("cuda", 0)
+    P0 = synth.assemble_P_torch(scene, dev)
+    n = scene.x0.size
+    g = capi.Filter(cam.as9(), N + 1)
+    x0 = torch.from_numpy(scene.x0).to(dev)
+    g.upload_state_device(x0.data_ptr(), P0.data_ptr(), n, n, N)
+    g.map_delete_feature(1000)
+    xg, Pg = g.download_state()
+    keep = np.r_[0:13 + 6000, 13 + 6006:n]
+    P0h = P0.cpu().numpy()
+    assert np.array_equal(Pg, P0h[np.ix_(keep, keep)]) and np.array_equal(xg, scene.x0[keep])
+    g.map_add_feature(np.array([640.0, 480.0]))
+    x2, P2 = g.download_state()
+    assert P2.shape == (n, n) and np.array_equal(P2[: n - 6, : n - 6], Pg) and np.array_equal(P2, P2.T)
+    assert np.all(np.linalg.eigvalsh(P2[-6:, -6:]) > 0)
