@@ -181,6 +181,19 @@ int rslam_set_counters(rslam_filter* f, int b, const int* times_predicted, const
 /* record stored at initialisation for feature i: patch41[1681] (row-major), pose14 = r_wc(3), R_wc row-major(9), uv(2) */
 int rslam_download_feature_init(rslam_filter* f, int b, int i, uint8_t* patch41, double* pose14);
 
+/* --- feature initialisation (src/Map.cpp:198-338) -------------------------------------------------------- */
+/* Map::fast_corner_detect_9 (src/Map.cpp:324-338): cv::FAST(TYPE_9_16, non-maximum suppression) on the window (x0, y0, w, h) of the
+ * image bound to filter b.  *n_kp = number of corners; the first min(*n_kp, max_kp) as xy[2 i] = (x, y) relative to the window, in
+ * OpenCV's output order (row by row, left to right).  The reference uses threshold 100. */
+int rslam_fast_corner_detect_9(rslam_filter* f, int b, int x0, int y0, int w, int h, int threshold, int max_kp, int* n_kp, int* xy);
+/* Map::initialize_features (src/Map.cpp:198-211): up to 50 attempts of initialize_a_features (:212-323) until min_features_to_init
+ * features were added.  u01 (host): 2 uniform draws in [0,1) per attempt, replacing ExtendKF::rand(2,1,0,1) (:231). */
+int rslam_map_initialize_features(rslam_filter* f, int b, int step, int min_features_to_init, const double* u01, int n_pairs, int* n_initialized,
+                                  int* attempts);
+/* Map::map_management (src/Map.cpp:16-67), all four steps; batch-1 handles only.  info4 = {deleted, converted index or -1,
+ * initialised, attempts}. */
+int rslam_map_management(rslam_filter* f, int b, int step, int min_features, int reference_indexing, const double* u01, int n_pairs, int* info4);
+
 #ifdef __cplusplus
 }
 #endif

@@ -61,6 +61,10 @@ def lib():
         _lib.orc_undistort.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         _lib.orc_lu_inverse.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         _lib.orc_dgemm.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        _lib.orc_fast9.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        _lib.orc_initialize_features.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        _lib.orc_map_management.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        _lib.orc_initialize_x_and_p.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double]
         _lib.orc_map_delete_pass.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         _lib.orc_map_delete_feature.argtypes = [C.c_void_p, C.c_int]
         _lib.orc_map_inversedepth_to_cartesian.argtypes = [C.c_void_p]
@@ -215,6 +219,27 @@ class OracleFilter:
         img = np.ascontiguousarray(image, dtype=np.uint8)
         return self.L.orc_map_add_feature(self.h, _p(uv), _p(img), img.shape[0], img.shape[1], img.shape[1])
 
+    def initialize_x_and_p(self, v0=0.0, w0=1e-11, std_v0=0.025, std_w0=0.025):
+        """ExtendKF::initialize_x_and_p (src/ExtendKF.cpp:32-54) with the yaml's Velocity.* values"""
+        self.L.orc_initialize_x_and_p(self.h, v0, w0, std_v0, std_w0)
+
+    def initialize_features(self, step, n, image, u01):
+        """Map::initialize_features (src/Map.cpp:198-211); u01: 2 draws per attempt.  Returns (initialised or -1, attempts)"""
+        img = np.ascontiguousarray(image, dtype=np.uint8)
+        u = _f64(u01)
+        att = C.c_int(0)
+        r = self.L.orc_initialize_features(self.h, int(step), int(n), _p(img), img.shape[0], img.shape[1], img.shape[1], _p(u), u.size // 2, C.byref(att))
+        return r, att.value
+
+    def map_management(self, image, step, min_features, u01, reference_indexing=True):
+        """Map::map_management (src/Map.cpp:16-67).  Returns (status, dict(deleted, converted, initialised, attempts))"""
+        img = np.ascontiguousarray(image, dtype=np.uint8)
+        u = _f64(u01)
+        info = np.zeros(4, dtype=np.int32)
+        rc = self.L.orc_map_management(self.h, _p(img), img.shape[0], img.shape[1], img.shape[1], int(step), int(min_features), int(reference_indexing), _p(u),
+                                       u.size // 2, _p(info))
+        return rc, dict(deleted=int(info[0]), converted=int(info[1]), initialised=int(info[2]), attempts=int(info[3]))
+
     def set_counters(self, times_predicted, times_measured):
         tp = np.ascontiguousarray(times_predicted, dtype=np.int32)
         tm = np.ascontiguousarray(times_measured, dtype=np.int32)
@@ -243,6 +268,14 @@ class OracleFilter:
         self.rescue_hi()
         self.update_hi()
         return rc, info
+
+
+def fast9(image, threshold=100, nonmax=True, max_kp=4096):
+    """cv::FAST restatement (src/Map.cpp:324-338 calls cv::FAST(im, kps, 100, true)); returns keypoints (x, y) in OpenCV's order"""
+    img = np.ascontiguousarray(image, dtype=np.uint8)
+    xy = np.zeros((max_kp, 2), dtype=np.int32)
+    n = lib().orc_fast9(_p(img), img.shape[0], img.shape[1], img.shape[1], int(threshold), int(nonmax), max_kp, _p(xy))
+    return xy[: min(n, max_kp)].copy()
 
 
 def cv_remap(src, mapx, mapy):

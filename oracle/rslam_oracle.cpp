@@ -1237,6 +1237,139 @@ static int map_add_feature(Filter& F, const double* uv, const uint8_t* image, in
     return (int)F.fi.size() - 1;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Feature initialisation: cv::FAST + Map::initialize_features (src/Map.cpp:198-338) -- SURVEY 8f row 4
+// ---------------------------------------------------------------------------------------------------------
+// cv::FAST(image, keypoints, threshold, nonmaxSuppression = true) with the default TYPE_9_16, restated from the published
+// algorithm (OpenCV 3.2, pinned by CMakeLists.txt:28-29; modules/features2d/src/fast.cpp FAST_t<16> + fast_score.cpp
+// cornerScore<16>): a pixel is a corner iff 9 contiguous pixels of the 16-pixel Bresenham circle of radius 3 are all darker than
+// v - t or all brighter than v + t; its score is the largest t for which that still holds; with non-maximum suppression a corner is
+// kept iff its score is strictly greater than the scores of its 8 neighbours (non-corners count 0).  Keypoints come out row by row,
+// left to right; the 3-pixel border is never tested.  Pinned against cv2 4.13 by tests/golden/fast_fixtures.npz.
+static const int kFastRing[16][2] = {{0, 3},  {1, 3},   {2, 2},   {3, 1},   {3, 0},  {3, -1}, {2, -2}, {1, -3},
+                                     {0, -3}, {-1, -3}, {-2, -2}, {-3, -1}, {-3, 0}, {-3, 1}, {-2, 2}, {-1, 3}};  // (dx, dy)
+static int fast9_strength(const uint8_t* img, int stride, int x, int y) {
+    // max over the 16 arcs of 9 contiguous ring pixels of min(v - ring) ("darker" arc) and of min(ring - v) ("brighter" arc)
+    const int v = img[(size_t)y * stride + x];
+    int d[25];
+    for (int k = 0; k < 25; k++) d[k] = v - img[(size_t)(y + kFastRing[k % 16][1]) * stride + (x + kFastRing[k % 16][0])];
+    int best = -256;
+    for (int s0 = 0; s0 < 16; s0++) {
+        int a = 256, b = 256;
+        for (int j = 0; j < 9; j++) {
+            a = std::min(a, d[s0 + j]);
+            b = std::min(b, -d[s0 + j]);
+        }
+        best = std::max(best, std::max(a, b));
+    }
+    return best;
+}
+static void fast9(const uint8_t* img, int rows, int cols, int stride, int threshold, bool nonmax, std::vector<int>& xs, std::vector<int>& ys) {
+    xs.clear();
+    ys.clear();
+    threshold = std::min(std::max(threshold, 0), 255);
+    if (rows < 7 || cols < 7) return;
+    std::vector<int> score((size_t)rows * cols, 0);
+    for (int y = 3; y < rows - 3; y++)
+        for (int x = 3; x < cols - 3; x++) {
+            int sgth = fast9_strength(img, stride, x, y);
+            if (sgth > threshold) score[(size_t)y * cols + x] = nonmax ? sgth - 1 : 1;
+        }
+    for (int y = 3; y < rows - 3; y++)
+        for (int x = 3; x < cols - 3; x++) {
+            const int sc = score[(size_t)y * cols + x];
+            if (!sc) continue;
+            bool keep = true;
+            if (nonmax)
+                for (int dy = -1; dy <= 1 && keep; dy++)
+                    for (int dx = -1; dx <= 1; dx++)
+                        if ((dx || dy) && !(sc > score[(size_t)(y + dy) * cols + (x + dx)])) {
+                            keep = false;
+                            break;
+                        }
+            if (keep) {
+                xs.push_back(x);
+                ys.push_back(y);
+            }
+        }
+}
+
+// Map::initialize_a_features (src/Map.cpp:212-323) with the two uniform draws of `rand(2,1,0,1)` (:231) supplied by the caller.
+// Returns 1 if a feature was added.
+static int initialize_a_features(Filter& F, int step, const uint8_t* image, int rows, int cols, int stride, const double* u2) {
+    (void)step;
+    const int excluded_band = 21;
+    const int semi[2] = {30, 20};
+    predict_camera_measurements(F, F.x_k_k);
+    std::vector<std::pair<double, double>> h_pred;
+    for (auto& ft : F.fi)
+        if (ft.has_h) h_pred.push_back({ft.h[0], ft.h[1]});
+    double cx = std::round(u2[0] * (F.cam.nCols - 2 * excluded_band - 2 * semi[0])) + excluded_band + semi[0];
+    double cy = std::round(u2[1] * (F.cam.nRows - 2 * excluded_band - 2 * semi[1])) + excluded_band + semi[1];
+    const int x0 = (int)(cx - semi[0]), y0 = (int)(cy - semi[1]);  // cv::Range truncation
+    const int wr = (int)(cy + semi[1] + 1) - y0, wc = (int)(cx + semi[0] + 1) - x0;
+    (void)rows;
+    (void)cols;
+    std::vector<int> kx, ky;
+    fast9(image + (size_t)y0 * stride + x0, wr, wc, stride, 100, true, kx, ky);
+    int added = 0;
+    int features_in_the_box = 0;
+    for (auto& h : h_pred)
+        if (h.first > (cx - semi[0]) && h.first < (cx + semi[0]) && h.second > (cy - semi[1]) && h.second < (cy + semi[1])) features_in_the_box++;
+    if (!kx.empty() && !features_in_the_box) {
+        // MATLAB-style "- 1" kept by the port (src/Map.cpp:243-244): the corner is shifted one pixel up and left
+        double uv[2] = {kx[0] + (-semi[0] + cx - 1), ky[0] + (-semi[1] + cy - 1)};
+        map_add_feature(F, uv, image, F.cam.nRows, F.cam.nCols, stride);
+        added = 1;
+    }
+    for (auto& ft : F.fi) ft.has_h = false;  // :320-322
+    return added;
+}
+
+// Map::initialize_features (src/Map.cpp:198-211): u01 holds 2 draws per attempt; returns the number of features initialised, or -1
+// if the draws ran out before the loop ended
+static int initialize_features(Filter& F, int step, int min_features_to_init, const uint8_t* image, int rows, int cols, int stride, const double* u01,
+                               int n_pairs, int* attempts_out) {
+    const int max_attempts = 50;
+    int attempts = 0, initialized = 0;
+    while (initialized < min_features_to_init && attempts < max_attempts) {
+        if (attempts >= n_pairs) {
+            if (attempts_out) *attempts_out = attempts;
+            return -1;
+        }
+        initialized += initialize_a_features(F, step, image, rows, cols, stride, u01 + 2 * attempts);
+        attempts++;
+    }
+    if (attempts_out) *attempts_out = attempts;
+    return initialized;
+}
+
+// Map::map_management (src/Map.cpp:16-67)
+static int map_management(Filter& F, const uint8_t* image, int rows, int cols, int stride, int step, int min_features, bool reference_indexing,
+                          const double* u01, int n_pairs, int* info3) {
+    int nd = 0;
+    int rc = map_delete_pass(F, reference_indexing, &nd);
+    if (rc) return rc;
+    int measured = 0;
+    for (auto& ft : F.fi)
+        if (ft.low_innovation_inlier || ft.high_innovation_inlier) measured++;
+    map_reset_flags(F);
+    int conv = inversedepth_2_cartesian_map(F);
+    int attempts = 0, init = 0;
+    if (measured == 0)
+        init = initialize_features(F, step, min_features, image, rows, cols, stride, u01, n_pairs, &attempts);
+    else if (measured < min_features)
+        init = initialize_features(F, step, min_features - measured, image, rows, cols, stride, u01, n_pairs, &attempts);
+    if (info3) {
+        info3[0] = nd;
+        info3[1] = conv;
+        info3[2] = init;
+        info3[3] = attempts;
+    }
+    return init < 0 ? -5 : 0;
+}
+
 }  // namespace orc
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1490,5 +1623,40 @@ void orc_get_feature_init(void* h, int i, uint8_t* patch41, double* pose14) {
         for (int c = 0; c < 3; c++) pose14[3 + 3 * r + c] = ft.R_wc_when_initialized(r, c);
     pose14[12] = ft.uv_when_initialized[0];
     pose14[13] = ft.uv_when_initialized[1];
+}
+
+// --- FAST + feature initialisation + full map management ---------------------------------------------------------------------
+int orc_fast9(const uint8_t* img, int rows, int cols, int stride, int threshold, int nonmax, int max_kp, int* xy) {
+    std::vector<int> xs, ys;
+    fast9(img, rows, cols, stride, threshold, nonmax != 0, xs, ys);
+    for (size_t i = 0; i < xs.size() && (int)i < max_kp; i++) {
+        xy[2 * i] = xs[i];
+        xy[2 * i + 1] = ys[i];
+    }
+    return (int)xs.size();
+}
+int orc_initialize_features(void* h, int step, int n, const uint8_t* image, int rows, int cols, int stride, const double* u01, int n_pairs, int* attempts) {
+    return initialize_features(*(Filter*)h, step, n, image, rows, cols, stride, u01, n_pairs, attempts);
+}
+int orc_map_management(void* h, const uint8_t* image, int rows, int cols, int stride, int step, int min_features, int reference_indexing, const double* u01,
+                       int n_pairs, int* info4) {
+    return map_management(*(Filter*)h, image, rows, cols, stride, step, min_features, reference_indexing != 0, u01, n_pairs, info4);
+}
+// ExtendKF::initialize_x_and_p (src/ExtendKF.cpp:32-54): 13-state start, no features
+void orc_initialize_x_and_p(void* h, double v0, double w0, double std_v0, double std_w0) {
+    Filter& F = *(Filter*)h;
+    F.fi.clear();
+    F.x_k_k.resize(13, 1);
+    F.x_k_k[3] = 1;
+    F.x_k_k[7] = F.x_k_k[8] = F.x_k_k[9] = v0;
+    F.x_k_k[10] = F.x_k_k[11] = F.x_k_k[12] = w0;
+    F.p_k_k.resize(13, 13);
+    const double eps = F.eps;
+    for (int i = 0; i < 7; i++)
+        if (i != 5) F.p_k_k(i, i) = eps;  // Q7: index 5 is skipped by the reference (src/ExtendKF.cpp:42-47)
+    for (int i = 7; i < 10; i++) F.p_k_k(i, i) = std_v0 * std_v0;
+    for (int i = 10; i < 13; i++) F.p_k_k(i, i) = std_w0 * std_w0;
+    F.x_k_km1 = F.x_k_k;
+    F.p_k_km1 = F.p_k_k;
 }
 }

@@ -94,6 +94,9 @@ def load():
     L.rslam_map_delete_features.argtypes = [vp, ci, ci, vp]
     L.rslam_map_inversedepth_to_cartesian.argtypes = [vp, ci, vp]
     L.rslam_map_add_feature.argtypes = [vp, ci, vp, vp]
+    L.rslam_fast_corner_detect_9.argtypes = [vp, ci, ci, ci, ci, ci, ci, ci, vp, vp]
+    L.rslam_map_initialize_features.argtypes = [vp, ci, ci, ci, vp, ci, vp, vp]
+    L.rslam_map_management.argtypes = [vp, ci, ci, ci, ci, vp, ci, vp]
     L.rslam_feature_types.argtypes = [vp, ci, vp]
     L.rslam_set_counters.argtypes = [vp, ci, vp, vp]
     L.rslam_download_feature_init.argtypes = [vp, ci, ci, vp, vp]
@@ -304,6 +307,27 @@ class Filter:
         idx = C.c_int(-1)
         self._ck(self.L.rslam_map_add_feature(self.h, b, _p(uv), C.byref(idx)))
         return idx.value
+
+    def fast_corner_detect_9(self, x0=0, y0=0, w=None, h=None, threshold=100, max_kp=4096, b=0):
+        """cv::FAST on a window of the bound image; keypoints (x, y) relative to the window, OpenCV order"""
+        n = C.c_int(0)
+        xy = np.zeros((max_kp, 2), dtype=np.int32)
+        self._ck(self.L.rslam_fast_corner_detect_9(self.h, b, x0, y0, w, h, threshold, max_kp, C.byref(n), _p(xy)))
+        return xy[: min(n.value, max_kp)].copy(), n.value
+
+    def map_initialize_features(self, step, n, u01, b=0):
+        u = np.ascontiguousarray(u01, dtype=np.float64)
+        ni, att = C.c_int(0), C.c_int(0)
+        self._ck(self.L.rslam_map_initialize_features(self.h, b, int(step), int(n), _p(u), u.size // 2, C.byref(ni), C.byref(att)))
+        return ni.value, att.value
+
+    def map_management(self, step, min_features, u01, reference_indexing=True, b=0):
+        u = np.ascontiguousarray(u01, dtype=np.float64)
+        info = np.zeros(4, dtype=np.int32)
+        rc = self.L.rslam_map_management(self.h, b, int(step), int(min_features), int(reference_indexing), _p(u), u.size // 2, _p(info))
+        if rc not in (0, -4):
+            self._ck(rc)
+        return rc, dict(deleted=int(info[0]), converted=int(info[1]), initialised=int(info[2]), attempts=int(info[3]))
 
     def types(self, b=0):
         N = self.L.rslam_num_features(self.h, b)

@@ -214,4 +214,126 @@ __global__ void __launch_bounds__(256) k_map_xform(DevFilter* Fs, int b, MapXfor
     if (c == 0) xdst[r] = rs ? scratch[kMapX + (r - xf.sp_at)] : F.x_kk[map_old_row(xf, r)];
 }
 
+// ---- feature initialisation: cv::FAST (TYPE_9_16, non-maximum suppression) + the "features in the box" test ----
+// cv::FAST as the reference calls it (src/Map.cpp:324-338: cv::FAST(im, keypoints, 100, true)), from the published algorithm
+// (OpenCV 3.2 modules/features2d/src/fast.cpp, fast_score.cpp): corner iff 9 contiguous pixels of the radius-3 Bresenham circle are
+// all darker than v - t or all brighter than v + t; score = the largest t for which that holds; a corner survives iff its score is
+// strictly greater than its 8 neighbours' (non-corners score 0); the 3-pixel border is never tested; output row by row, left to right.
+// pass 1: score of every pixel of the window (x0, y0, w, h) of the filter's image; thread per pixel
+__global__ void __launch_bounds__(256) k_fast9_score(DevFilter* Fs, int b, int x0, int y0, int w, int h, int threshold, int* score) {
+    const DevFilter& F = Fs[b];
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= w * h) return;
+    const int x = e % w, y = e / w;
+    int out = 0;
+    if (x >= 3 && x < w - 3 && y >= 3 && y < h - 3) {
+        const unsigned char* img = F.image + (size_t)(y0 + y) * F.img_stride + (x0 + x);
+        const int v = img[0];
+        const int RX[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
+        const int RY[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
+        int d[16];
+#pragma unroll 1
+        for (int k = 0; k < 16; k++) d[k] = v - (int)img[RY[k] * F.img_stride + RX[k]];
+        // NOTE: written with plain compare-and-assign loops that are NOT unrolled on purpose.  The obvious fully unrolled
+        // min()/max() form of this arc search is miscompiled by nvcc 12.9 for sm_100a (the fused three-input VIMNMX3 chain returns
+        // wrong strengths, e.g. 36 instead of 117; reproduced in isolation by tools/ubench/fast_dbg.cu), so keep it this way.
+        int best = -256;
+#pragma unroll 1
+        for (int s0 = 0; s0 < 16; s0++) {
+            int a = 256, bb = 256;
+#pragma unroll 1
+            for (int j = 0; j < 9; j++) {
+                const int t = d[(s0 + j) & 15];
+                if (t < a) a = t;
+                if (-t < bb) bb = -t;
+            }
+            const int m = a > bb ? a : bb;
+            if (m > best) best = m;
+        }
+        if (best > threshold) out = best - 1;
+    }
+    score[e] = out;
+}
+
+// pass 2: non-maximum suppression and ORDERED compaction (row-major) by one CTA: res[0] = number of keypoints, xy[2 i] = (x, y)
+__global__ void __launch_bounds__(1024) k_fast9_nms(const int* score, int w, int h, int max_kp, int* res, int* xy) {
+    __shared__ int s_warp[32];
+    __shared__ int s_base;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int e0 = 0; e0 < w * h; e0 += 1024) {
+        const int e = e0 + threadIdx.x;
+        bool keep = false;
+        int x = 0, y = 0;
+        if (e < w * h) {
+            x = e % w;
+            y = e / w;
+            const int sc = score[e];
+            if (sc > 0) {  // inside the tested area by construction, so all 8 neighbours exist
+                keep = sc > score[e - 1] && sc > score[e + 1] && sc > score[e - w - 1] && sc > score[e - w] && sc > score[e - w + 1] &&
+                       sc > score[e + w - 1] && sc > score[e + w] && sc > score[e + w + 1];
+            }
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) s_warp[wid] = __popc(bal);
+        __syncthreads();
+        int before = 0, total = 0;
+        for (int k = 0; k < 32; k++) {
+            const int c = s_warp[k];
+            if (k < wid) before += c;
+            total += c;
+        }
+        if (keep) {
+            const int pos = s_base + before + __popc(bal & ((1u << lane) - 1));
+            if (pos < max_kp) {
+                xy[2 * pos] = x;
+                xy[2 * pos + 1] = y;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_base += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) res[0] = s_base;
+}
+
+// predicted (distorted) pixel of feature i at state x, with the reference's two visibility gates (src/ExtendKF.cpp:56-135)
+__device__ __forceinline__ bool predict_pixel_dev(const CamDev& cam, const double* x, int off, int type, double& hx, double& hy) {
+    double R[9];
+    q2r_dev(x + 3, R);
+    double d[3];
+    if (type == 0) {
+        const double th = x[off + 3], ph = x[off + 4], rho = x[off + 5];
+        const double mi[3] = {cos(ph) * sin(th), -sin(ph), cos(ph) * cos(th)};
+        for (int k = 0; k < 3; k++) d[k] = (x[off + k] - x[k]) * rho + mi[k];
+    } else {
+        for (int k = 0; k < 3; k++) d[k] = x[off + k] - x[k];
+    }
+    double hrl[3];
+    if (type == 0) {
+        for (int k = 0; k < 3; k++) hrl[k] = R[k] * d[0] + R[3 + k] * d[1] + R[6 + k] * d[2];  // R^T d (:75)
+    } else {
+        double Ri[9];
+        inv3_dev(R, Ri);
+        for (int k = 0; k < 3; k++) hrl[k] = Ri[3 * k] * d[0] + Ri[3 * k + 1] * d[1] + Ri[3 * k + 2] * d[2];  // R^-1 d (:83)
+    }
+    const double ax = atan2(hrl[0], hrl[2]) * 180 / M_PI, ay = atan2(hrl[1], hrl[2]) * 180 / M_PI;
+    if (ax < -60 || ax > 60 || ay < -60 || ay > 60) return false;
+    const double uu = cam.Cx + (hrl[0] / hrl[2]) * cam.f * (1.0 / cam.dx);
+    const double vu = cam.Cy + (hrl[1] / hrl[2]) * cam.f * (1.0 / cam.dy);
+    distort_dev(cam, uu, vu, hx, hy);
+    return (hx > 0) && (hx < cam.nCols) && (hy > 0) && (hy < cam.nRows);
+}
+
+// step 3 of Map::initialize_a_features (src/Map.cpp:248-261): how many features predicted at x_k_k fall inside the sampling box
+__global__ void k_map_box_count(DevFilter* Fs, int b, CamDev cam, double cx, double cy, double sx, double sy, int* res) {
+    const DevFilter& F = Fs[b];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= F.N) return;
+    double hx, hy;
+    if (!predict_pixel_dev(cam, F.x_kk, F.foff[i], F.ftype[i], hx, hy)) return;
+    if (hx > (cx - sx) && hx < (cx + sx) && hy > (cy - sy) && hy < (cy + sy)) atomicAdd(res, 1);
+}
+
 }  // namespace rslam

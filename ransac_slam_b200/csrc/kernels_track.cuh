@@ -687,7 +687,10 @@ __global__ void __launch_bounds__(kSearchThreads) k_search(DevFilter* Fs, CamDev
             if (!ok[t]) continue;
             const int cand = jx * ncy + iy0 + t;  // reference visiting order: x outer, y inner
             const double var_b = ((double)kPatchPix * sbb[t] - sb[t] * sb[t]) / kPatchPix;  // exact: integer-valued operands < 2^53
-            const double corr = sab[t] / sqrt(var_a * var_b);
+            // a constant candidate window (saturated image regions) has centred b == 0 exactly in the reference's covariance
+            // (cv::calcCovarMatrix centres both variables, src/Converter.cpp:195): 0 / 0 = NaN there, and NaN matters (it is sticky in
+            // slot 0, Q10).  The uncentred sum here would give +-inf instead, so the exact integer test decides.
+            const double corr = (var_b == 0.0 || var_a == 0.0) ? __longlong_as_double(0x7ff8000000000000LL) : sab[t] / sqrt(var_a * var_b);
             if (cand < first_idx) {
                 first_idx = cand;
                 first_c = corr;

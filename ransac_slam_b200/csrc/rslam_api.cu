@@ -51,6 +51,10 @@ struct rslam_filter {
     double* map_coef = nullptr;
     int* map_res = nullptr;
     unsigned char* map_tmp = nullptr;  // staging for erasing one entry of the per-feature arrays
+    int* fast_score = nullptr;         // FAST scores of the window under test
+    size_t fast_cap = 0;
+    int* fast_xy = nullptr;
+    int fast_xy_cap = 0;
     DevFilter* dF = nullptr;
     std::vector<void*> allocs;
     // shared buffers
@@ -1242,4 +1246,125 @@ int rslam_download_feature_init(rslam_filter* f, int b, int i, uint8_t* patch41,
     CK(cudaStreamSynchronize(f->stream));
     return RSLAM_OK;
 }
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Feature initialisation (src/Map.cpp:198-338): FAST corners on the device, sampling-box test, full map_management
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+int fast_detect(rslam_filter* f, int b, int x0, int y0, int w, int h, int threshold, int max_kp, int* n_kp_dev_res /* device int[>=1] */) {
+    const DevFilter& D = f->hF[b];
+    if (!D.image) return fail(RSLAM_ERR_INVALID, "FAST: no image is bound to filter %d (rslam_set_image)", b);
+    if (x0 < 0 || y0 < 0 || w < 1 || h < 1 || x0 + w > D.img_cols || y0 + h > D.img_rows) return fail(RSLAM_ERR_INVALID, "FAST: window outside the image");
+    if ((size_t)w * h > f->fast_cap) {
+        int rc = dev_alloc(f, &f->fast_score, (size_t)w * h);
+        if (rc) return rc;
+        f->fast_cap = (size_t)w * h;
+    }
+    if (max_kp > f->fast_xy_cap) {
+        int rc = dev_alloc(f, &f->fast_xy, (size_t)2 * max_kp);
+        if (rc) return rc;
+        f->fast_xy_cap = max_kp;
+    }
+    threshold = threshold < 0 ? 0 : (threshold > 255 ? 255 : threshold);
+    LAUNCH(f, k_fast9_score, cdiv(w * h, 256), 256, 0, f->dF, b, x0, y0, w, h, threshold, f->fast_score);
+    LAUNCH(f, k_fast9_nms, 1, 1024, 0, (const int*)f->fast_score, w, h, max_kp, n_kp_dev_res, f->fast_xy);
+    return check_launch();
+}
+}  // namespace
+
+extern "C" {
+
+int rslam_fast_corner_detect_9(rslam_filter* f, int b, int x0, int y0, int w, int h, int threshold, int max_kp, int* n_kp, int* xy) {
+    if (!f || b < 0 || b >= f->B || !n_kp || max_kp < 1) return fail(RSLAM_ERR_INVALID, "rslam_fast_corner_detect_9: bad arguments");
+    CK(cudaSetDevice(f->device));
+    int rc = ensure_map_ws(f);
+    if (rc) return rc;
+    if ((rc = fast_detect(f, b, x0, y0, w, h, threshold, max_kp, f->map_res))) return rc;
+    CK(cudaMemcpyAsync(n_kp, f->map_res, sizeof(int), cudaMemcpyDeviceToHost, f->stream));
+    CK(cudaStreamSynchronize(f->stream));
+    const int n = *n_kp < max_kp ? *n_kp : max_kp;
+    if (xy && n > 0) {
+        CK(cudaMemcpyAsync(xy, f->fast_xy, sizeof(int) * 2 * n, cudaMemcpyDeviceToHost, f->stream));
+        CK(cudaStreamSynchronize(f->stream));
+    }
+    return RSLAM_OK;
+}
+
+int rslam_map_initialize_features(rslam_filter* f, int b, int step, int min_features_to_init, const double* u01, int n_pairs, int* n_initialized,
+                                  int* attempts_out) {
+    (void)step;
+    if (!f || b < 0 || b >= f->B || (!u01 && n_pairs > 0)) return fail(RSLAM_ERR_INVALID, "rslam_map_initialize_features: bad arguments");
+    CK(cudaSetDevice(f->device));
+    int rc = ensure_map_ws(f);
+    if (rc) return rc;
+    const int max_attempts = 50, excluded_band = 21, sx = 30, sy = 20;  // src/Map.cpp:200, 215-216
+    int attempts = 0, initialized = 0;
+    if (n_initialized) *n_initialized = 0;
+    while (initialized < min_features_to_init && attempts < max_attempts) {
+        if (attempts >= n_pairs) {
+            if (attempts_out) *attempts_out = attempts;
+            if (n_initialized) *n_initialized = initialized;
+            return fail(RSLAM_ERR_INVALID, "rslam_map_initialize_features: the uniform draws ran out after %d attempts", attempts);
+        }
+        const double cx = round(u01[2 * attempts] * (f->cam.nCols - 2 * excluded_band - 2 * sx)) + excluded_band + sx;
+        const double cy = round(u01[2 * attempts + 1] * (f->cam.nRows - 2 * excluded_band - 2 * sy)) + excluded_band + sy;
+        attempts++;
+        CK(cudaMemsetAsync(f->map_res, 0, sizeof(int) * 4, f->stream));
+        const DevFilter& D = f->hF[b];
+        if (D.N) LAUNCH(f, k_map_box_count, cdiv(D.N, 128), 128, 0, f->dF, b, f->camd, cx, cy, (double)sx, (double)sy, f->map_res + 1);
+        const int x0 = (int)(cx - sx), y0 = (int)(cy - sy);
+        const int w = (int)(cx + sx + 1) - x0, h = (int)(cy + sy + 1) - y0;
+        if ((rc = fast_detect(f, b, x0, y0, w, h, 100, 1, f->map_res))) return rc;
+        int res[2] = {0, 0}, kp[2] = {0, 0};
+        CK(cudaMemcpyAsync(res, f->map_res, sizeof(int) * 2, cudaMemcpyDeviceToHost, f->stream));
+        CK(cudaMemcpyAsync(kp, f->fast_xy, sizeof(int) * 2, cudaMemcpyDeviceToHost, f->stream));
+        CK(cudaStreamSynchronize(f->stream));
+        if (res[0] > 0 && res[1] == 0) {
+            // the port keeps MATLAB's "- 1" (src/Map.cpp:243-244): the corner lands one pixel up and left of where FAST found it
+            const double uv[2] = {kp[0] + (-sx + cx - 1), kp[1] + (-sy + cy - 1)};
+            if (f->hF[b].N + 1 > f->Nmax) {
+                if (attempts_out) *attempts_out = attempts;
+                if (n_initialized) *n_initialized = initialized;
+                return fail(RSLAM_ERR_CAPACITY, "rslam_map_initialize_features: the handle was created for at most %d features", f->Nmax);
+            }
+            if ((rc = rslam_map_add_feature(f, b, uv, nullptr))) return rc;
+            initialized++;
+        }
+    }
+    if (attempts_out) *attempts_out = attempts;
+    if (n_initialized) *n_initialized = initialized;
+    return RSLAM_OK;
+}
+
+int rslam_map_management(rslam_filter* f, int b, int step, int min_features, int reference_indexing, const double* u01, int n_pairs, int* info4) {
+    if (!f || b < 0 || b >= f->B) return fail(RSLAM_ERR_INVALID, "rslam_map_management: bad arguments");
+    if (f->B != 1) return fail(RSLAM_ERR_INVALID, "rslam_map_management: step 2 resets the flags of every filter of the handle; use a batch of 1");
+    CK(cudaSetDevice(f->device));
+    int rc, nd = 0, conv = -1, init = 0, attempts = 0;
+    if ((rc = rslam_map_delete_features(f, b, reference_indexing, &nd))) return rc;
+    const int N = f->hF[b].N;
+    int measured = 0;
+    if (N) {
+        std::vector<unsigned char> li(N), hi(N);
+        CK(cudaMemcpyAsync(li.data(), f->hF[b].li, N, cudaMemcpyDeviceToHost, f->stream));
+        CK(cudaMemcpyAsync(hi.data(), f->hF[b].hi, N, cudaMemcpyDeviceToHost, f->stream));
+        CK(cudaStreamSynchronize(f->stream));
+        for (int i = 0; i < N; i++) measured += (li[i] || hi[i]) ? 1 : 0;
+    }
+    if ((rc = rslam_begin_frame(f))) return rc;
+    if ((rc = rslam_map_inversedepth_to_cartesian(f, b, &conv))) return rc;
+    if (measured == 0)
+        rc = rslam_map_initialize_features(f, b, step, min_features, u01, n_pairs, &init, &attempts);
+    else if (measured < min_features)
+        rc = rslam_map_initialize_features(f, b, step, min_features - measured, u01, n_pairs, &init, &attempts);
+    if (info4) {
+        info4[0] = nd;
+        info4[1] = conv;
+        info4[2] = init;
+        info4[3] = attempts;
+    }
+    return rc;
+}
+
 }  // extern "C"

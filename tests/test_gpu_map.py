@@ -158,3 +158,82 @@ def test_large_map_properties():
     x2, P2 = g.download_state()
     assert P2.shape == (n, n) and np.array_equal(P2[: n - 6, : n - 6], Pg) and np.array_equal(P2, P2.T)
     assert np.all(np.linalg.eigvalsh(P2[-6:, -6:]) > 0)
+
+
+# ---- feature initialisation -------------------------------------------------------------------------------
+import os
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _empty_pair(max_features=40):
+    from ransac_slam_b200 import capi
+
+    cam = synth.Camera()
+    o = O.OracleFilter(cam.as9())
+    o.initialize_x_and_p()
+    x, P = o.get_state()
+    g = capi.Filter(cam.as9(), max_features)
+    g.upload_state(x, P, feat_types=np.zeros(0, np.int32))
+    return cam, o, g
+
+
+def test_fast9_matches_cv2_fixtures_on_device():
+    from ransac_slam_b200 import capi
+
+    g = np.load(os.path.join(GOLD, "fast_fixtures.npz"))
+    cam = synth.Camera()
+    f = capi.Filter(cam.as9(), 4)
+    total = 0
+    for name in g["names"]:
+        img = g[f"{name}_img"]
+        f.set_image(img)
+        for t in (100, 40):
+            kp, n = f.fast_corner_detect_9(0, 0, img.shape[1], img.shape[0], t, 20000)
+            ref = g[f"{name}_kp{t}"]
+            assert n == len(ref) and (kp == ref).all(), (name, t)
+            total += n
+    assert total > 300
+    p = np.load(os.path.join(GOLD, "pgm_frames.npz"))
+    for i in range(p["frames"].shape[0]):
+        f.set_image(p["frames"][i])
+        kp, n = f.fast_corner_detect_9(0, 0, 320, 240, 100, 20000)
+        assert n == len(p[f"kp{i}"]) and (kp == p[f"kp{i}"]).all()
+        # a window, as Map::initialize_a_features cuts it (61 x 41)
+        kpw, nw = f.fast_corner_detect_9(100, 80, 61, 41, 100, 100)
+        ref = O.fast9(p["frames"][i][80:121, 100:161], 100, True)
+        assert nw == len(ref) and (kpw == ref).all()
+
+
+def test_map_management_bootstrap_and_replay_match_oracle():
+    """ROS-free replay of frames of the reference's bundled sequence (config C1) through the WHOLE TrackRunning loop
+    (src/System.cpp:103-129): map_management (delete / reset / convert / FAST initialisation) + prediction + search + RANSAC +
+    li / hi updates, device against oracle, same uniform draws."""
+    p = np.load(os.path.join(GOLD, "pgm_frames.npz"))
+    frames = p["frames"]
+    cam, o, g = _empty_pair(max_features=60)
+    g.set_patch_warp(True)
+    o.set_options(O.Q_ALL, sparse=False, fast_corr=True, warp_patches=True)
+    rng = np.random.default_rng(11)
+    for k in range(6):
+        um = rng.random(200)
+        ur = rng.random(1000)
+        g.set_image(frames[k])
+        rco, io = o.map_management(frames[k], k + 1, 25, um)
+        rcg, ig = g.map_management(k + 1, 25, um)
+        assert (rco, io) == (rcg, ig), (k, rco, io, rcg, ig)
+        assert list(g.types()) == list(o.types())
+        xo, Po = o.get_state()
+        xg, Pg = g.download_state()
+        H.assert_x_close(xg, xo, what=f"x after map_management, frame {k}")
+        H.assert_P_close(Pg, Po, what=f"P after map_management, frame {k}")
+        o.frame(frames[k], ur)
+        g.frame(frames[k][None], ur[None])
+        fo, fg = o.features(), g.features()
+        for key in ("ic", "li", "hi"):
+            assert (fo[key] == fg[key]).all(), (k, key)
+        xo, Po = o.get_state()
+        xg, Pg = g.download_state()
+        H.assert_x_close(xg, xo, what=f"x after frame {k}")
+        H.assert_P_close(Pg, Po, what=f"P after frame {k}")
+    assert g.N >= 20

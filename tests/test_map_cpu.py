@@ -138,3 +138,42 @@ def test_add_feature_matches_python_restatement_and_reprojects():
     np.testing.assert_allclose(pose[:3], x[:3])
     np.testing.assert_allclose(pose[3:12].reshape(3, 3), synth.q2r(x[3:7]))
     assert tuple(pose[12:]) == (201.0, 77.0)
+
+
+def test_fast9_matches_cv2_fixtures():
+    """the oracle's cv::FAST restatement against keypoints produced by cv2 4.13 (tests/golden/make_fast_fixtures.py), order included"""
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fast_fixtures.npz"))
+    total = 0
+    for name in g["names"]:
+        for t in (100, 40):
+            kp = O.fast9(g[f"{name}_img"], t, True, 20000)
+            ref = g[f"{name}_kp{t}"]
+            assert kp.shape == ref.shape and (kp == ref).all(), (name, t)
+            total += len(ref)
+    assert total > 300
+    p = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pgm_frames.npz"))
+    for i in range(p["frames"].shape[0]):  # frames of the reference's bundled sequence
+        kp = O.fast9(p["frames"][i], 100, True, 20000)
+        assert kp.shape == p[f"kp{i}"].shape and (kp == p[f"kp{i}"]).all()
+
+
+def test_map_management_bootstraps_a_map_from_nothing():
+    """first frame: no features -> measured == 0 -> initialize_features(min_features) (src/Map.cpp:58-62)"""
+    import os
+
+    p = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pgm_frames.npz"))
+    cam = synth.Camera()
+    o = O.OracleFilter(cam.as9())
+    o.initialize_x_and_p()
+    u = np.random.default_rng(5).random(200)
+    rc, info = o.map_management(p["frames"][0], 1, 25, u)
+    assert rc == 0 and info["deleted"] == 0 and info["converted"] == -1
+    assert 0 < info["initialised"] <= 25 and info["attempts"] <= 50 and o.N == info["initialised"] and o.n == 13 + 6 * o.N
+    x, P = o.get_state()
+    assert np.allclose(P, P.T) and np.all(np.diag(P)[13:] >= 0)
+    for i in range(o.N):  # every new feature sits where FAST found a corner, shifted by the port's (-1, -1)
+        patch, pose = o.feature_init(i)
+        uv = pose[12:].astype(int)
+        assert np.array_equal(patch, p["frames"][0][uv[1] - 20:uv[1] + 21, uv[0] - 20:uv[0] + 21])
