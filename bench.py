@@ -161,6 +161,14 @@ def algorithmic_work(kernel, N, n, st):
         if kernel.endswith("chol_outer") or kernel.endswith("chol_inner"):
             return "tensor", sum(k**3 / 3.0 for k in ks)
         return "tensor", sum(float(n) * n * k + float(n) * k * k + k**3 / 3.0 for k in ks)
+    if kernel in ("k_chol_small", "k_chol_panel"):
+        # Cholesky k^3/3 + the explicit inverses of the 64 x 64 diagonal blocks (64^3/3 each): fp64, one CTA, a serial column chain
+        ks = [2.0 * mli, 2.0 * mhi]
+        return "tensor", sum(k**3 / 3.0 + np.ceil(k / 64.0) * 64.0**3 / 3.0 for k in ks if k > 0)
+    if kernel in ("k_trsm_small", "k_trsm_ll"):
+        return "tensor", sum(float(n + 1) * k * k for k in (2.0 * mli, 2.0 * mhi))
+    if kernel == "k_syrk_rows":
+        return "tensor", sum(float(n + 1) * n * k for k in (2.0 * mli, 2.0 * mhi))
     if kernel == "k_ekf_prediction":
         return "hbm", 2 * 13 * n * 8.0 * 2
     if kernel == "k_upd_jnorm":
@@ -304,7 +312,10 @@ def bench_c2(args, world, rank, local):
         fp64_peak = fp64_gemm_peak()
         per_frame_us = 1e3 * prof[top][1] / PF
         roof.update(bound="tensor", achieved=amount / (per_frame_us * 1e-6) / 1e12, peak=fp64_peak, unit="TFLOP/s",
-                    note="fp64 DMMA GEMM; peak = cuBLAS fp64 GEMM measured live (no fp64 figure in MEASURED_PEAKS.json); flops per frame of this use / its time per frame")
+                    note="fp64 (DMMA) work of this kernel per frame / its time per frame; peak = cuBLAS fp64 GEMM measured live (no fp64 figure in "
+                         "MEASURED_PEAKS.json).  C2 is ONE 613-state filter: every kernel of the step is launch/latency bound by construction "
+                         "(a frame touches ~3 MB and ~1e8 flop), so this fraction is small; the roofline fractions that mean something are "
+                         "under workloads.C3 (DMMA), workloads.C4 (support sweep, HBM) and workloads.C5 (batched filters)")
     else:
         roof.update(bound="hbm", achieved=(amount or 0.0) / (per_launch_us * 1e-6) / 1e9, peak=pk["hbm_gbs"], unit="GB/s", note="peak: " + pk["source"])
     roof["frac"] = roof["achieved"] / roof["peak"] if roof.get("peak") else None
