@@ -1,0 +1,1 @@
+// stand-in: the reference includes this Boost header but uses nothing from it

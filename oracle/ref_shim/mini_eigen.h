@@ -1,0 +1,908 @@
+// mini_eigen.h -- a small, eager, value-semantics stand-in for the part of Eigen 3 that the reference's sources use.
+// TEST INFRASTRUCTURE (oracle/): it exists only so that the reference's OWN translation units (src/ExtendKF.cpp, src/Tracking.cpp,
+// src/Converter.cpp, src/Map.cpp under /root/reference, compiled unmodified from where they lie) can be built in an image that has
+// no Eigen.  Nothing here is derived from Eigen's code; it implements the documented semantics the reference relies on:
+//   * column-major dense storage, (i, j) and linear (i) indexing, resize() that keeps the buffer when the element count is unchanged;
+//   * block views (block / row / col / head / tail / segment / top.. / bottom.. / left.. / middle..) that alias the parent;
+//   * comma initialisation with Eigen's block-row fill rule (blocks laid left to right, a new block row when the line is full);
+//   * .array() coefficient-wise arithmetic, pow / sqrt / sin / cos, comparison + rowwise().count();
+//   * vector <-> row-vector assignment transposes implicitly; a 1 x 1 result converts to its scalar;
+//   * MatrixXd::inverse() = LU with partial pivoting, inverse = solve(identity); fixed 2x2 / 3x3 / 4x4 inverse() = cofactor form
+//     (Eigen picks the algorithm by compile-time size; SURVEY.md 8c lists the call sites where that choice matters);
+//   * maxCoeff(&idx): first maximum under strict '>' starting from element 0 (so a NaN in element 0 is sticky);
+//   * SelfAdjointEigenSolver: eigenvalues ascending (cyclic Jacobi here; Eigen uses tridiagonal QR -- same values to rounding).
+// Products are evaluated left to right exactly as written in the reference (no expression-template re-association).
+#pragma once
+#include <algorithm>
+#include <cassert>
+#include <cmath>
+#include <cstddef>
+#include <cstdlib>
+#include <iostream>
+#include <type_traits>
+#include <vector>
+
+namespace Eigen {
+const int Dynamic = -1;
+typedef std::ptrdiff_t Index;
+enum ComputationInfo { Success = 0, NumericalIssue = 1, NoConvergence = 2, InvalidInput = 3 };
+
+template <class T> class Dyn;
+template <class T> class Blk;
+template <class T> class Arr;
+class ArrB;
+template <class T, int R, int C> class Matrix;
+template <class T> class CommaInit;
+
+[[noreturn]] inline void shim_fail(const char* what) {
+    std::cerr << "mini_eigen: " << what << std::endl;
+    std::abort();
+}
+#define MINI_EIGEN_ASSERT(c, what) \
+    do {                           \
+        if (!(c)) ::Eigen::shim_fail(what); \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// read-only interface shared by owning matrices and views
+// ---------------------------------------------------------------------------------------------------------------------------
+template <class D, class T> struct Ops {
+    const D& d() const { return *static_cast<const D*>(this); }
+    Dyn<T> eval() const;
+    Dyn<T> transpose() const;
+    Arr<T> array() const;
+    Dyn<T> matrix() const { return eval(); }
+    T sum() const {
+        T s = T(0);
+        for (Index j = 0; j < d().cols(); j++)
+            for (Index i = 0; i < d().rows(); i++) s += d().coeff(i, j);
+        return s;
+    }
+    T squaredNorm() const {
+        T s = T(0);
+        for (Index j = 0; j < d().cols(); j++)
+            for (Index i = 0; i < d().rows(); i++) s += d().coeff(i, j) * d().coeff(i, j);
+        return s;
+    }
+    T norm() const { return std::sqrt(squaredNorm()); }
+    T mean() const { return sum() / T(d().rows() * d().cols()); }
+    T trace() const {
+        T s = T(0);
+        for (Index i = 0; i < std::min(d().rows(), d().cols()); i++) s += d().coeff(i, i);
+        return s;
+    }
+    Index size() const { return d().rows() * d().cols(); }
+    T lin(Index k) const { return d().coeff(k % d().rows(), k / d().rows()); }
+    template <class I> T maxCoeff(I* idx) const {
+        MINI_EIGEN_ASSERT(size() > 0, "maxCoeff on an empty matrix");
+        T best = lin(0);
+        Index bi = 0;
+        for (Index k = 1; k < size(); k++)
+            if (lin(k) > best) {
+                best = lin(k);
+                bi = k;
+            }
+        if (idx) *idx = (I)bi;
+        return best;
+    }
+    T maxCoeff() const { return maxCoeff<Index>(nullptr); }
+    template <class I> T minCoeff(I* idx) const {
+        MINI_EIGEN_ASSERT(size() > 0, "minCoeff on an empty matrix");
+        T best = lin(0);
+        Index bi = 0;
+        for (Index k = 1; k < size(); k++)
+            if (lin(k) < best) {
+                best = lin(k);
+                bi = k;
+            }
+        if (idx) *idx = (I)bi;
+        return best;
+    }
+    T minCoeff() const { return minCoeff<Index>(nullptr); }
+    Dyn<T> inverse() const;  // dynamic size: partial-pivot LU
+    Dyn<T> asDiagonal() const;
+    Dyn<T> normalized() const;
+    template <class E> Dyn<T> cross(const Ops<E, T>& o) const;
+    template <class E> T dot(const Ops<E, T>& o) const {
+        MINI_EIGEN_ASSERT(size() == o.size(), "dot: size mismatch");
+        T s = T(0);
+        for (Index k = 0; k < size(); k++) s += lin(k) * o.lin(k);
+        return s;
+    }
+    T determinant() const;
+    // views (alias the parent's storage; obtainable from const objects too, like Eigen's const blocks, but writable: the shim does
+    // not model const-correctness)
+    Blk<T> block(Index i, Index j, Index r, Index c) const;
+    Blk<T> row(Index i) const { return block(i, 0, 1, d().cols()); }
+    Blk<T> col(Index j) const { return block(0, j, d().rows(), 1); }
+    Blk<T> topLeftCorner(Index r, Index c) const { return block(0, 0, r, c); }
+    Blk<T> topRightCorner(Index r, Index c) const { return block(0, d().cols() - c, r, c); }
+    Blk<T> bottomLeftCorner(Index r, Index c) const { return block(d().rows() - r, 0, r, c); }
+    Blk<T> bottomRightCorner(Index r, Index c) const { return block(d().rows() - r, d().cols() - c, r, c); }
+    Blk<T> topRows(Index n) const { return block(0, 0, n, d().cols()); }
+    Blk<T> bottomRows(Index n) const { return block(d().rows() - n, 0, n, d().cols()); }
+    Blk<T> middleRows(Index i, Index n) const { return block(i, 0, n, d().cols()); }
+    Blk<T> leftCols(Index n) const { return block(0, 0, d().rows(), n); }
+    Blk<T> rightCols(Index n) const { return block(0, d().cols() - n, d().rows(), n); }
+    Blk<T> middleCols(Index j, Index n) const { return block(0, j, d().rows(), n); }
+    Blk<T> segment(Index i, Index n) const {
+        MINI_EIGEN_ASSERT(d().rows() == 1 || d().cols() == 1, "segment on a non-vector");
+        const bool as_row = d().rows() == 1 && (d().cols() != 1 || d().row_vector_type());
+        return as_row ? block(0, i, 1, n) : block(i, 0, n, 1);
+    }
+    Blk<T> head(Index n) const { return segment(0, n); }
+    Blk<T> tail(Index n) const { return segment(size() - n, n); }
+};
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// write interface shared by owning matrices and views
+// ---------------------------------------------------------------------------------------------------------------------------
+template <class D, class T> struct WOps : Ops<D, T> {
+    D& md() { return *static_cast<D*>(this); }
+    template <class E> void copy_from(const Ops<E, T>& o);  // sizes must already agree
+    void fill(T v) {
+        for (Index j = 0; j < md().cols(); j++)
+            for (Index i = 0; i < md().rows(); i++) md().ref(i, j) = v;
+    }
+    D& setZero() {
+        fill(T(0));
+        return md();
+    }
+    D& setOnes() {
+        fill(T(1));
+        return md();
+    }
+    D& setConstant(T v) {
+        fill(v);
+        return md();
+    }
+    D& setIdentity() {
+        for (Index j = 0; j < md().cols(); j++)
+            for (Index i = 0; i < md().rows(); i++) md().ref(i, j) = (i == j) ? T(1) : T(0);
+        return md();
+    }
+    void normalize() {
+        T nrm = this->norm();
+        for (Index j = 0; j < md().cols(); j++)
+            for (Index i = 0; i < md().rows(); i++) md().ref(i, j) /= nrm;
+    }
+    T& operator()(Index i, Index j) { return md().ref(i, j); }
+    const T& operator()(Index i, Index j) const { return const_cast<D&>(this->d()).ref(i, j); }
+    T& operator()(Index k) { return md().ref(k % md().rows(), k / md().rows()); }
+    const T& operator()(Index k) const { return const_cast<D&>(this->d()).ref(k % this->d().rows(), k / this->d().rows()); }
+    T& operator[](Index k) { return (*this)(k); }
+    const T& operator[](Index k) const { return (*this)(k); }
+    T& x() { return (*this)(0); }
+    T& y() { return (*this)(1); }
+    T& z() { return (*this)(2); }
+    CommaInit<T> operator<<(const T& s);
+    template <class E> CommaInit<T> operator<<(const Ops<E, T>& o);
+    CommaInit<T> operator<<(const Arr<T>& o);
+    template <class E> D& operator+=(const Ops<E, T>& o) {
+        Dyn<T> e = o.eval();
+        MINI_EIGEN_ASSERT(e.rows() == md().rows() && e.cols() == md().cols(), "+=: size mismatch");
+        for (Index j = 0; j < md().cols(); j++)
+            for (Index i = 0; i < md().rows(); i++) md().ref(i, j) += e.coeff(i, j);
+        return md();
+    }
+    template <class E> D& operator-=(const Ops<E, T>& o) {
+        Dyn<T> e = o.eval();
+        MINI_EIGEN_ASSERT(e.rows() == md().rows() && e.cols() == md().cols(), "-=: size mismatch");
+        for (Index j = 0; j < md().cols(); j++)
+            for (Index i = 0; i < md().rows(); i++) md().ref(i, j) -= e.coeff(i, j);
+        return md();
+    }
+    D& operator*=(T s) {
+        for (Index j = 0; j < md().cols(); j++)
+            for (Index i = 0; i < md().rows(); i++) md().ref(i, j) *= s;
+        return md();
+    }
+    D& operator/=(T s) {
+        for (Index j = 0; j < md().cols(); j++)
+            for (Index i = 0; i < md().rows(); i++) md().ref(i, j) /= s;
+        return md();
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// owning dynamic matrix
+// ---------------------------------------------------------------------------------------------------------------------------
+template <class T> class Dyn : public WOps<Dyn<T>, T> {
+  public:
+    typedef T Scalar;
+    Dyn() : r_(0), c_(0) {}
+    Dyn(Index r, Index c) : r_(r), c_(c), a_((size_t)(r * c), T(0)) {}
+    template <class E> Dyn(const Ops<E, T>& o) : r_(o.d().rows()), c_(o.d().cols()), a_((size_t)(r_ * c_)) {
+        for (Index j = 0; j < c_; j++)
+            for (Index i = 0; i < r_; i++) a_[(size_t)(i + j * r_)] = o.d().coeff(i, j);
+    }
+    Dyn(const Arr<T>& o);
+    Index rows() const { return r_; }
+    Index cols() const { return c_; }
+    bool row_vector_type() const { return rowvec_; }
+    T coeff(Index i, Index j) const {
+        MINI_EIGEN_ASSERT(i >= 0 && i < r_ && j >= 0 && j < c_, "index out of range");
+        return a_[(size_t)(i + j * r_)];
+    }
+    T& ref(Index i, Index j) {
+        MINI_EIGEN_ASSERT(i >= 0 && i < r_ && j >= 0 && j < c_, "index out of range");
+        return a_[(size_t)(i + j * r_)];
+    }
+    T* data() { return a_.data(); }
+    const T* data() const { return a_.data(); }
+    Index ld() const { return r_; }
+    void resize(Index r, Index c) {
+        MINI_EIGEN_ASSERT(r >= 0 && c >= 0, "resize: negative size");
+        if ((size_t)(r * c) != a_.size()) a_.assign((size_t)(r * c), T(0));
+        r_ = r;
+        c_ = c;
+    }
+    void conservativeResize(Index r, Index c) {
+        Dyn<T> n(r, c);
+        for (Index j = 0; j < std::min(c, c_); j++)
+            for (Index i = 0; i < std::min(r, r_); i++) n.ref(i, j) = coeff(i, j);
+        *this = n;
+    }
+    using WOps<Dyn<T>, T>::setZero;
+    using WOps<Dyn<T>, T>::setIdentity;
+    using WOps<Dyn<T>, T>::setOnes;
+    Dyn& setZero(Index r, Index c) {
+        resize(r, c);
+        return this->setZero();
+    }
+    Dyn& setIdentity(Index r, Index c) {
+        resize(r, c);
+        return this->setIdentity();
+    }
+    Dyn& setOnes(Index r, Index c) {
+        resize(r, c);
+        return this->setOnes();
+    }
+    static Dyn Zero(Index r, Index c) { return Dyn(r, c); }
+    static Dyn Ones(Index r, Index c) {
+        Dyn m(r, c);
+        m.setOnes();
+        return m;
+    }
+    static Dyn Constant(Index r, Index c, T v) {
+        Dyn m(r, c);
+        m.fill(v);
+        return m;
+    }
+    static Dyn Identity(Index r, Index c) {
+        Dyn m(r, c);
+        m.setIdentity();
+        return m;
+    }
+    template <class E> Dyn& operator=(const Ops<E, T>& o) {
+        Dyn<T> e(o);
+        assign_dyn(e);
+        return *this;
+    }
+    Dyn& operator=(const Arr<T>& o);
+    operator T() const {  // Eigen: a 1 x 1 expression converts to its scalar
+        MINI_EIGEN_ASSERT(r_ == 1 && c_ == 1, "implicit scalar conversion of a matrix that is not 1 x 1");
+        return a_[0];
+    }
+    void assign_dyn(const Dyn<T>& e) {
+        r_ = e.r_;
+        c_ = e.c_;
+        a_ = e.a_;
+    }
+
+  protected:
+    Index r_, c_;
+    std::vector<T> a_;
+    bool rowvec_ = false;  // compile-time row-vector types set this so that head/segment on an empty row vector keep orientation
+};
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// view
+// ---------------------------------------------------------------------------------------------------------------------------
+template <class T> class Blk : public WOps<Blk<T>, T> {
+  public:
+    Blk(T* p, Index ld, Index r, Index c, bool rowvec) : p_(p), ld_(ld), r_(r), c_(c), rowvec_(rowvec) {}
+    Blk(const Blk&) = default;
+    Index rows() const { return r_; }
+    Index cols() const { return c_; }
+    bool row_vector_type() const { return rowvec_; }
+    T coeff(Index i, Index j) const {
+        MINI_EIGEN_ASSERT(i >= 0 && i < r_ && j >= 0 && j < c_, "block index out of range");
+        return p_[i + j * ld_];
+    }
+    T& ref(Index i, Index j) {
+        MINI_EIGEN_ASSERT(i >= 0 && i < r_ && j >= 0 && j < c_, "block index out of range");
+        return p_[i + j * ld_];
+    }
+    T* data() const { return p_; }
+    Index ld() const { return ld_; }
+    Blk& operator=(const Blk& o) {
+        Dyn<T> e(o);
+        assign(e);
+        return *this;
+    }
+    template <class E> Blk& operator=(const Ops<E, T>& o) {
+        Dyn<T> e(o);
+        assign(e);
+        return *this;
+    }
+    Blk& operator=(const Arr<T>& o);
+    void assign(const Dyn<T>& e) {
+        if (e.rows() == r_ && e.cols() == c_) {
+            for (Index j = 0; j < c_; j++)
+                for (Index i = 0; i < r_; i++) p_[i + j * ld_] = e.coeff(i, j);
+        } else if ((r_ == 1 || c_ == 1) && e.rows() == c_ && e.cols() == r_) {  // vector <- transposed vector
+            for (Index j = 0; j < c_; j++)
+                for (Index i = 0; i < r_; i++) p_[i + j * ld_] = e.coeff(j, i);
+        } else
+            shim_fail("block assignment: size mismatch");
+    }
+
+  private:
+    T* p_;
+    Index ld_, r_, c_;
+    bool rowvec_;
+};
+
+template <class D, class T> Blk<T> Ops<D, T>::block(Index i, Index j, Index r, Index c) const {
+    MINI_EIGEN_ASSERT(i >= 0 && j >= 0 && r >= 0 && c >= 0 && i + r <= d().rows() && j + c <= d().cols(), "block out of range");
+    D& m = const_cast<D&>(d());
+    return Blk<T>(m.data() + i + j * m.ld(), m.ld(), r, c, r == 1 && c != 1);
+}
+template <class D, class T> Dyn<T> Ops<D, T>::eval() const { return Dyn<T>(*this); }
+template <class D, class T> Dyn<T> Ops<D, T>::transpose() const {
+    Dyn<T> t(d().cols(), d().rows());
+    for (Index j = 0; j < d().cols(); j++)
+        for (Index i = 0; i < d().rows(); i++) t.ref(j, i) = d().coeff(i, j);
+    return t;
+}
+template <class D, class T> Dyn<T> Ops<D, T>::asDiagonal() const {
+    Index n = size();
+    Dyn<T> m(n, n);
+    for (Index k = 0; k < n; k++) m.ref(k, k) = lin(k);
+    return m;
+}
+template <class D, class T> Dyn<T> Ops<D, T>::normalized() const {
+    Dyn<T> m(*this);
+    m.normalize();
+    return m;
+}
+template <class D, class T> template <class E> Dyn<T> Ops<D, T>::cross(const Ops<E, T>& o) const {
+    MINI_EIGEN_ASSERT(size() == 3 && o.size() == 3, "cross: 3-vectors only");
+    Dyn<T> m(d().rows(), d().cols());
+    T a0 = lin(0), a1 = lin(1), a2 = lin(2), b0 = o.lin(0), b1 = o.lin(1), b2 = o.lin(2);
+    m(0) = a1 * b2 - a2 * b1;
+    m(1) = a2 * b0 - a0 * b2;
+    m(2) = a0 * b1 - a1 * b0;
+    return m;
+}
+template <class D, class T> template <class E> void WOps<D, T>::copy_from(const Ops<E, T>& o) {
+    Dyn<T> e(o);
+    for (Index j = 0; j < md().cols(); j++)
+        for (Index i = 0; i < md().rows(); i++) md().ref(i, j) = e.coeff(i, j);
+}
+
+// LU with partial pivoting (first largest |pivot| in the column), inverse = solve(P * I): forward substitution with the unit lower
+// factor, back substitution with the upper factor.
+template <class T> Dyn<T> lu_inverse(const Dyn<T>& A) {
+    Index n = A.rows();
+    MINI_EIGEN_ASSERT(n == A.cols(), "inverse of a non-square matrix");
+    Dyn<T> lu(A);
+    std::vector<Index> perm((size_t)n);
+    for (Index i = 0; i < n; i++) perm[(size_t)i] = i;
+    for (Index k = 0; k < n; k++) {
+        Index piv = k;
+        T best = std::abs(lu.coeff(k, k));
+        for (Index i = k + 1; i < n; i++)
+            if (std::abs(lu.coeff(i, k)) > best) {
+                best = std::abs(lu.coeff(i, k));
+                piv = i;
+            }
+        if (piv != k) {
+            for (Index j = 0; j < n; j++) std::swap(lu.ref(k, j), lu.ref(piv, j));
+            std::swap(perm[(size_t)k], perm[(size_t)piv]);
+        }
+        T p = lu.coeff(k, k);
+        for (Index i = k + 1; i < n; i++) lu.ref(i, k) /= p;
+        for (Index j = k + 1; j < n; j++) {
+            T u = lu.coeff(k, j);
+            for (Index i = k + 1; i < n; i++) lu.ref(i, j) -= lu.coeff(i, k) * u;
+        }
+    }
+    Dyn<T> X(n, n);
+    for (Index i = 0; i < n; i++) X.ref(i, perm[(size_t)i]) = T(1);
+    for (Index c = 0; c < n; c++) {
+        for (Index k = 0; k < n; k++) {
+            T xk = X.coeff(k, c);
+            if (xk != T(0))
+                for (Index i = k + 1; i < n; i++) X.ref(i, c) -= lu.coeff(i, k) * xk;
+        }
+        for (Index k = n - 1; k >= 0; k--) {
+            X.ref(k, c) /= lu.coeff(k, k);
+            T xk = X.coeff(k, c);
+            for (Index i = 0; i < k; i++) X.ref(i, c) -= lu.coeff(i, k) * xk;
+        }
+    }
+    return X;
+}
+template <class D, class T> Dyn<T> Ops<D, T>::inverse() const { return lu_inverse<T>(eval()); }
+
+template <class T> T det_small(const Dyn<T>& m) {
+    Index n = m.rows();
+    if (n == 1) return m.coeff(0, 0);
+    if (n == 2) return m.coeff(0, 0) * m.coeff(1, 1) - m.coeff(1, 0) * m.coeff(0, 1);
+    T s = T(0);
+    for (Index c = 0; c < n; c++) {
+        Dyn<T> sub(n - 1, n - 1);
+        for (Index i = 1; i < n; i++)
+            for (Index j = 0, jj = 0; j < n; j++)
+                if (j != c) sub.ref(i - 1, jj++) = m.coeff(i, j);
+        s += ((c & 1) ? -T(1) : T(1)) * m.coeff(0, c) * det_small(sub);
+    }
+    return s;
+}
+template <class D, class T> T Ops<D, T>::determinant() const { return det_small<T>(eval()); }
+// closed-form inverse for compile-time sizes <= 4: adjugate / determinant
+template <class T> Dyn<T> cofactor_inverse(const Dyn<T>& m) {
+    Index n = m.rows();
+    Dyn<T> r(n, n);
+    if (n == 1) {
+        r.ref(0, 0) = T(1) / m.coeff(0, 0);
+        return r;
+    }
+    if (n == 2) {
+        T invdet = T(1) / (m.coeff(0, 0) * m.coeff(1, 1) - m.coeff(1, 0) * m.coeff(0, 1));
+        r.ref(0, 0) = m.coeff(1, 1) * invdet;
+        r.ref(1, 0) = -m.coeff(1, 0) * invdet;
+        r.ref(0, 1) = -m.coeff(0, 1) * invdet;
+        r.ref(1, 1) = m.coeff(0, 0) * invdet;
+        return r;
+    }
+    Dyn<T> cof(n, n);
+    for (Index i = 0; i < n; i++)
+        for (Index j = 0; j < n; j++) {
+            Dyn<T> sub(n - 1, n - 1);
+            for (Index a = 0, aa = 0; a < n; a++) {
+                if (a == i) continue;
+                for (Index b = 0, bb = 0; b < n; b++)
+                    if (b != j) sub.ref(aa, bb++) = m.coeff(a, b);
+                aa++;
+            }
+            cof.ref(i, j) = (((i + j) & 1) ? -T(1) : T(1)) * det_small(sub);
+        }
+    T det = T(0);
+    for (Index i = 0; i < n; i++) det += cof.coeff(i, 0) * m.coeff(i, 0);
+    T invdet = T(1) / det;
+    for (Index i = 0; i < n; i++)
+        for (Index j = 0; j < n; j++) r.ref(i, j) = cof.coeff(j, i) * invdet;
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// comma initialiser (Eigen's rule: blocks are laid left to right; when the current line is full the next item opens a new block row)
+// ---------------------------------------------------------------------------------------------------------------------------
+template <class T> class CommaInit {
+  public:
+    CommaInit(const Blk<T>& target, const T& s) : t_(target), row_(0), col_(1), brows_(1) {
+        MINI_EIGEN_ASSERT(t_.rows() > 0 && t_.cols() > 0, "comma initialiser on an empty matrix");
+        t_.ref(0, 0) = s;
+    }
+    CommaInit(const Blk<T>& target, const Dyn<T>& o) : t_(target), row_(0), col_(o.cols()), brows_(o.rows()) {
+        MINI_EIGEN_ASSERT(o.rows() <= t_.rows() && o.cols() <= t_.cols(), "comma initialiser: first block too large");
+        t_.block(0, 0, o.rows(), o.cols()).assign(o);
+    }
+    CommaInit& operator,(const T& s) {
+        if (col_ == t_.cols()) {
+            row_ += brows_;
+            col_ = 0;
+            brows_ = 1;
+        }
+        MINI_EIGEN_ASSERT(row_ < t_.rows() && col_ < t_.cols(), "comma initialiser: too many coefficients");
+        t_.ref(row_, col_++) = s;
+        return *this;
+    }
+    CommaInit& add(const Dyn<T>& o) {
+        if (o.cols() == 0 || o.rows() == 0) return *this;
+        if (col_ == t_.cols()) {
+            row_ += brows_;
+            col_ = 0;
+            brows_ = o.rows();
+        }
+        MINI_EIGEN_ASSERT(row_ + o.rows() <= t_.rows() && col_ + o.cols() <= t_.cols(), "comma initialiser: block does not fit");
+        t_.block(row_, col_, o.rows(), o.cols()).assign(o);
+        col_ += o.cols();
+        return *this;
+    }
+    template <class E> CommaInit& operator,(const Ops<E, T>& o) { return add(Dyn<T>(o)); }
+    CommaInit& operator,(const Arr<T>& o);
+
+  private:
+    Blk<T> t_;
+    Index row_, col_, brows_;
+};
+template <class D, class T> CommaInit<T> WOps<D, T>::operator<<(const T& s) { return CommaInit<T>(this->block(0, 0, md().rows(), md().cols()), s); }
+template <class D, class T> template <class E> CommaInit<T> WOps<D, T>::operator<<(const Ops<E, T>& o) {
+    return CommaInit<T>(this->block(0, 0, md().rows(), md().cols()), Dyn<T>(o));
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// compile-time-sized front end: Matrix<T, R, C>
+// ---------------------------------------------------------------------------------------------------------------------------
+template <class T, int R, int C> class Matrix : public Dyn<T> {
+    static const bool kColVec = (C == 1 && R != 1), kRowVec = (R == 1 && C != 1);
+
+  public:
+    Matrix() : Dyn<T>(R < 0 ? 0 : R, C < 0 ? 0 : C) { this->rowvec_ = kRowVec; }
+    explicit Matrix(Index n) : Dyn<T>(kRowVec ? 1 : n, kRowVec ? n : 1) { this->rowvec_ = kRowVec; }
+    Matrix(Index r, Index c) : Dyn<T>(r, c) { this->rowvec_ = kRowVec; }
+    Matrix(const Matrix& o) : Dyn<T>(o) { this->rowvec_ = kRowVec; }
+    template <class E> Matrix(const Ops<E, T>& o) : Dyn<T>() {
+        this->rowvec_ = kRowVec;
+        take(Dyn<T>(o));
+    }
+    Matrix(const Arr<T>& o);
+    Matrix& operator=(const Matrix& o) {
+        this->assign_dyn(o);
+        this->rowvec_ = kRowVec;
+        return *this;
+    }
+    template <class E> Matrix& operator=(const Ops<E, T>& o) {
+        take(Dyn<T>(o));
+        return *this;
+    }
+    Matrix& operator=(const Arr<T>& o);
+    void take(const Dyn<T>& e) {
+        // vector types accept the other orientation (Eigen transposes implicitly on vector <- vector assignment)
+        if ((kColVec && e.cols() != 1 && e.rows() == 1) || (kRowVec && e.rows() != 1 && e.cols() == 1))
+            this->assign_dyn(e.transpose());
+        else
+            this->assign_dyn(e);
+    }
+    using Dyn<T>::resize;
+    using Dyn<T>::setZero;
+    using Dyn<T>::setIdentity;
+    using Dyn<T>::setOnes;
+    void resize(Index n) {
+        if (kRowVec)
+            Dyn<T>::resize(1, n);
+        else
+            Dyn<T>::resize(n, 1);
+    }
+    Matrix& setZero(Index n) {
+        resize(n);
+        Dyn<T>::setZero();
+        return *this;
+    }
+    using Dyn<T>::Zero;
+    using Dyn<T>::Ones;
+    using Dyn<T>::Identity;
+    static Matrix Zero() { return Matrix(); }
+    static Matrix Zero(Index n) { return Matrix(n); }
+    static Matrix Ones() {
+        Matrix m;
+        m.setOnes();
+        return m;
+    }
+    static Matrix Identity() {
+        Matrix m;
+        m.setIdentity();
+        return m;
+    }
+    Dyn<T> inverse() const {
+        if (R == C && R > 0 && R <= 4) return cofactor_inverse<T>(*this);
+        return lu_inverse<T>(*this);
+    }
+};
+typedef Matrix<double, Dynamic, Dynamic> MatrixXd;
+typedef Matrix<double, Dynamic, 1> VectorXd;
+typedef Matrix<double, 1, Dynamic> RowVectorXd;
+typedef Matrix<double, 2, 2> Matrix2d;
+typedef Matrix<double, 3, 3> Matrix3d;
+typedef Matrix<double, 4, 4> Matrix4d;
+typedef Matrix<double, 2, 1> Vector2d;
+typedef Matrix<double, 3, 1> Vector3d;
+typedef Matrix<double, 4, 1> Vector4d;
+typedef Matrix<double, 1, 2> RowVector2d;
+typedef Matrix<double, 1, 3> RowVector3d;
+typedef Matrix<double, 1, 4> RowVector4d;
+typedef Matrix<int, Dynamic, Dynamic> MatrixXi;
+typedef Matrix<int, Dynamic, 1> VectorXi;
+typedef Matrix<float, Dynamic, Dynamic> MatrixXf;
+
+// Eigen::Map<M>(ptr, rows, cols): the reference only ever uses it as an rvalue that is copied at once (a reshape), so a copy is
+// taken at construction -- which also makes the reference's self-aliasing `m = Map(m.data(), r, c)` reshapes safe.
+template <class M> class Map : public M {
+  public:
+    typedef typename M::Scalar S;
+    Map(const S* p, Index r, Index c) : M(r, c) {
+        for (Index k = 0; k < r * c; k++) this->data()[k] = p[k];
+    }
+    Map(const S* p, Index n) : M(n) {
+        for (Index k = 0; k < n; k++) this->data()[k] = p[k];
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// matrix arithmetic (eager)
+// ---------------------------------------------------------------------------------------------------------------------------
+template <class A, class B, class T> Dyn<T> operator+(const Ops<A, T>& a, const Ops<B, T>& b) {
+    MINI_EIGEN_ASSERT(a.d().rows() == b.d().rows() && a.d().cols() == b.d().cols(), "operator+: size mismatch");
+    Dyn<T> m(a.d().rows(), a.d().cols());
+    for (Index j = 0; j < m.cols(); j++)
+        for (Index i = 0; i < m.rows(); i++) m.ref(i, j) = a.d().coeff(i, j) + b.d().coeff(i, j);
+    return m;
+}
+template <class A, class B, class T> Dyn<T> operator-(const Ops<A, T>& a, const Ops<B, T>& b) {
+    MINI_EIGEN_ASSERT(a.d().rows() == b.d().rows() && a.d().cols() == b.d().cols(), "operator-: size mismatch");
+    Dyn<T> m(a.d().rows(), a.d().cols());
+    for (Index j = 0; j < m.cols(); j++)
+        for (Index i = 0; i < m.rows(); i++) m.ref(i, j) = a.d().coeff(i, j) - b.d().coeff(i, j);
+    return m;
+}
+template <class A, class T> Dyn<T> operator-(const Ops<A, T>& a) {
+    Dyn<T> m(a.d().rows(), a.d().cols());
+    for (Index j = 0; j < m.cols(); j++)
+        for (Index i = 0; i < m.rows(); i++) m.ref(i, j) = -a.d().coeff(i, j);
+    return m;
+}
+template <class A, class B, class T> Dyn<T> operator*(const Ops<A, T>& a, const Ops<B, T>& b) {
+    Dyn<T> x(a), y(b);
+    MINI_EIGEN_ASSERT(x.cols() == y.rows(), "operator*: inner dimensions differ");
+    Index M = x.rows(), N = y.cols(), K = x.cols();
+    Dyn<T> m(M, N);
+    const T* xa = x.data();
+    T* ma = m.data();
+    for (Index j = 0; j < N; j++)
+        for (Index k = 0; k < K; k++) {
+            T v = y.coeff(k, j);
+            const T* xc = xa + k * M;
+            T* mc = ma + j * M;
+            for (Index i = 0; i < M; i++) mc[i] += xc[i] * v;
+        }
+    return m;
+}
+template <class A, class T> Dyn<T> operator*(const Ops<A, T>& a, double s) {
+    Dyn<T> m(a);
+    for (Index k = 0; k < m.size(); k++) m.data()[k] = (T)(m.data()[k] * s);
+    return m;
+}
+template <class A, class T> Dyn<T> operator*(double s, const Ops<A, T>& a) {
+    Dyn<T> m(a);
+    for (Index k = 0; k < m.size(); k++) m.data()[k] = (T)(s * m.data()[k]);
+    return m;
+}
+template <class A, class T> Dyn<T> operator/(const Ops<A, T>& a, double s) {
+    Dyn<T> m(a);
+    for (Index k = 0; k < m.size(); k++) m.data()[k] = (T)(m.data()[k] / s);
+    return m;
+}
+template <class A, class T> std::ostream& operator<<(std::ostream& os, const Ops<A, T>& a) {
+    for (Index i = 0; i < a.d().rows(); i++) {
+        for (Index j = 0; j < a.d().cols(); j++) os << (j ? " " : "") << a.d().coeff(i, j);
+        if (i + 1 < a.d().rows()) os << "\n";
+    }
+    return os;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// coefficient-wise world
+// ---------------------------------------------------------------------------------------------------------------------------
+class RowwiseB;
+class ArrB {
+  public:
+    Dyn<char> m;
+    RowwiseB rowwise() const;
+    Index count() const {
+        Index n = 0;
+        for (Index k = 0; k < m.size(); k++) n += m.data()[k] ? 1 : 0;
+        return n;
+    }
+    bool any() const { return count() > 0; }
+    bool all() const { return count() == m.size(); }
+};
+class RowwiseB {
+  public:
+    explicit RowwiseB(const Dyn<char>& m) : m_(m) {}
+    Dyn<Index> count() const {
+        Dyn<Index> c(m_.rows(), 1);
+        for (Index i = 0; i < m_.rows(); i++)
+            for (Index j = 0; j < m_.cols(); j++) c.ref(i, 0) += m_.coeff(i, j) ? 1 : 0;
+        return c;
+    }
+
+  private:
+    Dyn<char> m_;
+};
+inline RowwiseB ArrB::rowwise() const { return RowwiseB(m); }
+
+template <class T> class Arr {
+  public:
+    Dyn<T> m;
+    Arr() {}
+    explicit Arr(const Dyn<T>& v) : m(v) {}
+    Index rows() const { return m.rows(); }
+    Index cols() const { return m.cols(); }
+    const Arr& array() const { return *this; }
+    Dyn<T> matrix() const { return m; }
+    Arr transpose() const { return Arr(m.transpose()); }
+    T sum() const { return m.sum(); }
+    template <class F> Arr map(F f) const {
+        Arr r(m);
+        for (Index k = 0; k < r.m.size(); k++) r.m.data()[k] = f(m.data()[k]);
+        return r;
+    }
+    template <class P> Arr pow(P e) const {
+        return map([e](T v) { return (T)std::pow(v, e); });
+    }
+    Arr sqrt() const {
+        return map([](T v) { return (T)std::sqrt(v); });
+    }
+    Arr sin() const {
+        return map([](T v) { return (T)std::sin(v); });
+    }
+    Arr cos() const {
+        return map([](T v) { return (T)std::cos(v); });
+    }
+    Arr abs() const {
+        return map([](T v) { return (T)std::abs(v); });
+    }
+    Arr square() const {
+        return map([](T v) { return v * v; });
+    }
+    Arr exp() const {
+        return map([](T v) { return (T)std::exp(v); });
+    }
+    Arr log() const {
+        return map([](T v) { return (T)std::log(v); });
+    }
+    Arr operator-() const {
+        return map([](T v) { return -v; });
+    }
+};
+template <class T, class F> Arr<T> arr_zip(const Arr<T>& a, const Arr<T>& b, F f) {
+    MINI_EIGEN_ASSERT(a.rows() == b.rows() && a.cols() == b.cols(), "array operation: size mismatch");
+    Arr<T> r(a.m);
+    for (Index k = 0; k < r.m.size(); k++) r.m.data()[k] = f(a.m.data()[k], b.m.data()[k]);
+    return r;
+}
+template <class T> Arr<T> operator+(const Arr<T>& a, const Arr<T>& b) {
+    return arr_zip(a, b, [](T x, T y) { return x + y; });
+}
+template <class T> Arr<T> operator-(const Arr<T>& a, const Arr<T>& b) {
+    return arr_zip(a, b, [](T x, T y) { return x - y; });
+}
+template <class T> Arr<T> operator*(const Arr<T>& a, const Arr<T>& b) {
+    return arr_zip(a, b, [](T x, T y) { return x * y; });
+}
+template <class T> Arr<T> operator/(const Arr<T>& a, const Arr<T>& b) {
+    return arr_zip(a, b, [](T x, T y) { return x / y; });
+}
+// scalar on either side; the scalar parameter is a non-deduced double so that int literals work
+template <class T> struct ident { typedef T type; };
+template <class T> Arr<T> operator+(const Arr<T>& a, typename ident<T>::type s) {
+    return a.map([s](T v) { return v + s; });
+}
+template <class T> Arr<T> operator+(typename ident<T>::type s, const Arr<T>& a) {
+    return a.map([s](T v) { return s + v; });
+}
+template <class T> Arr<T> operator-(const Arr<T>& a, typename ident<T>::type s) {
+    return a.map([s](T v) { return v - s; });
+}
+template <class T> Arr<T> operator-(typename ident<T>::type s, const Arr<T>& a) {
+    return a.map([s](T v) { return s - v; });
+}
+template <class T> Arr<T> operator*(const Arr<T>& a, typename ident<T>::type s) {
+    return a.map([s](T v) { return v * s; });
+}
+template <class T> Arr<T> operator*(typename ident<T>::type s, const Arr<T>& a) {
+    return a.map([s](T v) { return s * v; });
+}
+template <class T> Arr<T> operator/(const Arr<T>& a, typename ident<T>::type s) {
+    return a.map([s](T v) { return v / s; });
+}
+template <class T> Arr<T> operator/(typename ident<T>::type s, const Arr<T>& a) {
+    return a.map([s](T v) { return s / v; });
+}
+template <class T, class F> ArrB arr_cmp(const Arr<T>& a, F f) {
+    ArrB r;
+    r.m = Dyn<char>(a.rows(), a.cols());
+    for (Index k = 0; k < r.m.size(); k++) r.m.data()[k] = f(a.m.data()[k]) ? 1 : 0;
+    return r;
+}
+template <class T> ArrB operator<(const Arr<T>& a, typename ident<T>::type s) {
+    return arr_cmp(a, [s](T v) { return v < s; });
+}
+template <class T> ArrB operator>(const Arr<T>& a, typename ident<T>::type s) {
+    return arr_cmp(a, [s](T v) { return v > s; });
+}
+template <class T> ArrB operator<=(const Arr<T>& a, typename ident<T>::type s) {
+    return arr_cmp(a, [s](T v) { return v <= s; });
+}
+template <class T> ArrB operator>=(const Arr<T>& a, typename ident<T>::type s) {
+    return arr_cmp(a, [s](T v) { return v >= s; });
+}
+
+template <class D, class T> Arr<T> Ops<D, T>::array() const { return Arr<T>(eval()); }
+template <class T> Dyn<T>::Dyn(const Arr<T>& o) : r_(o.m.rows()), c_(o.m.cols()), a_(o.m.data(), o.m.data() + o.m.size()) {}
+template <class T> Dyn<T>& Dyn<T>::operator=(const Arr<T>& o) {
+    assign_dyn(o.m);
+    return *this;
+}
+template <class T> Blk<T>& Blk<T>::operator=(const Arr<T>& o) {
+    assign(o.m);
+    return *this;
+}
+template <class T, int R, int C> Matrix<T, R, C>::Matrix(const Arr<T>& o) : Dyn<T>() {
+    this->rowvec_ = kRowVec;
+    take(o.m);
+}
+template <class T, int R, int C> Matrix<T, R, C>& Matrix<T, R, C>::operator=(const Arr<T>& o) {
+    take(o.m);
+    return *this;
+}
+template <class T> CommaInit<T>& CommaInit<T>::operator,(const Arr<T>& o) { return add(o.m); }
+template <class D, class T> CommaInit<T> WOps<D, T>::operator<<(const Arr<T>& o) { return CommaInit<T>(this->block(0, 0, md().rows(), md().cols()), o.m); }
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// symmetric eigen-decomposition: cyclic Jacobi, eigenvalues ascending with matching eigenvector columns
+// ---------------------------------------------------------------------------------------------------------------------------
+template <class M> class SelfAdjointEigenSolver {
+  public:
+    SelfAdjointEigenSolver() {}
+    template <class E> explicit SelfAdjointEigenSolver(const Ops<E, double>& A) { compute(A); }
+    template <class E> SelfAdjointEigenSolver& compute(const Ops<E, double>& Ain) {
+        Dyn<double> A(Ain);
+        Index n = A.rows();
+        MINI_EIGEN_ASSERT(n == A.cols(), "eigen-solver: square matrices only");
+        // like Eigen, only the lower triangle is read
+        for (Index i = 0; i < n; i++)
+            for (Index j = i + 1; j < n; j++) A.ref(i, j) = A.coeff(j, i);
+        Dyn<double> V = Dyn<double>::Identity(n, n);
+        for (int sweep = 0; sweep < 64; sweep++) {
+            double off = 0;
+            for (Index p = 0; p < n; p++)
+                for (Index q = p + 1; q < n; q++) off += A.coeff(p, q) * A.coeff(p, q);
+            if (off == 0.0) break;
+            for (Index p = 0; p < n; p++)
+                for (Index q = p + 1; q < n; q++) {
+                    double apq = A.coeff(p, q);
+                    if (apq == 0.0) continue;
+                    double theta = (A.coeff(q, q) - A.coeff(p, p)) / (2.0 * apq);
+                    double t = (theta >= 0 ? 1.0 : -1.0) / (std::abs(theta) + std::sqrt(theta * theta + 1.0));
+                    double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
+                    for (Index k = 0; k < n; k++) {
+                        double akp = A.coeff(k, p), akq = A.coeff(k, q);
+                        A.ref(k, p) = c * akp - s * akq;
+                        A.ref(k, q) = s * akp + c * akq;
+                    }
+                    for (Index k = 0; k < n; k++) {
+                        double apk = A.coeff(p, k), aqk = A.coeff(q, k);
+                        A.ref(p, k) = c * apk - s * aqk;
+                        A.ref(q, k) = s * apk + c * aqk;
+                    }
+                    for (Index k = 0; k < n; k++) {
+                        double vkp = V.coeff(k, p), vkq = V.coeff(k, q);
+                        V.ref(k, p) = c * vkp - s * vkq;
+                        V.ref(k, q) = s * vkp + c * vkq;
+                    }
+                }
+        }
+        std::vector<Index> order((size_t)n);
+        for (Index i = 0; i < n; i++) order[(size_t)i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](Index a, Index b) { return A.coeff(a, a) < A.coeff(b, b); });
+        vals_.resize(n, 1);
+        vecs_.resize(n, n);
+        for (Index k = 0; k < n; k++) {
+            vals_.ref(k, 0) = A.coeff(order[(size_t)k], order[(size_t)k]);
+            for (Index i = 0; i < n; i++) vecs_.ref(i, k) = V.coeff(i, order[(size_t)k]);
+        }
+        return *this;
+    }
+    const Dyn<double>& eigenvalues() const { return vals_; }
+    const Dyn<double>& eigenvectors() const { return vecs_; }
+    ComputationInfo info() const { return Success; }
+
+  private:
+    Dyn<double> vals_, vecs_;
+};
+}  // namespace Eigen

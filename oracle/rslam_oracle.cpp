@@ -1172,9 +1172,12 @@ static Mat add_a_feature_covariance_inverse_depth(const Filter& F, const Mat& P,
     Mat dyprima_dgw(5, 3);
     dyprima_dgw.set_block(3, 0, dtheta_dgw);
     dyprima_dgw.set_block(4, 0, dphi_dgw);
+    // src/Map.cpp:375-379: `Eigen::Matrix<double,3,2> dgc_dhu; dgc_dhu << 1/fku, 0, 0, 0, 1/fkv, 0;` -- the comma initialiser fills
+    // ROW BY ROW, so the matrix is [1/fku 0; 0 0; 1/fkv 0] (the MATLAB original had the transpose of a 2 x 3).  Quirk Q16, found by
+    // running the reference's own Map.cpp (oracle/_ref); reproduced.
     Mat dgc_dhu(3, 2);
     dgc_dhu(0, 0) = 1 / fku;
-    dgc_dhu(1, 1) = 1 / fkv;
+    dgc_dhu(2, 0) = 1 / fkv;
     Mat dhu_dhd = jacob_undistor_fm(cam, uvd);
     Mat dyprima_dhd = dyprima_dgw * R_wc * dgc_dhu * dhu_dhd;
     Mat dy_dhd(6, 3);

@@ -129,10 +129,14 @@ __global__ void k_map_prep_add(DevFilter* Fs, int b, CamDev cam, double ud, doub
             tR[0][c] = dth[0] * R[c] + dth[1] * R[3 + c] + dth[2] * R[6 + c];
             tR[1][c] = dph[0] * R[c] + dph[1] * R[3 + c] + dph[2] * R[6 + c];
         }
-        double tg[2][2];  // * dgc_dhu = [1/fku 0; 0 1/fkv; 0 0]
+        // * dgc_dhu.  The reference comma-initialises the 3 x 2 matrix with "1/fku, 0, 0, 0, 1/fkv, 0" (src/Map.cpp:375-379); Eigen
+        // fills row by row, so what it multiplies by is [1/fku 0; 0 0; 1/fkv 0], not the [1/fku 0; 0 1/fkv; 0 0] of the MATLAB
+        // original (quirk Q16, found by compiling and running the reference's own Map.cpp).  Reproduced: the new feature's
+        // (theta, phi) covariance block is rank one.
+        double tg[2][2];
         for (int r = 0; r < 2; r++) {
-            tg[r][0] = tR[r][0] * (1 / cam.fku);
-            tg[r][1] = tR[r][1] * (1 / cam.fkv);
+            tg[r][0] = tR[r][0] * (1 / cam.fku) + tR[r][2] * (1 / cam.fkv);
+            tg[r][1] = 0.0;
         }
         double dy_dhd[6][3];
         for (int r = 0; r < 6; r++)

@@ -109,8 +109,12 @@ def hinv(cam, uvd, xv, rho0):
     return np.array([xv[0], xv[1], xv[2], np.arctan2(n[0], n[2]), np.arctan2(-n[1], np.hypot(n[0], n[2])), rho0])
 
 
-def feature_init_jacobians(cam, uvd, xv):
-    """dy_dxv (6x13) and dy_dhd (6x3) of a new inverse-depth feature (src/Map.cpp:339-386)."""
+def feature_init_jacobians(cam, uvd, xv, reference_fill=False):
+    """dy_dxv (6x13) and dy_dhd (6x3) of a new inverse-depth feature (src/Map.cpp:339-386).
+
+    reference_fill: the reference comma-initialises the 3 x 2 dgc_dhu with "1/fku, 0, 0, 0, 1/fkv, 0" (src/Map.cpp:379), which Eigen
+    lays out row by row as [1/fku 0; 0 0; 1/fkv 0] (quirk Q16) -- what Map::add_a_feature_covariance_inverse_depth really computes.
+    The synthetic scene generator keeps the intended [1/fku 0; 0 1/fkv; 0 0] (any SPD prior is a valid input)."""
     q = xv[3:7]
     R = q2r(q)
     uvu = undistort(cam, uvd)[0]
@@ -130,7 +134,7 @@ def feature_init_jacobians(cam, uvd, xv):
     dyp_dgw = np.zeros((5, 3))
     dyp_dgw[3] = dth
     dyp_dgw[4] = dph
-    dgc_dhu = np.array([[1 / cam.fku, 0], [0, 1 / cam.fkv], [0, 0]])
+    dgc_dhu = np.array([[1 / cam.fku, 0], [0, 0], [1 / cam.fkv, 0]]) if reference_fill else np.array([[1 / cam.fku, 0], [0, 1 / cam.fkv], [0, 0]])
     dyp_dhd = dyp_dgw @ R @ dgc_dhu @ jacob_undistort(cam, uvd)
     dy_dhd = np.zeros((6, 3))
     dy_dhd[0:5, 0:2] = dyp_dhd

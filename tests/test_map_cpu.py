@@ -122,7 +122,7 @@ def test_add_feature_matches_python_restatement_and_reprojects():
     xo, Po = o.get_state()
     y = synth.hinv(scene.cam, uv, x[:13], 1.0)
     np.testing.assert_allclose(xo[-6:], y, rtol=1e-14)
-    dy_dxv, dy_dhd = synth.feature_init_jacobians(scene.cam, uv, x[:13])
+    dy_dxv, dy_dhd = synth.feature_init_jacobians(scene.cam, uv, x[:13], reference_fill=True)
     n = x.size
     Padd = np.diag([scene.std_z**2, scene.std_z**2, 1.0])
     np.testing.assert_array_equal(Po[:n, :n], P)
