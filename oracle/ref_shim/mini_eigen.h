@@ -645,20 +645,49 @@ template <class A, class T> Dyn<T> operator-(const Ops<A, T>& a) {
         for (Index i = 0; i < m.rows(); i++) m.ref(i, j) = -a.d().coeff(i, j);
     return m;
 }
+// operands that already own contiguous storage are used in place (no copy of a 613 x 613 covariance per product)
+template <class A, class T> const Dyn<T>& as_dyn(const Ops<A, T>& a, Dyn<T>& tmp) {
+    if constexpr (std::is_base_of<Dyn<T>, A>::value || std::is_same<A, Dyn<T>>::value)
+        return static_cast<const Dyn<T>&>(a.d());
+    else {
+        tmp = Dyn<T>(a);
+        return tmp;
+    }
+}
+// every output entry is sum_k a(i,k) b(k,j) accumulated in ascending k (plain left-to-right sums, no blocking)
 template <class A, class B, class T> Dyn<T> operator*(const Ops<A, T>& a, const Ops<B, T>& b) {
-    Dyn<T> x(a), y(b);
+    Dyn<T> ta, tb;
+    const Dyn<T>&x = as_dyn(a, ta), &y = as_dyn(b, tb);
     MINI_EIGEN_ASSERT(x.cols() == y.rows(), "operator*: inner dimensions differ");
-    Index M = x.rows(), N = y.cols(), K = x.cols();
+    const Index M = x.rows(), N = y.cols(), K = x.cols();
     Dyn<T> m(M, N);
-    const T* xa = x.data();
+    if (M == 0 || N == 0 || K == 0) return m;
+    const T *xa = x.data(), *ya = y.data();
     T* ma = m.data();
-    for (Index j = 0; j < N; j++)
+    if (M <= 4 && K >= 16) {  // short-and-wide left operand (H_i P): rows made contiguous, one dot product per output entry
+        std::vector<T> xt((size_t)(M * K));
+        for (Index k = 0; k < K; k++)
+            for (Index i = 0; i < M; i++) xt[(size_t)(i * K + k)] = xa[i + k * M];
+        for (Index j = 0; j < N; j++) {
+            const T* yc = ya + j * K;
+            for (Index i = 0; i < M; i++) {
+                const T* xr = xt.data() + i * K;
+                T s = T(0);
+                for (Index k = 0; k < K; k++) s += xr[k] * yc[k];
+                ma[i + j * M] = s;
+            }
+        }
+        return m;
+    }
+    for (Index j = 0; j < N; j++) {
+        T* mc = ma + j * M;
+        const T* yc = ya + j * K;
         for (Index k = 0; k < K; k++) {
-            T v = y.coeff(k, j);
+            const T v = yc[k];
             const T* xc = xa + k * M;
-            T* mc = ma + j * M;
             for (Index i = 0; i < M; i++) mc[i] += xc[i] * v;
         }
+    }
     return m;
 }
 template <class A, class T> Dyn<T> operator*(const Ops<A, T>& a, double s) {
