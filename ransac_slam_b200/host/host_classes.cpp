@@ -96,7 +96,7 @@ int ExtendKF::ensure_device(int max_features) {
     p.std_a = std_a;
     p.std_alpha = std_alpha;
     p.std_z = std_z;
-    int cap = max_features < 64 ? 64 : max_features + max_features / 2;
+    int cap = max_features < 256 ? 256 : max_features + max_features / 2;  // the map grows on the device (Map::map_management)
     status_ = rslam_create(&c, &p, cap, 1, 0, &dev_);
     if (status_ == 0) dev_capacity_ = cap;
     return status_;
@@ -105,8 +105,8 @@ int ExtendKF::ensure_device(int max_features) {
 int ExtendKF::sync_to_device() {
     const int N = (int)features_info.size();
     if ((status_ = ensure_device(N))) return status_;
-    std::vector<int> types(N);
-    std::vector<double> patches((size_t)N * 169, 0.0);
+    std::vector<int> types(N + 1);
+    std::vector<double> patches((size_t)N * 169 + 1, 0.0);
     for (int i = 0; i < N; i++) {
         types[i] = features_info[i].type == "cartesian" ? 1 : 0;
         const Eigen::MatrixXd& pm = features_info[i].patch_when_matching;
@@ -119,10 +119,11 @@ int ExtendKF::sync_to_device() {
     if (status_ == 0 && N) status_ = rslam_upload_patches(dev_, 0, patches.data(), N);
     // when every feature carries its 41 x 41 initialisation patch (Map::initialize_a_features, src/Map.cpp:286-294) the predicted
     // appearance is warped on the device (Tracking::pred_patch_fc); otherwise patch_when_matching is used as given
-    bool have_init = N > 0;
+    // (an empty map counts as "has them": its features will be created on the device by Map::map_management, patches included)
+    bool have_init = true;
     for (int i = 0; i < N && have_init; i++)
         have_init = features_info[i].patch_when_initialized.rows() == 41 && features_info[i].patch_when_initialized.cols() == 41;
-    if (status_ == 0 && have_init) {
+    if (status_ == 0 && have_init && N > 0) {
         std::vector<uint8_t> p41((size_t)N * 1681);
         std::vector<double> r(3 * (size_t)N), R(9 * (size_t)N), uv(2 * (size_t)N);
         for (int i = 0; i < N; i++) {
@@ -153,8 +154,13 @@ int ExtendKF::sync_to_host(bool want_P) {
     std::vector<int> cnt(2 * N);
     if ((status_ = rslam_download_features(dev_, 0, h.data(), S.data(), z.data(), fl.data(), cnt.data()))) return status_;
     if ((status_ = rslam_download_H(dev_, 0, Hc.data(), Hf.data()))) return status_;
-    for (int i = 0; i < N && i < (int)features_info.size(); i++) {
+    // the map may have changed on the device (delete / convert / initialise): the mirror follows its size and types
+    std::vector<int> types(N);
+    if (N && (status_ = rslam_feature_types(dev_, 0, types.data()))) return status_;
+    features_info.resize(N);
+    for (int i = 0; i < N; i++) {
         Feature& f = features_info[i];
+        f.type = types[i] ? "cartesian" : "inversedepth";
         f.individually_compatible = fl[4 * i + 1];
         f.low_innovation_inlier = fl[4 * i + 2];
         f.high_innovation_inlier = fl[4 * i + 3];
@@ -243,10 +249,23 @@ void Tracking::rescue_hi_inliers(void) {
 // ---------------------------------------------------------------------------------------------------------------------
 Map::Map(const int min_fea, ExtendKF* m_ExtendKF) : min_features(min_fea), mM_ExtendKF(m_ExtendKF) {}
 Map::~Map() {}
-void Map::map_management(cv::Mat, int) {
-    rslam_filter* d = mM_ExtendKF->dev_;
-    mM_ExtendKF->status_ = d ? rslam_begin_frame(d) : RSLAM_ERR_INVALID;
-    (void)min_features;
+void Map::set_uniform_draws(const double* u01, int n) { u01_.assign(u01, u01 + n); }
+void Map::map_management(cv::Mat image, int step) {  // src/Map.cpp:16-67, on the device
+    ExtendKF* kf = mM_ExtendKF;
+    if (!kf->dev_ && kf->sync_to_device()) return;  // first frame: push the freshly initialised 13-state filter
+    rslam_filter* d = kf->dev_;
+    if (frozen_) {  // fixed synthetic maps: only step 2, the counters + flag reset (src/Map.cpp:34-55)
+        kf->status_ = rslam_begin_frame(d);
+        return;
+    }
+    if (u01_.empty()) {  // reference behaviour: ExtendKF::rand(2,1,0,1) per attempt, at most 50 attempts (src/Map.cpp:200,231)
+        u01_.resize(100);
+        for (double& u : u01_) u = (double)std::rand() / ((double)RAND_MAX + 1.0);
+    }
+    int rc = rslam_set_image(d, 0, image.data, image.rows, image.cols, (int)image.step, 0);
+    if (rc == 0) rc = rslam_map_management(d, 0, step, min_features, 1, u01_.data(), (int)(u01_.size() / 2), info_);
+    kf->status_ = rc;
+    u01_.clear();
 }
 
 }  // namespace ransac_slam

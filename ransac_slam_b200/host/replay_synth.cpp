@@ -38,6 +38,7 @@ int main(int argc, char** argv) {
     cam.dy = cam9[8];
     ExtendKF kf("", &cam, "constant_velocity");
     Map map(25, &kf);
+    map.set_frozen(true);  // the synthetic map is fixed: map_management only resets the per-frame flags
     Tracking tr("", &kf);
     kf.x_k_k.resize(n);
     kf.p_k_k.resize(n, n);
