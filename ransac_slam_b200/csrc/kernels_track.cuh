@@ -840,29 +840,41 @@ __global__ void __launch_bounds__(128) k_ransac_hyp(DevFilter* Fs) {
 }
 
 // c.3 support scoring (compute_hypothesis_support_fast, inlined at src/Tracking.cpp:424-503).
-//     CTA = tile of SJT matched inverse-depth features x batch of SHB distinct hypotheses.  The hypothesised feature rows are
-//     formed on the fly,      x_i[row] = x[row] + P[row, 0..6] a_p + P[row, y_p] b_p ,
+//     CTA = tile of SJT = 64 matched inverse-depth features x batch of SHB = 6 distinct hypotheses, 192 threads, 5 CTAs per SM.
+//     The hypothesised feature rows are formed on the fly,      x_i[row] = x[row] + P[row, 0..6] a_p + P[row, y_p] b_p ,
 //     so K (n x 2) is never materialised; the only pair-unique HBM traffic is the 6x6 block P[y_j, y_p] (288 B).
-//       phase 1: one thread per needed state row (coalesced down the columns of P, 6*SHB independent loads in flight per thread;
-//                the 7 camera columns are read once per row and reused for the SHB hypotheses) -> x_i tile in shared memory
-//       phase 2: one thread per (match, hypothesis) pair: re-projection, 10-step Newton distortion, residual < std_z;
-//                a warp covers 32 consecutive matches of one hypothesis, so its ballot IS the mask word.
+//       phase 1: exactly two state rows per thread (384 rows per tile, coalesced down the columns of P); per row the 7 camera
+//                columns are read once and reused for the 6 hypotheses, whose 36 pair-unique entries are fetched 12 at a time.
+//       phase 2: exactly two (match, hypothesis) pairs per thread: re-projection, Newton distortion, residual < std_z; a warp
+//                covers 32 consecutive matches of one hypothesis, so its ballot IS the mask word.
+//     ncu (profiles/r01_s2a_support_c4.md) showed the previous version of this kernel ISSUE bound, not HBM bound: 44 warp
+//     instructions per pair at 53 % issue-slot utilisation with DRAM at 49 %, while a pure-load kernel with the same access pattern
+//     runs at the streaming-copy peak (tools/ubench/pblock_read.cu: 6.9-7.5 TB/s for every tile shape).  Hence the instruction diet:
+//     column pointers advanced by one 64-bit add per load instead of re-derived, hypothesis constants as 16-byte shared loads,
+//     read-only loads through the non-coherent path, balanced 2 + 2 work per thread, Newton iterations stopped as soon as a whole
+//     warp has reached its fixed point (bit-identical to running all 10: a step that leaves rd unchanged leaves it unchanged for
+//     good), one shared reciprocal instead of four divisions, squared residual against the squared threshold.
 //     Quirk Q1 (reference): the angles of match jj are entries (2jj, 2jj+1) of the stacked POSITION vector of all matches; those
 //     two extra rows replace the (unused) theta / phi rows, so the row count per pair is 6 either way.
-constexpr int SJT = 64, SHB = 8;
-__global__ void __launch_bounds__(256, 4) k_ransac_support(DevFilter* Fs, CamDev cam, ParDev par, const int* t_indirect, int t_begin, int t_end,
-                                                        int t_lo, int t_hi, const int* used, int* sup_alt, unsigned long long* pair_counter) {
+constexpr int SJT = 64, SHB = 6;
+constexpr int SUP_THREADS = 192;
+constexpr int kSupSmemBytes = 0;
+static_assert(6 * SJT == 2 * SUP_THREADS && SHB * SJT == 2 * SUP_THREADS, "two rows and two pairs per thread");
+__global__ void __launch_bounds__(SUP_THREADS, 5) k_ransac_support(DevFilter* Fs, CamDev cam, ParDev par, const int* t_indirect, int t_begin, int t_end,
+                                                                  int t_lo, int t_hi, const int* used, int* sup_alt, unsigned long long* pair_counter) {
     DevFilter& F = Fs[blockIdx.z];
     const int nIC = F.ctl[CTL_NIC];
     const int m = F.ctl[CTL_MID];
     const int J0 = blockIdx.x * SJT;
     if (J0 >= m) return;
-    __shared__ int s_t[SHB], s_slot[SHB], s_offp[SHB], s_fsp[SHB];
-    __shared__ double s_ab[SHB][13], s_xc[SHB][7], s_R[SHB][9];
-    __shared__ int s_row[6 * SJT];
+    __shared__ int s_t[SHB], s_slot[SHB], s_fsp[SHB];
+    __shared__ long long s_colbase[SHB];  // element offset of column y_p in P
+    __shared__ __align__(16) double s_ab[SHB][14];
+    __shared__ double s_xc[SHB][7], s_R[SHB][9];
     __shared__ double xi[SHB][6 * SJT];
     const int tid = threadIdx.x;
     const bool q1 = (par.quirks & RSLAM_Q1_ANGLES_FROM_POSITIONS) != 0;
+    const int ld = F.ldp;
     if (tid < SHB) {
         const int slot = t_begin + blockIdx.y * SHB + tid;
         int t = -1;
@@ -875,24 +887,18 @@ __global__ void __launch_bounds__(256, 4) k_ransac_support(DevFilter* Fs, CamDev
         s_slot[tid] = slot;
         if (t >= 0) {
             const int p = F.ic_list[t];
-            s_offp[tid] = F.foff[p];
+            s_colbase[tid] = (long long)F.foff[p] * ld;
             s_fsp[tid] = F.ftype[p] == 0 ? 6 : 3;
         } else {
-            s_offp[tid] = 0;
+            s_colbase[tid] = 0;
             s_fsp[tid] = 0;
         }
     }
-    const int nv = __syncthreads_count(tid < SHB && s_t[tid] >= 0);
-    if (nv == 0) return;
-    for (int e = tid; e < SHB * 13; e += blockDim.x) {
-        const int pl = e / 13, c = e % 13;
-        s_ab[pl][c] = s_t[pl] >= 0 ? F.hyp_ab[(size_t)s_t[pl] * 13 + c] : 0.0;
-    }
-    for (int e = tid; e < SHB * 7; e += blockDim.x) {
-        const int pl = e / 7, c = e % 7;
-        s_xc[pl][c] = s_t[pl] >= 0 ? F.hyp_xcam[(size_t)s_t[pl] * 7 + c] : 0.0;
-    }
-    for (int k = tid; k < 6 * SJT; k += blockDim.x) {
+    // the two state rows this thread owns (independent of the hypotheses: their dependent index loads overlap the ones above)
+    int rows[2];
+#pragma unroll
+    for (int rr = 0; rr < 2; rr++) {
+        const int k = tid + rr * SUP_THREADS;
         int row = -1;
         if (q1) {
             if (k < 4 * SJT) {
@@ -907,43 +913,72 @@ __global__ void __launch_bounds__(256, 4) k_ransac_support(DevFilter* Fs, CamDev
             const int jj = J0 + k / 6;
             if (jj < m) row = F.foff[F.id_list[jj]] + k % 6;
         }
-        s_row[k] = row;
+        rows[rr] = row;
     }
+    const int nv = __syncthreads_count(tid < SHB && s_t[tid] >= 0);
+    if (nv == 0) return;
+    for (int e = tid; e < SHB * 14; e += SUP_THREADS) {
+        const int pl = e / 14, c = e % 14;
+        s_ab[pl][c] = (s_t[pl] >= 0 && c < 13) ? F.hyp_ab[(size_t)s_t[pl] * 13 + c] : 0.0;
+    }
+    for (int e = tid; e < SHB * 7; e += SUP_THREADS) {
+        const int pl = e / 7, c = e % 7;
+        s_xc[pl][c] = s_t[pl] >= 0 ? F.hyp_xcam[(size_t)s_t[pl] * 7 + c] : 0.0;
+    }
+    if (pair_counter && tid == 0) atomicAdd(pair_counter, (unsigned long long)nv * (unsigned long long)min(SJT, m - J0));
     __syncthreads();
     if (tid < SHB && s_t[tid] >= 0) q2r_dev(&s_xc[tid][3], s_R[tid]);
-    if (pair_counter && tid == 0) atomicAdd(pair_counter, (unsigned long long)nv * (unsigned long long)min(SJT, m - J0));
     // ---- phase 1 ----
-    const int ld = F.ldp;
-    const double* P = F.P;
-    const double* x = F.x_km1;
-    for (int k = tid; k < 6 * SJT; k += blockDim.x) {
-        const int row = s_row[k];
+    const double* __restrict__ P = F.P;
+    const double* __restrict__ x = F.x_km1;
+#pragma unroll 1
+    for (int rr = 0; rr < 2; rr++) {
+        const int k = tid + rr * SUP_THREADS;
+        const int row = rows[rr];
         if (row < 0) {
 #pragma unroll
             for (int pl = 0; pl < SHB; pl++) xi[pl][k] = 0.0;
             continue;
         }
+        const double* prow = P + row;
         double pc[7];
+        {
+            const double* q = prow;
 #pragma unroll
-        for (int c = 0; c < 7; c++) pc[c] = P[row + (size_t)c * ld];
-        const double xr = x[row];
-#pragma unroll 1
-        for (int g = 0; g < SHB; g += 2) {  // 2 hypotheses = 12 independent loads in flight per thread (x 512+ threads per SM)
+            for (int c = 0; c < 7; c++) {
+                pc[c] = __ldg(q);
+                q += ld;
+            }
+        }
+        const double xr = __ldg(x + row);
+#pragma unroll
+        for (int g = 0; g < SHB; g += 2) {  // 2 hypotheses = 12 independent loads in flight per thread (x 960 threads per SM)
             double pv[2][6];
 #pragma unroll
             for (int q = 0; q < 2; q++) {
-                const double* col = P + (size_t)s_offp[g + q] * ld + row;
+                const double* col = prow + s_colbase[g + q];
                 const int fs = s_fsp[g + q];
 #pragma unroll
-                for (int c = 0; c < 6; c++) pv[q][c] = (c < fs) ? col[(size_t)c * ld] : 0.0;
+                for (int c = 0; c < 6; c++) {
+                    pv[q][c] = (c < 3 ? fs > 0 : fs > 3) ? __ldg(col) : 0.0;
+                    col += ld;
+                }
             }
 #pragma unroll
             for (int q = 0; q < 2; q++) {
+                const double2* ab = reinterpret_cast<const double2*>(s_ab[g + q]);
+                double a[14];
+#pragma unroll
+                for (int c = 0; c < 7; c++) {
+                    const double2 v = ab[c];
+                    a[2 * c] = v.x;
+                    a[2 * c + 1] = v.y;
+                }
                 double sacc = xr;
 #pragma unroll
-                for (int c = 0; c < 7; c++) sacc += pc[c] * s_ab[g + q][c];
+                for (int c = 0; c < 7; c++) sacc += pc[c] * a[c];
 #pragma unroll
-                for (int c = 0; c < 6; c++) sacc += pv[q][c] * s_ab[g + q][7 + c];
+                for (int c = 0; c < 6; c++) sacc += pv[q][c] * a[7 + c];
                 xi[g + q][k] = sacc;
             }
         }
@@ -951,13 +986,17 @@ __global__ void __launch_bounds__(256, 4) k_ransac_support(DevFilter* Fs, CamDev
     __syncthreads();
     // ---- phase 2 ----
     const double fku = cam.f * (1.0 / cam.dx);
-    for (int e = tid; e < SHB * SJT; e += blockDim.x) {
+    const double idx = 1.0 / cam.dx, idy = 1.0 / cam.dy;
+    const double thr2 = par.std_z * par.std_z;
+#pragma unroll 1
+    for (int e = tid; e < SHB * SJT; e += SUP_THREADS) {
         const int pl = e / SJT, jl = e % SJT;
         const int jj = J0 + jl;
         const int t = s_t[pl];
-        bool inl = false;
-        if (t >= 0 && jj < m) {
-            double r3[3], a0, a1, rho;
+        const bool live = t >= 0 && jj < m;
+        // dead lanes run the arithmetic on zeros (converges at once) so that the warp-uniform early exit below stays uniform
+        double r3[3] = {0, 0, 0}, a0 = 0, a1 = 0, rho = 0;
+        if (live) {
             if (q1) {
                 r3[0] = xi[pl][4 * jl];
                 r3[1] = xi[pl][4 * jl + 1];
@@ -973,24 +1012,46 @@ __global__ void __launch_bounds__(256, 4) k_ransac_support(DevFilter* Fs, CamDev
                 a1 = xi[pl][6 * jl + 4];
                 rho = xi[pl][6 * jl + 5];
             }
-            double s0, c0, s1, c1;
-            sincos(a0, &s0, &c0);
-            sincos(a1, &s1, &c1);
-            const double mi[3] = {c1 * s0, -s1, c1 * c0};
-            double v3[3];
+        }
+        double s0, c0, s1, c1;
+        sincos(a0, &s0, &c0);
+        sincos(a1, &s1, &c1);
+        const double mi[3] = {c1 * s0, -s1, c1 * c0};
+        double v3[3];
 #pragma unroll
-            for (int k = 0; k < 3; k++) v3[k] = (r3[k] - s_xc[pl][k]) * rho + mi[k];
-            double hc[3];
+        for (int k = 0; k < 3; k++) v3[k] = (r3[k] - s_xc[pl][k]) * rho + mi[k];
+        double hc[3];
 #pragma unroll
-            for (int k = 0; k < 3; k++) hc[k] = s_R[pl][k] * v3[0] + s_R[pl][3 + k] * v3[1] + s_R[pl][6 + k] * v3[2];  // R^T v
-            const double ihz = 1.0 / hc[2];
-            const double u = fku * (hc[0] * ihz) + cam.Cx;
-            const double v = fku * (hc[1] * ihz) + cam.Cy;  // ku for both rows (src/Tracking.cpp:471)
-            double ud, vd;
-            distort_fast_dev(cam, u, v, ud, vd);
+        for (int k = 0; k < 3; k++) hc[k] = s_R[pl][k] * v3[0] + s_R[pl][3 + k] * v3[1] + s_R[pl][6 + k] * v3[2];  // R^T v
+        const double ihz = 1.0 / hc[2];
+        const double u = fku * (hc[0] * ihz) + cam.Cx;
+        const double v = fku * (hc[1] * ihz) + cam.Cy;  // ku for both rows (src/Tracking.cpp:471)
+        // distort_fm (src/ExtendKF.cpp:175-204) with the refined-reciprocal Newton step of distort_fast_dev
+        const double xu = (u - cam.Cx) * cam.dx;
+        const double yu = (v - cam.Cy) * cam.dy;
+        const double ru = sqrt(xu * xu + yu * yu);
+        const double ru2 = ru * ru;
+        double rd = ru * fast_rcp(1 + cam.k1 * ru2 + cam.k2 * (ru2 * ru2));
+#pragma unroll 1
+        for (int it = 0; it < 10; it++) {
+            const double rd2 = rd * rd;
+            const double rd4 = rd2 * rd2;
+            const double f = rd + cam.k1 * (rd2 * rd) + cam.k2 * (rd4 * rd) - ru;
+            const double fp = 1 + 3 * cam.k1 * rd2 + 5 * cam.k2 * rd4;
+            const double rn = fma(-f, fast_rcp(fp), rd);
+            const bool same = !(rn != rd) || !live;  // NaN counts as settled
+            rd = rn;
+            if (__all_sync(0xffffffffu, same)) break;
+        }
+        const double rdd = rd * rd;
+        const double iD = 1.0 / (1 + cam.k1 * rdd + cam.k2 * (rdd * rdd));
+        const double ud = xu * iD * idx + cam.Cx;
+        const double vd = yu * iD * idy + cam.Cy;
+        bool inl = false;
+        if (live) {
             const int fj = F.id_list[jj];
             const double n0 = F.z[2 * fj] - ud, n1 = F.z[2 * fj + 1] - vd;
-            inl = sqrt(n0 * n0 + n1 * n1) < par.std_z;
+            inl = n0 * n0 + n1 * n1 < thr2;
         }
         const unsigned bal = __ballot_sync(0xffffffffu, inl);
         if ((tid & 31) == 0 && t >= 0 && (jj >> 5) < F.mwords) {

@@ -252,7 +252,7 @@ int run_ransac_core(rslam_filter* f, bool select, bool gather_li = false) {
     LAUNCH(f, k_ransac_compact, dim3(1, B), 256, 0, f->dF);
     LAUNCH(f, k_ransac_hyp, dim3(cdiv(N, 128), B), 128, 0, f->dF);
     if (select) {
-        LAUNCH(f, k_ransac_support, dim3(cdiv(N, SJT), cdiv(N, SHB), B), 256, 0, f->dF, f->camd, f->pard, (const int*)nullptr, 0, N, 0, N, (const int*)nullptr,
+        LAUNCH(f, k_ransac_support, dim3(cdiv(N, SJT), cdiv(N, SHB), B), SUP_THREADS, kSupSmemBytes, f->dF, f->camd, f->pard, (const int*)nullptr, 0, N, 0, N, (const int*)nullptr,
                (int*)nullptr, (unsigned long long*)nullptr);
         LAUNCH(f, k_ransac_select, dim3(1, B), 256, 0, f->dF, f->pard, gather_li ? 1 : 0);
     }
@@ -311,6 +311,7 @@ int rslam_create(const rslam_camera* cam, const rslam_params* par, int max_featu
     CK(cudaFuncSetAttribute(k_gemm_dmma<64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<64, 64>::kSmemBytes));
     CK(cudaFuncSetAttribute(k_trsm_ll<48, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TrsmCfg<48, 2>::kSmemBytes));
     CK(cudaFuncSetAttribute(k_trsm_ll<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TrsmCfg<32, 2>::kSmemBytes));
+    CK(cudaFuncSetAttribute(k_ransac_support, cudaFuncAttributeMaxDynamicSharedMemorySize, kSupSmemBytes));
     CK(cudaFuncSetAttribute(k_chol_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPanelSmemBytes));
     CK(cudaFuncSetAttribute(k_chol_small, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholSmallSmemBytes));
     CK(cudaFuncSetAttribute(k_trsm_small, cudaFuncAttributeMaxDynamicSharedMemorySize, trsm_small_smem_bytes(SR_KMAX)));
@@ -932,7 +933,7 @@ int rslam_support_sweep(rslam_filter* f, const int* hyp_match_idx, int n_hyp, in
             const int tlo = match_begin < N ? match_begin : N, thi = match_end < N ? match_end : N;
             LAUNCH(f, k_sweep_mark, cdiv(nh, 256) < 1024 ? cdiv(nh, 256) : 1024, 256, 0, f->dF, d_idx, hyp_begin, hyp_end, match_begin, match_end, f->d_used);
             if (thi > tlo)
-                LAUNCH(f, k_ransac_support, dim3(cdiv(N, SJT), cdiv(thi - tlo, SHB), 1), 256, 0, f->dF, f->camd, f->pard, (const int*)nullptr, tlo, thi, tlo, thi,
+                LAUNCH(f, k_ransac_support, dim3(cdiv(N, SJT), cdiv(thi - tlo, SHB), 1), SUP_THREADS, kSupSmemBytes, f->dF, f->camd, f->pard, (const int*)nullptr, tlo, thi, tlo, thi,
                        (const int*)f->d_used, (int*)nullptr, f->d_key + 1);
             LAUNCH(f, k_sweep_reduce, cdiv(nh, 256) < 512 ? cdiv(nh, 256) : 512, 256, 0, f->dF, d_idx, hyp_begin, hyp_end, match_begin, match_end, (const int*)nullptr,
                    f->d_key);
@@ -943,7 +944,7 @@ int rslam_support_sweep(rslam_filter* f, const int* hyp_match_idx, int n_hyp, in
                 f->sup_h_cap = n_hyp;
             }
             CK(cudaMemsetAsync(f->d_sup_h + hyp_begin, 0, sizeof(int) * (size_t)nh, f->stream));
-            LAUNCH(f, k_ransac_support, dim3(cdiv(N, SJT), cdiv(nh, SHB), 1), 256, 0, f->dF, f->camd, f->pard, d_idx, hyp_begin, hyp_end, match_begin, match_end,
+            LAUNCH(f, k_ransac_support, dim3(cdiv(N, SJT), cdiv(nh, SHB), 1), SUP_THREADS, kSupSmemBytes, f->dF, f->camd, f->pard, d_idx, hyp_begin, hyp_end, match_begin, match_end,
                    (const int*)nullptr, f->d_sup_h, f->d_key + 1);
             LAUNCH(f, k_sweep_reduce, cdiv(nh, 256) < 512 ? cdiv(nh, 256) : 512, 256, 0, f->dF, d_idx, hyp_begin, hyp_end, match_begin, match_end, (const int*)f->d_sup_h,
                    f->d_key);
