@@ -860,7 +860,13 @@ constexpr int SJT = 64, SHB = 6;
 constexpr int SUP_THREADS = 192;
 constexpr int kSupSmemBytes = 0;
 static_assert(6 * SJT == 2 * SUP_THREADS && SHB * SJT == 2 * SUP_THREADS, "two rows and two pairs per thread");
-__global__ void __launch_bounds__(SUP_THREADS, 5) k_ransac_support(DevFilter* Fs, CamDev cam, ParDev par, const int* t_indirect, int t_begin, int t_end,
+#ifndef RSLAM_SUP_PREFETCH
+#define RSLAM_SUP_PREFETCH 0
+#endif
+#ifndef RSLAM_SUP_MINB
+#define RSLAM_SUP_MINB 5
+#endif
+__global__ void __launch_bounds__(SUP_THREADS, RSLAM_SUP_MINB) k_ransac_support(DevFilter* Fs, CamDev cam, ParDev par, const int* t_indirect, int t_begin, int t_end,
                                                                   int t_lo, int t_hi, const int* used, int* sup_alt, unsigned long long* pair_counter) {
     DevFilter& F = Fs[blockIdx.z];
     const int nIC = F.ctl[CTL_NIC];
@@ -917,6 +923,28 @@ __global__ void __launch_bounds__(SUP_THREADS, 5) k_ransac_support(DevFilter* Fs
     }
     const int nv = __syncthreads_count(tid < SHB && s_t[tid] >= 0);
     if (nv == 0) return;
+#if RSLAM_SUP_PREFETCH
+    // everything this thread will read from P goes to L2 now, while the hypothesis constants are still being gathered: the demand
+    // loads of phase 1 (12 in flight per thread, register bound) then find their lines in L2 or already on the way
+    {
+        const double* __restrict__ Pp = F.P;
+#pragma unroll
+        for (int rr = 0; rr < RSLAM_SUP_PREFETCH; rr++) {
+            if (rows[rr] < 0) continue;
+            const double* prow = Pp + rows[rr];
+#pragma unroll
+            for (int pl = 0; pl < SHB; pl++) {
+                const double* col = prow + s_colbase[pl];
+                const int fs = s_fsp[pl];
+#pragma unroll
+                for (int c = 0; c < 6; c++) {
+                    if (c < 3 ? fs > 0 : fs > 3) asm volatile("prefetch.global.L2 [%0];" ::"l"(col));
+                    col += ld;
+                }
+            }
+        }
+    }
+#endif
     for (int e = tid; e < SHB * 14; e += SUP_THREADS) {
         const int pl = e / 14, c = e % 14;
         s_ab[pl][c] = (s_t[pl] >= 0 && c < 13) ? F.hyp_ab[(size_t)s_t[pl] * 13 + c] : 0.0;
@@ -1014,8 +1042,8 @@ __global__ void __launch_bounds__(SUP_THREADS, 5) k_ransac_support(DevFilter* Fs
             }
         }
         double s0, c0, s1, c1;
-        sincos(a0, &s0, &c0);
-        sincos(a1, &s1, &c1);
+        sincos_fast(a0, &s0, &c0);
+        sincos_fast(a1, &s1, &c1);
         const double mi[3] = {c1 * s0, -s1, c1 * c0};
         double v3[3];
 #pragma unroll
@@ -1023,7 +1051,7 @@ __global__ void __launch_bounds__(SUP_THREADS, 5) k_ransac_support(DevFilter* Fs
         double hc[3];
 #pragma unroll
         for (int k = 0; k < 3; k++) hc[k] = s_R[pl][k] * v3[0] + s_R[pl][3 + k] * v3[1] + s_R[pl][6 + k] * v3[2];  // R^T v
-        const double ihz = 1.0 / hc[2];
+        const double ihz = fast_rcp(hc[2]);
         const double u = fku * (hc[0] * ihz) + cam.Cx;
         const double v = fku * (hc[1] * ihz) + cam.Cy;  // ku for both rows (src/Tracking.cpp:471)
         // distort_fm (src/ExtendKF.cpp:175-204) with the refined-reciprocal Newton step of distort_fast_dev
@@ -1044,7 +1072,7 @@ __global__ void __launch_bounds__(SUP_THREADS, 5) k_ransac_support(DevFilter* Fs
             if (__all_sync(0xffffffffu, same)) break;
         }
         const double rdd = rd * rd;
-        const double iD = 1.0 / (1 + cam.k1 * rdd + cam.k2 * (rdd * rdd));
+        const double iD = fast_rcp(1 + cam.k1 * rdd + cam.k2 * (rdd * rdd));
         const double ud = xu * iD * idx + cam.Cx;
         const double vd = yu * iD * idy + cam.Cy;
         bool inl = false;

@@ -48,7 +48,7 @@ def main():
         N, H = 5000, 100000
         scene, x, P, z = X.make_c4(dev, N)
         hyp = np.random.Generator(np.random.MT19937(99)).integers(0, N, H).astype(np.int32)
-        g = capi.Filter(scene.cam.as9(), N)
+        g = capi.Filter(scene.cam.as9(), N, dedupe=os.environ.get("RSLAM_DEDUPE", "1") == "1")
         xd = torch.from_numpy(x).to(dev)
         g.upload_state_device(xd.data_ptr(), P.data_ptr(), x.size, x.size, N, prior=True)
         g.set_matches(z, np.ones(N, dtype=np.uint8))
