@@ -229,6 +229,9 @@ __device__ __forceinline__ void smem_panel_factor(const PanelSmem& ps, int R, in
     double* sT = ps.sT;
     if (tid < kNB) ps.sRd[tid] = 1.0;
     __syncthreads();
+    // not unrolled: the body is ~3 k straight-line instructions (register-resident 16 x 16 potrf); four copies of it made the single-CTA
+    // kernel 260 KB of code, i.e. an instruction-cache miss stream on a path that runs every section once or twice per launch
+#pragma unroll 1
     for (int c0 = 0; c0 < kNB && c0 < w; c0 += kSB) {
         if (warp == 0) {  // (a) diagonal sub-block, in registers
             double a[kSB], rd[kSB];
@@ -324,17 +327,41 @@ __device__ __forceinline__ void store_linv(const double (*sX)[kNB + 1], double* 
     for (int e = t0; e < kNB * kNB; e += nt) out[e] = sX[e % kNB][e / kNB];
 }
 
-// load the diagonal block at (j0, j0) (identity padded beyond w) and `nr` rows starting at global row r0 into the panel
+// load the diagonal block at (j0, j0) (identity padded beyond w) and `nr` rows starting at global row r0 into the panel.
+// Warp `wp` takes columns wp, wp + 8, ...; a lane takes rows lane, lane + 32, ...: no integer divisions, and all of a thread's loads
+// of a column batch are issued before the first store (the element-indexed loop this replaces kept one load in flight per
+// thread and cost ~8.7 k cycles per 64 x 128 panel, a fifth of the single-CTA factorisation).
 __device__ __forceinline__ void panel_load(const PanelSmem& ps, const double* S, int ld, int j0, int w, int r0, int nr) {
-    for (int e = threadIdx.x; e < kNB * kNB; e += blockDim.x) {
-        const int i = e % kNB, c = e / kNB;
-        double v = (i == c) ? 1.0 : 0.0;
-        if (i < w && c < w && i >= c) v = S[(j0 + i) + (size_t)(j0 + c) * ld];
-        ps.sT[c * kTld + i] = v;
+    // plain (coherent) loads: k_chol_small re-reads entries of S that its own trailing update has just written.
+    // 256 threads: warp wp owns columns wp + 8 cs; all (up to 64) loads of a thread are issued before its first store.
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    double v[8][8];
+#pragma unroll
+    for (int cs = 0; cs < 8; cs++) {
+        const int c = wp + 8 * cs;
+        const double* col = S + (size_t)(j0 + c) * ld;
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            const int i = lane + 32 * q;
+            v[cs][q] = (i == c) ? 1.0 : 0.0;
+            if (i < w && c < w && i >= c) v[cs][q] = col[j0 + i];
+        }
+#pragma unroll
+        for (int q = 0; q < 6; q++) {
+            const int i = lane + 32 * q;
+            v[cs][2 + q] = (c < w && i < nr) ? col[r0 + i] : 0.0;
+        }
     }
-    for (int e = threadIdx.x; e < nr * kNB; e += blockDim.x) {
-        const int i = e % nr, c = e / nr;
-        ps.sT[c * kTld + kNB + i] = (c < w) ? S[(r0 + i) + (size_t)(j0 + c) * ld] : 0.0;
+#pragma unroll
+    for (int cs = 0; cs < 8; cs++) {
+        double* dst = ps.sT + (wp + 8 * cs) * kTld;
+        dst[lane] = v[cs][0];
+        dst[lane + 32] = v[cs][1];
+#pragma unroll
+        for (int q = 0; q < 6; q++) {
+            const int i = lane + 32 * q;
+            if (i < nr) dst[kNB + i] = v[cs][2 + q];
+        }
     }
 }
 
@@ -400,15 +427,16 @@ __global__ void __launch_bounds__(256) k_chol_small(DevFilter* Fs) {
         PH(1);
         // inverse of the diagonal block (all warps), then store the panel and run the trailing update on DMMA tiles
         smem_trinv64(ps);
+        PH(4);
         {
-            const int t = threadIdx.x, nt = blockDim.x;
-            for (int e = t; e < kNB * kNB; e += nt) {
-                const int i = e % kNB, c = e / kNB;
-                if (i < w && c < w) S[(j0 + i) + (size_t)(j0 + c) * ld] = ps.sT[c * kTld + i];
-            }
-            for (int e = t; e < rem * kNB; e += nt) {
-                const int i = e % rem, c = e / rem;
-                S[(j0 + kNB + i) + (size_t)(j0 + c) * ld] = ps.sT[c * kTld + kNB + i];
+            {
+                const int ln = threadIdx.x & 31, wp = threadIdx.x >> 5;
+                for (int c = wp; c < w; c += 8) {  // warp per column, lanes down the rows: coalesced, no divisions
+                    double* col = S + (size_t)(j0 + c) * ld + j0;
+                    const double* src = ps.sT + c * kTld;
+                    for (int i = ln; i < w; i += 32) col[i] = src[i];
+                    for (int i = ln; i < rem; i += 32) col[kNB + i] = src[kNB + i];
+                }
             }
             // trailing update S[a, b] -= sum_c X[a, c] X[b, c] (lower triangle), warp tiles 16 x 32 straight from the k-major panel
             const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;

@@ -145,7 +145,38 @@ def convert(out):
     out["convert_types"] = f["types"]
     out["convert_x"] = xo
     out["convert_P"] = Po
-    print("convert: types", f["types"], "n", xo.size, "draws", r.draws_consumed())
+    # ... then a whole frame on the mixed map (one cartesian feature among inverse-depth ones: 3- and 6-wide state blocks): prediction,
+    # h / H / S for both kinds (calculate_Hi_cartesian, src/Tracking.cpp:71-112), RANSAC and both updates with matches on the
+    # inverse-depth features only (a matched cartesian feature makes the reference itself fail)
+    r.ekf_prediction()
+    r.predict_only()
+    f1 = r.features()
+    icm = ic & f1["has_h"] & (f["types"] == 0)
+    r.set_matches(z, icm)
+    dr = R.make_draws(np.random.default_rng(78), 1000)
+    r.set_draws(dr)
+    r.ransac_hypotheses()
+    used = r.draws_consumed()
+    f2 = r.features()
+    r.update_li()
+    r.rescue_hi()
+    f3 = r.features()
+    r.update_hi()
+    x2, P2 = r.get_state()
+    out["convert_z"] = z
+    out["convert_ic"] = icm
+    out["convert_has_h"] = f1["has_h"]
+    out["convert_h"] = f1["h"]
+    out["convert_S"] = f1["S"]
+    out["convert_H3"] = r.H_dense(3)
+    out["convert_draws_ransac"] = dr
+    out["convert_used_ransac"] = np.array(used)
+    out["convert_li"] = f2["li"]
+    out["convert_hi"] = f3["hi"]
+    out["convert_x_frame"] = x2
+    out["convert_P_frame"] = P2
+    print("convert: types", f["types"], "n", xo.size, "draws", int(out["convert_used"]), "| frame: has_h", f1["has_h"].sum(), "ic", icm.sum(), "li", f2["li"].sum(), "hi",
+          f3["hi"].sum(), "hyp", used)
 
 
 if __name__ == "__main__":

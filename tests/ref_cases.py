@@ -244,3 +244,22 @@ def run_convert(make_engine):
     xo, Po = e.state()
     H.assert_x_close(xo, g["convert_x"], what=f"{e.name}: x after conversion")
     H.assert_P_close(Po, g["convert_P"], what=f"{e.name}: P after conversion")
+    # a whole frame on the mixed map (3- and 6-wide state blocks; calculate_Hi_cartesian, src/Tracking.cpp:71-112)
+    e.ekf_prediction()
+    e.search(None)
+    f = e.features()
+    assert np.array_equal(f["has_h"], g["convert_has_h"])
+    hh = g["convert_has_h"]
+    np.testing.assert_allclose(f["h"][hh], g["convert_h"][hh], rtol=1e-12, atol=1e-10)
+    np.testing.assert_allclose(f["S"][hh], g["convert_S"][hh], rtol=1e-9, atol=1e-12)
+    e.set_matches(g["convert_z"], g["convert_ic"])
+    rc, run = e.ransac(u01_of(g["convert_draws_ransac"]))
+    assert rc == 0 and run == int(g["convert_used_ransac"]), (rc, run)
+    assert np.array_equal(e.features()["li"], g["convert_li"])
+    e.update_li()
+    e.rescue_hi()
+    assert np.array_equal(e.features()["hi"], g["convert_hi"])
+    e.update_hi()
+    x2, P2 = e.state()
+    H.assert_x_close(x2, g["convert_x_frame"], what=f"{e.name}: x after the frame on the mixed map")
+    H.assert_P_close(P2, g["convert_P_frame"], what=f"{e.name}: P after the frame on the mixed map")
