@@ -152,6 +152,75 @@ __global__ void __launch_bounds__(256) k_upd_S(DevFilter* Fs) {
     S[(2 * ti + 1) + (size_t)(2 * tj + 1) * ld] = s11;
 }
 
+// ---- U3d: S = H P H^T + I straight from P, for the latency path of a single small filter: with no dependency on W it lets
+//           W = P H^T (side stream) run concurrently with S and its single-CTA Cholesky factorisation.  Warp per (ti >= tj)
+//           measurement pair; lane l < 7 + fs_i owns one of the state rows H_i touches, forms (P H_j^T)[row, 0..1] in the same
+//           order as k_upd_W, multiplies by H_i's two coefficients for that row, and a fixed shuffle tree adds the lanes.
+__global__ void __launch_bounds__(256) k_upd_S_direct(DevFilter* Fs) {
+    DevFilter& F = Fs[blockIdx.z];
+    const int m = F.ctl[CTL_M];
+    const int lane = threadIdx.x & 31;
+    const int pr = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (pr >= m * (m + 1) / 2) return;
+    int ti = (int)((sqrt(8.0 * (double)pr + 1.0) - 1.0) * 0.5);  // pr = ti (ti + 1) / 2 + tj, tj <= ti
+    while (ti * (ti + 1) / 2 > pr) ti--;
+    while ((ti + 1) * (ti + 2) / 2 <= pr) ti++;
+    const int tj = pr - ti * (ti + 1) / 2;
+    const int fi = F.upd_list[ti], fj = F.upd_list[tj];
+    const int offi = F.foff[fi], fsi = F.ftype[fi] == 0 ? 6 : 3;
+    const int offj = F.foff[fj], fsj = F.ftype[fj] == 0 ? 6 : 3;
+    double p00 = 0, p01 = 0, p10 = 0, p11 = 0;
+    if (lane < 7 + fsi) {
+        const int ld = F.ldp;
+        const double* prow = F.P + (lane < 7 ? lane : offi + lane - 7);
+        const double* Hcj = F.Hc + 14 * fj;
+        const double* Hfj = F.Hf + 12 * fj;
+        double pc[7], pf[6];
+#pragma unroll
+        for (int c = 0; c < 7; c++) pc[c] = prow[(size_t)c * ld];
+#pragma unroll
+        for (int c = 0; c < 6; c++) pf[c] = c < fsj ? prow[(size_t)(offj + c) * ld] : 0.0;
+        double w0 = 0, w1 = 0;
+#pragma unroll
+        for (int c = 0; c < 7; c++) {
+            w0 += pc[c] * Hcj[c];
+            w1 += pc[c] * Hcj[7 + c];
+        }
+#pragma unroll
+        for (int c = 0; c < 6; c++)
+            if (c < fsj) {
+                w0 += pf[c] * Hfj[c];
+                w1 += pf[c] * Hfj[6 + c];
+            }
+        const double h0 = lane < 7 ? F.Hc[14 * fi + lane] : F.Hf[12 * fi + lane - 7];
+        const double h1 = lane < 7 ? F.Hc[14 * fi + 7 + lane] : F.Hf[12 * fi + 6 + lane - 7];
+        p00 = h0 * w0;
+        p01 = h0 * w1;
+        p10 = h1 * w0;
+        p11 = h1 * w1;
+    }
+#pragma unroll
+    for (int o = 8; o >= 1; o >>= 1) {
+        p00 += __shfl_down_sync(0xffffffffu, p00, o);
+        p01 += __shfl_down_sync(0xffffffffu, p01, o);
+        p10 += __shfl_down_sync(0xffffffffu, p10, o);
+        p11 += __shfl_down_sync(0xffffffffu, p11, o);
+    }
+    if (lane == 0) {
+        if (ti == tj) {
+            p00 += 1.0;  // R = I (src/ExtendKF.cpp:594,676)
+            p11 += 1.0;
+            p01 = p10;   // keep the diagonal block exactly symmetric: use the lower entry for both
+        }
+        double* S = F.Sm;
+        const int lds = F.lds;
+        S[(2 * ti) + (size_t)(2 * tj) * lds] = p00;
+        S[(2 * ti + 1) + (size_t)(2 * tj) * lds] = p10;
+        S[(2 * ti) + (size_t)(2 * tj + 1) * lds] = p01;
+        S[(2 * ti + 1) + (size_t)(2 * tj + 1) * lds] = p11;
+    }
+}
+
 // ---- async-copy / DMMA primitives ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem);

@@ -77,6 +77,9 @@ struct rslam_filter {
     // CUDA-graph replay of the per-frame launch sequence
     bool graph_enabled = true;
     bool capturing = false;
+    // side stream for work that is independent of the critical path of a single small filter (W = P H^T beside S + Cholesky)
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaGraphExec_t graph_exec = nullptr;
     long long graph_key = -1;
     long long graph_nodes = 0;
@@ -165,18 +168,19 @@ cudaEvent_t prof_event(rslam_filter* f) {
 }
 
 #define LAUNCH(f, kern, grid, block, smem, ...) LAUNCH_N(f, #kern, kern, grid, block, smem, __VA_ARGS__)
-#define LAUNCH_N(f, name, kern, grid, block, smem, ...)                       \
+#define LAUNCH_N(f, name, kern, grid, block, smem, ...) LAUNCH_ON(f, (f)->stream, name, kern, grid, block, smem, __VA_ARGS__)
+#define LAUNCH_ON(f, strm, name, kern, grid, block, smem, ...)                \
     do {                                                                      \
         const bool prof__ = (f)->prof && !(f)->capturing;                     \
         cudaEvent_t e0__ = nullptr, e1__ = nullptr;                           \
         if (prof__) {                                                         \
             e0__ = prof_event(f);                                             \
             e1__ = prof_event(f);                                             \
-            cudaEventRecord(e0__, (f)->stream);                               \
+            cudaEventRecord(e0__, (strm));                                    \
         }                                                                     \
-        kern<<<grid, block, smem, (f)->stream>>>(__VA_ARGS__);                \
+        kern<<<grid, block, smem, (strm)>>>(__VA_ARGS__);                     \
         if (prof__) {                                                         \
-            cudaEventRecord(e1__, (f)->stream);                               \
+            cudaEventRecord(e1__, (strm));                                    \
             (f)->prof_recs.push_back(rslam_filter::ProfRec{name, e0__, e1__}); \
         }                                                                     \
         (f)->launches++;                                                      \
@@ -196,11 +200,28 @@ int run_update(rslam_filter* f, int which, bool gathered = false) {
     const int kmax = 2 * N;
     const int nsteps = cdiv(kmax, kNB);
     if (!gathered) LAUNCH(f, k_upd_gather, dim3(1, B), 256, 0, f->dF, which);
-    LAUNCH(f, k_upd_W, dim3(cdiv(n, 256), cdiv(N, kWChunk), B), 256, 0, f->dF);
-    LAUNCH(f, k_upd_S, dim3(cdiv(N, 16), cdiv(N, 16), B), 256, 0, f->dF);
-    if (kmax <= kCholSmallMaxK) {
+    if (kmax <= kCholSmallMaxK && B == 1) {
+        // latency path of one small filter: S comes straight from P, so W = P H^T (needed only by the TRSM) runs on the side stream
+        // next to S and its Cholesky factorisation (a fork / join that the frame graph captures as parallel branches).  Under
+        // per-launch profiling everything stays on the one stream so that the events bracket single kernels.
+        const bool fork = !(f->prof && !f->capturing);
+        cudaStream_t ws = fork ? f->side : f->stream;
+        if (fork) {
+            CK(cudaEventRecord(f->ev_fork, f->stream));
+            CK(cudaStreamWaitEvent(f->side, f->ev_fork, 0));
+        }
+        LAUNCH_ON(f, ws, "k_upd_W", k_upd_W, dim3(cdiv(n, 256), cdiv(N, kWChunk), B), 256, 0, f->dF);
+        if (fork) CK(cudaEventRecord(f->ev_join, f->side));
+        LAUNCH_N(f, "k_upd_S", k_upd_S_direct, dim3(cdiv(N * (N + 1) / 2, 8), 1, B), 256, 0, f->dF);
+        LAUNCH(f, k_chol_small, dim3(1, B), 256, kCholSmallSmemBytes, f->dF);
+        if (fork) CK(cudaStreamWaitEvent(f->stream, f->ev_join, 0));
+    } else if (kmax <= kCholSmallMaxK) {
+        LAUNCH(f, k_upd_W, dim3(cdiv(n, 256), cdiv(N, kWChunk), B), 256, 0, f->dF);
+        LAUNCH(f, k_upd_S, dim3(cdiv(N, 16), cdiv(N, 16), B), 256, 0, f->dF);
         LAUNCH(f, k_chol_small, dim3(1, B), 256, kCholSmallSmemBytes, f->dF);
     } else {
+        LAUNCH(f, k_upd_W, dim3(cdiv(n, 256), cdiv(N, kWChunk), B), 256, 0, f->dF);
+        LAUNCH(f, k_upd_S, dim3(cdiv(N, 16), cdiv(N, 16), B), 256, 0, f->dF);
         for (int s = 0; s < nsteps; s++) {
             LAUNCH(f, k_chol_panel, dim3(nsteps - s, B), 256, kPanelSmemBytes, f->dF, s);
             const int o = kNB * (s + 1), oend = kNB * kOB * (s / kOB + 1);
@@ -307,6 +328,9 @@ int rslam_create(const rslam_camera* cam, const rslam_params* par, int max_featu
     f->pard = ParDev{f->par.std_z, f->par.chi2_095_2, f->par.corr_threshold, f->par.p_spurious_free, f->par.max_ellipse_eig,
                      (f->par.std_a * 1.0) * (f->par.std_a * 1.0), (f->par.std_alpha * 1.0) * (f->par.std_alpha * 1.0), f->par.n_hyp_initial, f->par.quirks};
     CK(cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&f->side, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&f->ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&f->ev_join, cudaEventDisableTiming));
     CK(cudaFuncSetAttribute(k_gemm_dmma<128, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<128, 64>::kSmemBytes));
     CK(cudaFuncSetAttribute(k_gemm_dmma<64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<64, 64>::kSmemBytes));
     CK(cudaFuncSetAttribute(k_trsm_ll<48, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TrsmCfg<48, 2>::kSmemBytes));
@@ -419,6 +443,9 @@ int rslam_destroy(rslam_filter* f) {
     if (f->d_u01) cudaFree(f->d_u01);
     if (f->d_hyp_idx) cudaFree(f->d_hyp_idx);
     if (f->d_sup_h) cudaFree(f->d_sup_h);
+    if (f->ev_fork) cudaEventDestroy(f->ev_fork);
+    if (f->ev_join) cudaEventDestroy(f->ev_join);
+    if (f->side) cudaStreamDestroy(f->side);
     if (f->stream) cudaStreamDestroy(f->stream);
     delete f;
     return RSLAM_OK;

@@ -144,10 +144,20 @@ def test_batch_matches_single_and_graph_matches_stream():
     for k in range(3):
         ref.frame(seq.images[k][None], seq.u01[k][None])
         bat.frame(np.repeat(seq.images[k][None], 3, 0), np.repeat(seq.u01[k][None], 3, 0))
+    gra = H.gpu_from(scene, scene.x0, scene.P0, prior=False)  # single filter again, frame replayed as a CUDA graph
+    for k in range(3):
+        gra.frame(seq.images[k][None], seq.u01[k][None])
     xr, Pr = ref.download_state()
+    xg, Pg = gra.download_state()
+    # same kernels, same order (the graph captures the side-stream fork / join of W beside S + Cholesky as parallel branches): bitwise
+    assert np.array_equal(xr, xg) and np.array_equal(Pr, Pg)
+    x0, P0 = bat.download_state(b=0)
     for b in range(3):
         xb, Pb = bat.download_state(b=b)
-        assert np.array_equal(xr, xb) and np.array_equal(Pr, Pb), b  # same kernels, same order: bitwise
+        assert np.array_equal(x0, xb) and np.array_equal(P0, Pb), b  # members of a batch: bitwise
+        # a batch forms S = H W from the stored W, a single filter straight from P (different summation order): 1e-9 bar
+        H.assert_x_close(xb, xr, what=f"batch member {b} vs single")
+        H.assert_P_close(Pb, Pr, what=f"batch member {b} vs single")
         assert (bat.features(b)["hi"] == ref.features()["hi"]).all()
 
 
