@@ -470,12 +470,20 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
+    # stdout carries exactly ONE line, the JSON: everything libraries print while we run (NCCL's version banner ...) goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(json_fd, (json.dumps(obj) + "\n").encode())
+
     if args.impl == "reference":
         rank = int(os.environ.get("RANK", "0"))
         world = int(os.environ.get("WORLD_SIZE", "1"))
         line = bench_reference(args, world, rank)
         if line is not None:
-            print(json.dumps(line))
+            emit(line)
         return
     world, rank, local = dist_setup(args.gpus)
     line = bench_c2(args, world, rank, local)
@@ -487,7 +495,7 @@ def main():
         except Exception as e:  # extras must never cost the main line
             line["workloads"] = dict(error=repr(e))
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         import torch.distributed as dist
 
