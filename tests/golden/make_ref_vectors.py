@@ -22,7 +22,8 @@ sys.path.insert(0, ROOT)
 from oracle import ref_py as R  # noqa: E402
 from tests import helpers as H  # noqa: E402
 
-BUNDLED_FRAMES = 6
+BUNDLED_FRAMES = 9          # frames 7 and 8 run Map::map_management's delete pass (12 and 8 deletions, run-ahead index, src/Map.cpp:19-32)
+BUNDLED_FULL_P = 6          # full covariance stored for the first frames, diag + 4 fixed projections P v afterwards (file size)
 Q1_CASES = [(20, 3, 0.2), (16, 8, 0.45)]  # (N, seed, outlier fraction)
 
 
@@ -36,6 +37,7 @@ def bundled(out):
     for k in range(BUNDLED_FRAMES):
         dm = R.make_draws(rng, 200)
         dr = R.make_draws(rng, 1000)
+        n_before = r.N
         r.set_draws(dm)
         r.map_management(frames[k], k + 1)
         used_m = r.draws_consumed()
@@ -58,6 +60,7 @@ def bundled(out):
         out[pre + "draws_map"] = dm
         out[pre + "draws_ransac"] = dr
         out[pre + "used"] = np.array([used_m, used_r])
+        out[pre + "N_before_after"] = np.array([n_before, r.N])
         out[pre + "x_map"] = x_map
         out[pre + "Pdiag_map"] = np.diag(P_map).copy()
         out[pre + "types"] = f_map["types"]
@@ -70,7 +73,12 @@ def bundled(out):
         out[pre + "li"] = f_r["li"]
         out[pre + "hi"] = f_h["hi"]
         out[pre + "x"] = x
-        out[pre + "P"] = P
+        if k < BUNDLED_FULL_P:
+            out[pre + "P"] = P
+        else:
+            V = np.random.default_rng(1000 + k).standard_normal((P.shape[0], 4))
+            out[pre + "Pdiag"] = np.diag(P).copy()
+            out[pre + "PV"] = P @ V
         print(f"bundled frame {k}: N={r.N} ic={f_s['ic'].sum()} li={f_r['li'].sum()} hi={f_h['hi'].sum()} draws {used_m}+{used_r}")
     out["bundled_frames"] = np.array(BUNDLED_FRAMES)
 

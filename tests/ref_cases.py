@@ -169,6 +169,7 @@ def run_bundled(make_engine, frames=None):
         rc, attempts = e.map_management(imgs[k], k + 1, 25, u01_of(g[pre + "draws_map"]))
         assert rc == 0 and 2 * attempts == int(g[pre + "used"][0]), (k, rc, attempts)
         x, P = e.state()
+        assert (x.size - 13) // 6 == int(g[pre + "N_before_after"][1])
         assert x.shape == g[pre + "x_map"].shape, (k, x.shape)
         assert list(e.types()) == list(g[pre + "types"])
         assert np.array_equal(e.init_uv(), g[pre + "init_uv"]), f"frame {k}: FAST picked different corners"
@@ -193,7 +194,13 @@ def run_bundled(make_engine, frames=None):
         e.update_hi()
         x, P = e.state()
         H.assert_x_close(x, g[pre + "x"], what=f"{e.name}: x after frame {k}")
-        H.assert_P_close(P, g[pre + "P"], what=f"{e.name}: P after frame {k}")
+        if pre + "P" in g.files:
+            H.assert_P_close(P, g[pre + "P"], what=f"{e.name}: P after frame {k}")
+        else:  # later frames store diag(P) and four fixed projections P v instead of the whole matrix
+            V = np.random.default_rng(1000 + k).standard_normal((P.shape[0], 4))
+            H.assert_x_close(np.diag(P), g[pre + "Pdiag"], what=f"{e.name}: diag P after frame {k}")
+            PV, PVg = P @ V, g[pre + "PV"]
+            assert np.abs(PV - PVg).max() <= 1e-9 * np.abs(PVg).max() + 1e-12 * np.abs(np.diag(P)).max(), f"{e.name}: P v after frame {k}"
     return nf
 
 

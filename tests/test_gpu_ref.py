@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 def test_cuda_reproduces_reference_on_bundled_sequence():
     """whole System::TrackRunning loop (map management incl. FAST initialisation and the run-ahead delete, prediction, patch warp,
     ZNCC search, 1-point RANSAC, li / hi updates) over frames of the reference's bundled sequence"""
-    assert RC.run_bundled(RC.GpuEngine) == 6
+    assert RC.run_bundled(RC.GpuEngine) == 9
 
 
 def test_cuda_reproduces_reference_ransac_and_updates():

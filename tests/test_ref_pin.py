@@ -20,7 +20,7 @@ needs_ref = pytest.mark.skipif(not R.available(), reason="oracle/_ref/libref.so 
 
 
 def test_oracle_reproduces_reference_on_bundled_sequence():
-    assert RC.run_bundled(RC.OracleEngine) == 6
+    assert RC.run_bundled(RC.OracleEngine) == 9
 
 
 def test_oracle_sparse_mode_reproduces_reference_on_bundled_sequence():
