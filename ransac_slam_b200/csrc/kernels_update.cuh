@@ -274,19 +274,28 @@ __device__ __forceinline__ PanelSmem panel_carve(double* base) {
 // lanes 0..15 hold row `lane` of a 16 x 16 SPD block (lower triangle in a[0..lane]); on exit a[] is row `lane` of L and rd[j] =
 // 1 / l_jj on every lane.  Upper entries are garbage and must be ignored by the caller.
 __device__ __forceinline__ void warp_potrf16(double (&a)[kSB], double (&rd)[kSB]) {
+    // Per column the serial chain is  pivot shuffle -> 1 / d -> one FMA:  the column entries a_cj are shuffled UNSCALED together with
+    // the pivot, the products a_ij a_cj are formed while the reciprocal is in flight, and the update is a_ic -= (a_ij a_cj) (1 / d).
+    // The reciprocal is a MUFU.RCP64H seed + two Newton steps (~50 cycles); rsqrt(d) (77 cycles), needed only to scale the finished
+    // column and for rd, runs beside the chain.  (Scaling first and shuffling l_ij, as before, put shuffle -> rsqrt -> multiply ->
+    // shuffle -> FMA = ~143 cycles on the chain; this is ~85.)
     const unsigned fm = 0xffffffffu;
 #pragma unroll
     for (int j = 0; j < kSB; j++) {
-        const double d = __shfl_sync(fm, a[j], j);
+        const double aj = a[j];
+        const double d = __shfl_sync(fm, aj, j);
+        double t[kSB];
+#pragma unroll
+        for (int c = j + 1; c < kSB; c++) t[c] = aj * __shfl_sync(fm, aj, c);
+        double q;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(q) : "d"(d));
+        q = q * fma(-d, q, 2.0);
+        q = q * fma(-d, q, 2.0);
+#pragma unroll
+        for (int c = j + 1; c < kSB; c++) a[c] = fma(-t[c], q, a[c]);
         const double r = rsqrt(d);
         rd[j] = r;
-        const double lj = a[j] * r;  // l_ij (lane j: d * rsqrt(d) = sqrt(d))
-        a[j] = lj;
-#pragma unroll
-        for (int c = j + 1; c < kSB; c++) {
-            const double lc = __shfl_sync(fm, lj, c);
-            a[c] = fma(-lj, lc, a[c]);
-        }
+        a[j] = aj * r;  // l_ij (lane j: d * rsqrt(d) = sqrt(d))
     }
 }
 
