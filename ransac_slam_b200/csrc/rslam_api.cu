@@ -79,6 +79,13 @@ struct rslam_filter {
     bool capturing = false;
     // side stream for work that is independent of the critical path of a single small filter (W = P H^T beside S + Cholesky)
     cudaStream_t side = nullptr;
+    // what k_set_inputs last wrote into the device descriptors (rslam_frame skips the launch when unchanged)
+    const unsigned char* bound_img = nullptr;
+    long long bound_iper = -1;
+    int bound_geom[3] = {-1, -1, -1};
+    const double* bound_u01 = nullptr;
+    int bound_nu = -1;
+    bool bound_has_img = false;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaGraphExec_t graph_exec = nullptr;
     long long graph_key = -1;
@@ -111,6 +118,8 @@ int push_descr(rslam_filter* f) {
     CK(cudaMemcpyAsync(f->dF, f->hF.data(), sizeof(DevFilter) * f->B, cudaMemcpyHostToDevice, f->stream));
     // hF is pageable: the copy is staged before the call returns, so later host edits are safe
     f->descr_dirty = false;
+    f->bound_iper = -1;  // the pushed descriptors carry their own image / u01 bindings: rslam_frame must re-bind
+    f->bound_nu = -1;
     return 0;
 }
 
@@ -653,6 +662,8 @@ static int set_images(rslam_filter* f, int b_first, int count, const uint8_t* gr
     if (count == f->B || share) {
         const unsigned char* b0 = dev ? gray : f->d_images;
         LAUNCH(f, k_set_inputs, cdiv(f->B, 128), 128, 0, f->dF, f->B, b0, (long long)(share ? 0 : per), rows, cols, stride, 1, (const double*)nullptr, 0, 0);
+    f->bound_iper = -1;  // bound outside rslam_frame: its cache is stale
+    f->bound_nu = -1;
         for (int b = 0; b < f->B; b++) {
             f->hF[b].image = b0 + (share ? 0 : per * b);
             f->hF[b].img_rows = rows;
@@ -718,6 +729,8 @@ static int set_u01(rslam_filter* f, const double* u01, int n_u01) {
         base = f->d_u01;
     }
     LAUNCH(f, k_set_inputs, cdiv(f->B, 128), 128, 0, f->dF, f->B, (const unsigned char*)nullptr, 0LL, 0, 0, 0, 0, base, n_u01, 1);
+    f->bound_iper = -1;  // bound outside rslam_frame: its cache is stale
+    f->bound_nu = -1;
     for (int b = 0; b < f->B; b++) {
         f->hF[b].u01 = base + (size_t)n_u01 * b;
         f->hF[b].n_u01 = n_u01;
@@ -832,7 +845,19 @@ int rslam_frame(rslam_filter* f, const uint8_t* images, int rows, int cols, int 
     const double* ubase = nullptr;
     if ((rc = resolve_u01(f, u01, n_u01, &ubase))) return rc;
     if ((rc = ensure_update_ws(f))) return rc;
-    LAUNCH(f, k_set_inputs, cdiv(f->B, 128), 128, 0, f->dF, f->B, ibase, iper, rows, cols, stride, images ? 1 : 0, ubase, n_u01, 1);
+    // bind the inputs in the device descriptors -- skipped when nothing changed (host inputs always land in the same staging buffers)
+    if (f->descr_dirty || f->bound_img != ibase || f->bound_iper != iper || f->bound_geom[0] != rows || f->bound_geom[1] != cols || f->bound_geom[2] != stride ||
+        f->bound_u01 != ubase || f->bound_nu != n_u01 || (images != nullptr) != f->bound_has_img) {
+        LAUNCH(f, k_set_inputs, cdiv(f->B, 128), 128, 0, f->dF, f->B, ibase, iper, rows, cols, stride, images ? 1 : 0, ubase, n_u01, 1);
+        f->bound_img = ibase;
+        f->bound_iper = iper;
+        f->bound_geom[0] = rows;
+        f->bound_geom[1] = cols;
+        f->bound_geom[2] = stride;
+        f->bound_u01 = ubase;
+        f->bound_nu = n_u01;
+        f->bound_has_img = images != nullptr;
+    }
     for (int b = 0; b < f->B; b++) {
         if (images) {
             f->hF[b].image = ibase + iper * b;
