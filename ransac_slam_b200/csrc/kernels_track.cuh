@@ -177,14 +177,28 @@ __device__ __forceinline__ void mul_2x2_2x3(const double* a1, const double* a2, 
         for (int j = 0; j < 3; j++) o[i * 3 + j] = a1[i * 2] * a2[j] + a1[i * 2 + 1] * a2[3 + j];
 }
 
-__global__ void __launch_bounds__(128) k_predict(DevFilter* Fs, CamDev cam, ParDev par, int mode) {
+__device__ __forceinline__ void gather_inliers(DevFilter& F, int which, int* s_scan, int* s_base);  // kernels_update.cuh
+__device__ __forceinline__ void predict_feature(DevFilter& F, const CamDev& cam, const ParDev& par, int mode, int i, const double* sPcc);
+
+// fuse_gather (mode 1, single-CTA grids only): the ordered high-innovation inlier list + innovation (gather_inliers, the first step
+// of ekf_update_hi_inliers) is built by the same CTA right behind the gate, saving a dependent launch on the single-filter path.
+__global__ void __launch_bounds__(128) k_predict(DevFilter* Fs, CamDev cam, ParDev par, int mode, int fuse_gather) {
     DevFilter& F = Fs[blockIdx.y];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     __shared__ double sPcc[49];
+    __shared__ int s_scan[32], s_base;
     const int ld = F.ldp;
     if (threadIdx.x < 49) sPcc[threadIdx.x] = F.P[(threadIdx.x / 7) + (size_t)(threadIdx.x % 7) * ld];
     __syncthreads();
-    if (i >= F.N) return;
+    if (i < F.N) predict_feature(F, cam, par, mode, i, sPcc);
+    if (fuse_gather) {
+        __syncthreads();  // the hi flags of this CTA's features are written
+        gather_inliers(F, 1, s_scan, &s_base);
+    }
+}
+
+__device__ __forceinline__ void predict_feature(DevFilter& F, const CamDev& cam, const ParDev& par, int mode, int i, const double* sPcc) {
+    const int ld = F.ldp;
     const double* x = mode == 0 ? F.x_km1 : F.x_kk;
     const int off = F.foff[i];
     const int type = F.ftype[i];

@@ -20,32 +20,35 @@ namespace rslam {
 
 // ---- U1: ordered list of the inlier set + innovation ----------------------------------------------------------------
 // which = 0: low_innovation_inlier, prior state x_k_km1 (:559-596); which = 1: high_innovation_inlier, state x_k_k (:640-678).
-// CTA-collective (256 threads).  With an empty low-innovation set the reference copies the prior (src/ExtendKF.cpp:635-638).
-__device__ __forceinline__ void gather_inliers(DevFilter& F, int which, int* s_scan /*[256]*/, int* s_base) {
+// CTA-collective, any block size that is a multiple of 32 (every thread of the CTA must call it).  Flags are 0 / 1, so the ordered
+// positions come from one ballot per warp + the warp totals (two barriers per chunk instead of a 16-barrier shared-memory scan).
+// With an empty low-innovation set the reference copies the prior (src/ExtendKF.cpp:635-638).
+__device__ __forceinline__ void gather_inliers(DevFilter& F, int which, int* s_scan /*[>= 32]*/, int* s_base) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     if (threadIdx.x == 0) *s_base = 0;
     __syncthreads();
     const unsigned char* flag = which == 0 ? F.li : F.hi;
-    for (int base = 0; base < F.N; base += 256) {
+    for (int base = 0; base < F.N; base += blockDim.x) {
         const int i = base + threadIdx.x;
-        const int a = (i < F.N && flag[i]) ? 1 : 0;
-        s_scan[threadIdx.x] = a;
+        const bool a = i < F.N && flag[i];
+        const unsigned bal = __ballot_sync(0xffffffffu, a);
+        if (lane == 0) s_scan[wid] = __popc(bal);
         __syncthreads();
-        for (int o = 1; o < 256; o <<= 1) {
-            int v = 0;
-            if (threadIdx.x >= o) v = s_scan[threadIdx.x - o];
-            __syncthreads();
-            s_scan[threadIdx.x] += v;
-            __syncthreads();
-        }
+        int t = *s_base;
+        for (int w2 = 0; w2 < wid; w2++) t += s_scan[w2];
         if (a) {
-            const int t = *s_base + s_scan[threadIdx.x] - 1;
+            t += __popc(bal & ((1u << lane) - 1u));
             F.upd_list[t] = i;
             // innovation z - h rides along as row n of W
             F.W[F.n + (size_t)(2 * t) * F.ldw] = F.z[2 * i] - F.h[2 * i];
             F.W[F.n + (size_t)(2 * t + 1) * F.ldw] = F.z[2 * i + 1] - F.h[2 * i + 1];
         }
         __syncthreads();
-        if (threadIdx.x == 255) *s_base += s_scan[255];
+        if (threadIdx.x == 0) {
+            int tot = 0;
+            for (int w2 = 0; w2 < nw; w2++) tot += s_scan[w2];
+            *s_base += tot;
+        }
         __syncthreads();
     }
     const int m = *s_base;

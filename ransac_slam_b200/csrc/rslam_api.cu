@@ -78,6 +78,7 @@ struct rslam_filter {
     bool graph_enabled = true;
     bool capturing = false;
     // side stream for work that is independent of the critical path of a single small filter (W = P H^T beside S + Cholesky)
+    bool hi_gathered = false;  // the last rslam_rescue_hi also built the hi inlier list (single-CTA grids)
     cudaStream_t side = nullptr;
     // what k_set_inputs last wrote into the device descriptors (rslam_frame skips the launch when unchanged)
     const unsigned char* bound_img = nullptr;
@@ -709,7 +710,7 @@ int rslam_search_ic_matches(rslam_filter* f) {
     if (!f) return fail(RSLAM_ERR_INVALID, "null handle");
     CK(cudaSetDevice(f->device));
     if (f->hN == 0) return RSLAM_OK;
-    LAUNCH(f, k_predict, dim3(cdiv(f->hN, 128), f->B), 128, 0, f->dF, f->camd, f->pard, 0);
+    LAUNCH(f, k_predict, dim3(cdiv(f->hN, 128), f->B), 128, 0, f->dF, f->camd, f->pard, 0, 0);
     if (f->warp_patches) LAUNCH(f, k_pred_patch, dim3(f->hN, f->B), 192, 0, f->dF, f->camd);
     if (f->have_image) LAUNCH(f, k_search, dim3(f->hN, f->B), kSearchThreads, 0, f->dF, f->camd, f->pard);
     return check_launch();
@@ -772,14 +773,23 @@ int rslam_rescue_hi(rslam_filter* f) {
     if (!f) return fail(RSLAM_ERR_INVALID, "null handle");
     CK(cudaSetDevice(f->device));
     if (f->hN == 0) return RSLAM_OK;
-    LAUNCH(f, k_predict, dim3(cdiv(f->hN, 128), f->B), 128, 0, f->dF, f->camd, f->pard, 1);
+    // one CTA per filter: the hi inlier list is gathered by the same launch (consumed by the next rslam_update_hi / run_update(f, 1))
+    const int fuse = cdiv(f->hN, 128) == 1 ? 1 : 0;
+    if (fuse) {
+        int rc = ensure_update_ws(f);  // gather_inliers writes the innovation into W
+        if (rc) return rc;
+    }
+    LAUNCH(f, k_predict, dim3(cdiv(f->hN, 128), f->B), 128, 0, f->dF, f->camd, f->pard, 1, fuse);
+    f->hi_gathered = fuse != 0;
     return check_launch();
 }
 
 int rslam_update_hi(rslam_filter* f) {
     if (!f) return fail(RSLAM_ERR_INVALID, "null handle");
     CK(cudaSetDevice(f->device));
-    return run_update(f, 1);
+    const bool gathered = f->hi_gathered;
+    f->hi_gathered = false;
+    return run_update(f, 1, gathered);
 }
 
 // resolve a host-or-device image batch to a device base pointer (copying host data into the handle's staging buffer)
@@ -827,7 +837,9 @@ static int run_frame_stages(rslam_filter* f, int flags) {
     if ((rc = run_ransac_core(f, true, true))) return rc;
     if ((rc = run_update(f, 0, true))) return rc;
     if ((rc = rslam_rescue_hi(f))) return rc;
-    if ((rc = run_update(f, 1))) return rc;
+    const bool gathered = f->hi_gathered;
+    f->hi_gathered = false;
+    if ((rc = run_update(f, 1, gathered))) return rc;
     return 0;
 }
 
