@@ -234,11 +234,22 @@ def bench_c5(args, world, rank, local):
     bytes_per_filter = upd * 2.0 * n * ldp * 8 + 8.0 * n * (7 * upd + 6 * (m_li + m_hi))
     pk = B.peaks()
     ach = Bl * bytes_per_filter / (ms / K * 1e-3) / 1e9
+    # the dominant kernel against ITS roofline: the covariance downdate P -= V V^T on the fp64 tensor pipe, (n + 1) n k flop per filter
+    # (lower triangle x 2 flop), against the cuBLAS fp64 GEMM rate measured live
+    top = next(iter(breakdown))
+    kroof = None
+    if top in ("k_syrk_rows", "k_gemm_dmma/syrk_P"):
+        flops = Bl * float(n + 1) * n * 2.0 * (m_li + m_hi)
+        tf = flops / (breakdown[top]["ms"] * 1e-3) / 1e12
+        fp64_peak = B.fp64_gemm_peak()
+        kroof = dict(kernel=top, bound="tensor", unit="TFLOP/s", achieved=tf, peak=fp64_peak, frac=tf / fp64_peak, share_of_step=breakdown[top]["share"],
+                     note="(n + 1) n k flop per filter / kernel time; peak = cuBLAS fp64 GEMM measured live")
     return dict(workload=f"C5: {Btot} independent 100-feature filters, batch split over ranks, no inter-GPU traffic", n_gpus=world, scaling="strong",
                 value=Btot * K / (ms * 1e-3), unit="filter-frames/s", ms_per_batch_frame=ms / K, filters_per_gpu=Bl,
                 frame_stats=dict(m_li=m_li, m_hi=m_hi), kernels=breakdown,
                 roofline=dict(bound="hbm", unit="GB/s", achieved=ach, peak=pk["hbm_gbs"], frac=ach / pk["hbm_gbs"], bytes_per_filter_frame=bytes_per_filter,
                               note="whole batch frame against HBM: P read+written once per non-empty update + the P columns gathered by W = P H^T; peak " + pk["source"]),
+                roofline_dominant_kernel=kroof,
                 note="working set (P 12.5 GB per 4096 filters) exceeds L2; no flush needed")
 
 
