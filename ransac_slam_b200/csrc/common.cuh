@@ -64,8 +64,9 @@ struct DevFilter {
     // RANSAC workspace
     int* ic_list;      // [N]  features with individually_compatible, feature order
     int* id_list;      // [N]  matched inverse-depth features, feature order (z_id columns)
+    int* sup_rows;     // [6 * round_up(N, 64)]  state rows of the support-scoring tiles, tile order (k_ransac_compact)
     int* id_pos;       // [N]  feature -> column in z_id (or -1)
-    double* hyp_ab;    // [N x 13]  a_p (7) = Hc_p^T g_p, b_p (6) = Hf_p^T g_p
+    double* hyp_ab;    // [N x 16]  a_p (7) = Hc_p^T g_p, b_p (6) = Hf_p^T g_p, [13] element offset of column y_p in P (as bits), [14] feature size
     double* hyp_xcam;  // [N x 7]   hypothesised r, q
     int* support;      // [N]
     unsigned* masks;   // [N x mwords]

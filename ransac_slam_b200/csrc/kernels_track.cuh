@@ -766,6 +766,7 @@ __global__ void __launch_bounds__(kSearchThreads) k_search(DevFilter* Fs, CamDev
 // (c) 1-point RANSAC (src/Tracking.cpp:352-539)
 // ---------------------------------------------------------------------------------------------------------------
 // c.1 ordered compaction of the individually-compatible list and the matched inverse-depth list (z_id columns, :361-397)
+constexpr int kSupTile = 64;  // == SJT of k_ransac_support
 __global__ void __launch_bounds__(256) k_ransac_compact(DevFilter* Fs) {
     DevFilter& F = Fs[blockIdx.y];
     __shared__ int s_scan[2][256];
@@ -825,9 +826,34 @@ __global__ void __launch_bounds__(256) k_ransac_compact(DevFilter* Fs) {
 
 // c.2 one thread per distinct 1-point hypothesis t (match p = ic_list[t]): partial EKF state update restricted to the camera
 //     (src/Tracking.cpp:419-422):  g = S_p^-1 (z_p - h_p);  a = Hc_p^T g;  b = Hf_p^T g;  x_i[0..6] = x[0..6] + P[0..6,nz] [a;b]
-__global__ void __launch_bounds__(128) k_ransac_hyp(DevFilter* Fs) {
+__global__ void __launch_bounds__(128) k_ransac_hyp(DevFilter* Fs, int q1) {
     DevFilter& F = Fs[blockIdx.y];
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    // state rows read by the support-scoring tiles, in tile order (one coalesced load per thread there instead of a dependent
+    // id_list -> foff chain): kSupTile matches per tile, 6 rows per match, spread over the whole grid.  Quirk Q1 (reference): 3
+    // position rows + rho per match, and the two "angle" rows are entries (2jj, 2jj+1) of the stacked POSITION vector of all matches.
+    {
+        const int m = F.ctl[CTL_MID];
+        const int ntile = (m + kSupTile - 1) / kSupTile;
+        for (int e = t; e < ntile * 6 * kSupTile; e += gridDim.x * blockDim.x) {
+            const int J0 = (e / (6 * kSupTile)) * kSupTile, k = e % (6 * kSupTile);
+            int row = -1;
+            if (q1) {
+                if (k < 4 * kSupTile) {
+                    const int jj = J0 + (k >> 2), c = k & 3;
+                    if (jj < m) row = F.foff[F.id_list[jj]] + (c < 3 ? c : 5);
+                } else {
+                    const int tt = 2 * J0 + (k - 4 * kSupTile);  // index into the stacked position vector ri_v
+                    const int feat = tt / 3;
+                    if (feat < m && (tt >> 1) < m) row = F.foff[F.id_list[feat]] + tt % 3;
+                }
+            } else {
+                const int jj = J0 + k / 6;
+                if (jj < m) row = F.foff[F.id_list[jj]] + k % 6;
+            }
+            F.sup_rows[e] = row;
+        }
+    }
     if (t >= F.ctl[CTL_NIC]) return;
     const int p = F.ic_list[t];
     const int off = F.foff[p];
@@ -842,8 +868,12 @@ __global__ void __launch_bounds__(128) k_ransac_hyp(DevFilter* Fs) {
 #pragma unroll
     for (int c = 0; c < 6; c++) ab[7 + c] = (c < fs) ? (F.Hf[12 * p + c] * g0 + F.Hf[12 * p + 6 + c] * g1) : 0.0;
 #pragma unroll
-    for (int c = 0; c < 13; c++) F.hyp_ab[(size_t)t * 13 + c] = ab[c];
+    for (int c = 0; c < 13; c++) F.hyp_ab[(size_t)t * 16 + c] = ab[c];
     const int ld = F.ldp;
+    // the scoring kernel's per-hypothesis constants ride in the same 128-byte record: element offset of column y_p in P, feature size
+    F.hyp_ab[(size_t)t * 16 + 13] = __longlong_as_double((long long)off * ld);
+    F.hyp_ab[(size_t)t * 16 + 14] = (double)fs;
+    F.hyp_ab[(size_t)t * 16 + 15] = 0.0;
     for (int r = 0; r < 7; r++) {
         double s = 0;
 #pragma unroll
@@ -870,18 +900,21 @@ __global__ void __launch_bounds__(128) k_ransac_hyp(DevFilter* Fs) {
 //     good), one shared reciprocal instead of four divisions, squared residual against the squared threshold.
 //     Quirk Q1 (reference): the angles of match jj are entries (2jj, 2jj+1) of the stacked POSITION vector of all matches; those
 //     two extra rows replace the (unused) theta / phi rows, so the row count per pair is 6 either way.
-constexpr int SJT = 64, SHB = 6;
+#ifdef RSLAM_SUP_CLOCKS
+__device__ unsigned long long g_sup_clk[8];
+#endif
+constexpr int SJT = kSupTile, SHB = 6;
 constexpr int SUP_THREADS = 192;
 constexpr int kSupSmemBytes = 0;
 static_assert(6 * SJT == 2 * SUP_THREADS && SHB * SJT == 2 * SUP_THREADS, "two rows and two pairs per thread");
-#ifndef RSLAM_SUP_PREFETCH
-#define RSLAM_SUP_PREFETCH 0
-#endif
 #ifndef RSLAM_SUP_MINB
 #define RSLAM_SUP_MINB 5
 #endif
 __global__ void __launch_bounds__(SUP_THREADS, RSLAM_SUP_MINB) k_ransac_support(DevFilter* Fs, CamDev cam, ParDev par, const int* t_indirect, int t_begin, int t_end,
                                                                   int t_lo, int t_hi, const int* used, int* sup_alt, unsigned long long* pair_counter) {
+#ifdef RSLAM_SUP_CLOCKS
+    const long long ck0 = clock64();
+#endif
     DevFilter& F = Fs[blockIdx.z];
     const int nIC = F.ctl[CTL_NIC];
     const int m = F.ctl[CTL_MID];
@@ -895,81 +928,49 @@ __global__ void __launch_bounds__(SUP_THREADS, RSLAM_SUP_MINB) k_ransac_support(
     const int tid = threadIdx.x;
     const bool q1 = (par.quirks & RSLAM_Q1_ANGLES_FROM_POSITIONS) != 0;
     const int ld = F.ldp;
-    if (tid < SHB) {
-        const int slot = t_begin + blockIdx.y * SHB + tid;
+    // Set-up is pure latency (no pair-unique bytes in flight), so its dependent loads are kept to two round trips: every thread that
+    // fetches a hypothesis constant resolves the hypothesis itself (slot -> t), and the 128-byte record written by k_ransac_hyp
+    // carries a_p, b_p, the column offset of y_p and the feature size together.
+    int my_t = -1;
+    if (tid < SHB * 16 + SHB * 7) {
+        const int pl = tid < SHB * 16 ? (tid >> 4) : (tid - SHB * 16) / 7;
+        const int slot = t_begin + blockIdx.y * SHB + pl;
         int t = -1;
         if (slot < t_end) {
             t = t_indirect ? t_indirect[slot] : slot;
             if (t < t_lo || t >= t_hi || t >= nIC) t = -1;
             if (t >= 0 && used && !used[t]) t = -1;
         }
-        s_t[tid] = t;
-        s_slot[tid] = slot;
-        if (t >= 0) {
-            const int p = F.ic_list[t];
-            s_colbase[tid] = (long long)F.foff[p] * ld;
-            s_fsp[tid] = F.ftype[p] == 0 ? 6 : 3;
+        my_t = t;
+        if (tid < SHB * 16) {
+            const int c = tid & 15;
+            const double v = t >= 0 ? F.hyp_ab[(size_t)t * 16 + c] : 0.0;
+            if (c < 13) s_ab[pl][c] = v;
+            if (c == 13) {
+                s_ab[pl][13] = 0.0;
+                s_colbase[pl] = t >= 0 ? __double_as_longlong(v) : 0;
+            }
+            if (c == 14) s_fsp[pl] = t >= 0 ? (int)v : 0;
+            if (c == 15) {
+                s_t[pl] = t;
+                s_slot[pl] = slot;
+            }
         } else {
-            s_colbase[tid] = 0;
-            s_fsp[tid] = 0;
+            const int c = (tid - SHB * 16) % 7;
+            s_xc[pl][c] = t >= 0 ? F.hyp_xcam[(size_t)t * 7 + c] : 0.0;
         }
     }
-    // the two state rows this thread owns (independent of the hypotheses: their dependent index loads overlap the ones above)
+    // the two state rows this thread owns, from the table k_ransac_compact laid out in tile order
     int rows[2];
 #pragma unroll
-    for (int rr = 0; rr < 2; rr++) {
-        const int k = tid + rr * SUP_THREADS;
-        int row = -1;
-        if (q1) {
-            if (k < 4 * SJT) {
-                const int jj = J0 + (k >> 2), e = k & 3;
-                if (jj < m) row = F.foff[F.id_list[jj]] + (e < 3 ? e : 5);
-            } else {
-                const int tt = 2 * J0 + (k - 4 * SJT);  // index into the stacked position vector ri_v
-                const int feat = tt / 3;
-                if (feat < m && (tt >> 1) < m) row = F.foff[F.id_list[feat]] + tt % 3;
-            }
-        } else {
-            const int jj = J0 + k / 6;
-            if (jj < m) row = F.foff[F.id_list[jj]] + k % 6;
-        }
-        rows[rr] = row;
-    }
-    const int nv = __syncthreads_count(tid < SHB && s_t[tid] >= 0);
+    for (int rr = 0; rr < 2; rr++) rows[rr] = F.sup_rows[(size_t)blockIdx.x * (6 * SJT) + tid + rr * SUP_THREADS];
+    const int nv = __syncthreads_count(tid < SHB * 16 && (tid & 15) == 15 && my_t >= 0);
     if (nv == 0) return;
-#if RSLAM_SUP_PREFETCH
-    // everything this thread will read from P goes to L2 now, while the hypothesis constants are still being gathered: the demand
-    // loads of phase 1 (12 in flight per thread, register bound) then find their lines in L2 or already on the way
-    {
-        const double* __restrict__ Pp = F.P;
-#pragma unroll
-        for (int rr = 0; rr < RSLAM_SUP_PREFETCH; rr++) {
-            if (rows[rr] < 0) continue;
-            const double* prow = Pp + rows[rr];
-#pragma unroll
-            for (int pl = 0; pl < SHB; pl++) {
-                const double* col = prow + s_colbase[pl];
-                const int fs = s_fsp[pl];
-#pragma unroll
-                for (int c = 0; c < 6; c++) {
-                    if (c < 3 ? fs > 0 : fs > 3) asm volatile("prefetch.global.L2 [%0];" ::"l"(col));
-                    col += ld;
-                }
-            }
-        }
-    }
-#endif
-    for (int e = tid; e < SHB * 14; e += SUP_THREADS) {
-        const int pl = e / 14, c = e % 14;
-        s_ab[pl][c] = (s_t[pl] >= 0 && c < 13) ? F.hyp_ab[(size_t)s_t[pl] * 13 + c] : 0.0;
-    }
-    for (int e = tid; e < SHB * 7; e += SUP_THREADS) {
-        const int pl = e / 7, c = e % 7;
-        s_xc[pl][c] = s_t[pl] >= 0 ? F.hyp_xcam[(size_t)s_t[pl] * 7 + c] : 0.0;
-    }
     if (pair_counter && tid == 0) atomicAdd(pair_counter, (unsigned long long)nv * (unsigned long long)min(SJT, m - J0));
-    __syncthreads();
-    if (tid < SHB && s_t[tid] >= 0) q2r_dev(&s_xc[tid][3], s_R[tid]);
+    if (tid < SHB && s_t[tid] >= 0) q2r_dev(&s_xc[tid][3], s_R[tid]);  // consumed behind the barrier that separates the two phases
+#ifdef RSLAM_SUP_CLOCKS
+    const long long ck1 = clock64();
+#endif
     // ---- phase 1 ----
     const double* __restrict__ P = F.P;
     const double* __restrict__ x = F.x_km1;
@@ -1025,7 +1026,13 @@ __global__ void __launch_bounds__(SUP_THREADS, RSLAM_SUP_MINB) k_ransac_support(
             }
         }
     }
+#ifdef RSLAM_SUP_CLOCKS
+    const long long ck2a = clock64();
+#endif
     __syncthreads();
+#ifdef RSLAM_SUP_CLOCKS
+    const long long ck2 = clock64();
+#endif
     // ---- phase 2 ----
     const double fku = cam.f * (1.0 / cam.dx);
     const double idx = 1.0 / cam.dx, idy = 1.0 / cam.dy;
@@ -1102,6 +1109,16 @@ __global__ void __launch_bounds__(SUP_THREADS, RSLAM_SUP_MINB) k_ransac_support(
             if (cnt) atomicAdd(sup_alt ? &sup_alt[s_slot[pl]] : &F.support[t], cnt);
         }
     }
+#ifdef RSLAM_SUP_CLOCKS
+    if (tid == 0) {
+        const long long ck3 = clock64();
+        atomicAdd(&g_sup_clk[0], (unsigned long long)(ck1 - ck0));
+        atomicAdd(&g_sup_clk[1], (unsigned long long)(ck2a - ck1));
+        atomicAdd(&g_sup_clk[2], (unsigned long long)(ck2 - ck2a));
+        atomicAdd(&g_sup_clk[3], (unsigned long long)(ck3 - ck2));
+        atomicAdd(&g_sup_clk[4], 1ull);
+    }
+#endif
 }
 
 __device__ __forceinline__ void gather_inliers(DevFilter& F, int which, int* s_scan, int* s_base);  // kernels_update.cuh

@@ -281,7 +281,7 @@ int run_ransac_core(rslam_filter* f, bool select, bool gather_li = false) {
     const int B = f->B, N = f->hN;
     if (N == 0) return 0;
     LAUNCH(f, k_ransac_compact, dim3(1, B), 256, 0, f->dF);
-    LAUNCH(f, k_ransac_hyp, dim3(cdiv(N, 128), B), 128, 0, f->dF);
+    LAUNCH(f, k_ransac_hyp, dim3(cdiv(N, 128), B), 128, 0, f->dF, (int)((f->par.quirks & RSLAM_Q1_ANGLES_FROM_POSITIONS) != 0));
     if (select) {
         LAUNCH(f, k_ransac_support, dim3(cdiv(N, SJT), cdiv(N, SHB), B), SUP_THREADS, kSupSmemBytes, f->dF, f->camd, f->pard, (const int*)nullptr, 0, N, 0, N, (const int*)nullptr,
                (int*)nullptr, (unsigned long long*)nullptr);
@@ -356,7 +356,7 @@ int rslam_create(const rslam_camera* cam, const rslam_params* par, int max_featu
     f->htype.assign(B, std::vector<int>());
     int rc = 0;
     double *P, *xkk, *xkm1, *h, *Hc, *Hf, *S, *z, *hyp_ab, *hyp_xcam, *Jn;
-    int *ftype, *foff, *tp, *tm, *ic_list, *id_list, *id_pos, *support, *ctl, *upd_list;
+    int *ftype, *foff, *tp, *tm, *ic_list, *id_list, *id_pos, *support, *ctl, *upd_list, *sup_rows;
     unsigned char *has_h, *ic, *li, *hi;
     float* patch;
     unsigned* masks;
@@ -369,8 +369,8 @@ int rslam_create(const rslam_camera* cam, const rslam_params* par, int max_featu
         rslam_destroy(f);                                 \
         return rc;                                        \
     }
-    A(P, psz) A(xkk, n) A(xkm1, n) A(h, 2 * N) A(Hc, 14 * N) A(Hf, 12 * N) A(S, 4 * N) A(z, 2 * N) A(hyp_ab, 13 * N) A(hyp_xcam, 7 * N) A(Jn, 32)
-    A(ftype, N) A(foff, N) A(tp, N) A(tm, N) A(ic_list, N) A(id_list, N) A(id_pos, N) A(support, N) A(ctl, CTL_SIZE) A(upd_list, N)
+    A(P, psz) A(xkk, n) A(xkm1, n) A(h, 2 * N) A(Hc, 14 * N) A(Hf, 12 * N) A(S, 4 * N) A(z, 2 * N) A(hyp_ab, 16 * N) A(hyp_xcam, 7 * N) A(Jn, 32)
+    A(ftype, N) A(foff, N) A(tp, N) A(tm, N) A(ic_list, N) A(id_list, N) A(id_pos, N) A(support, N) A(ctl, CTL_SIZE) A(upd_list, N) A(sup_rows, 6 * (size_t)round_up(N, 64))
     A(has_h, N) A(ic, N) A(li, N) A(hi, N) A(patch, (size_t)N * kPatchPix) A(masks, (size_t)N * f->mwords)
     A(patch_init, (size_t)N * 1681) A(init_pose, (size_t)N * 14) A(last_id, N)
 #undef A
@@ -414,8 +414,9 @@ int rslam_create(const rslam_camera* cam, const rslam_params* par, int max_featu
         D.last_id = last_id + (size_t)N * b;
         D.ic_list = ic_list + (size_t)N * b;
         D.id_list = id_list + (size_t)N * b;
+        D.sup_rows = sup_rows + 6 * (size_t)round_up(N, 64) * b;
         D.id_pos = id_pos + (size_t)N * b;
-        D.hyp_ab = hyp_ab + (size_t)13 * N * b;
+        D.hyp_ab = hyp_ab + (size_t)16 * N * b;
         D.hyp_xcam = hyp_xcam + (size_t)7 * N * b;
         D.support = support + (size_t)N * b;
         f->d_support_all = support;
@@ -914,6 +915,15 @@ int rslam_frame(rslam_filter* f, const uint8_t* images, int rows, int cols, int 
     return RSLAM_OK;
 }
 
+#ifdef RSLAM_SUP_CLOCKS
+extern "C" int rslam_debug_sup_clocks(unsigned long long* out8) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out8, rslam::g_sup_clk, sizeof(unsigned long long) * 8);
+    unsigned long long z[8] = {0};
+    cudaMemcpyToSymbol(rslam::g_sup_clk, z, sizeof(z));
+    return 0;
+}
+#endif
 // diagnostics: the 32-double scratch block of filter b (phase clocks when built with -DRSLAM_PHASE_CLOCKS)
 int rslam_debug_scratch(rslam_filter* f, int b, double* out32) {
     if (!f || b < 0 || b >= f->B || !out32) return fail(RSLAM_ERR_INVALID, "rslam_debug_scratch: bad arguments");
