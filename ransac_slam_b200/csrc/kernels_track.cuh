@@ -40,68 +40,84 @@ __device__ void v2q_dev(const double* v, double* q) {  // src/ExtendKF.cpp:428-4
     }
 }
 
-__device__ void build_F_Q(const double* x, const ParDev& par, double* Fm /*13x13 row-major*/, double* Q /*13x13*/, double* xv_new /*13*/) {
+// F = dfv/dxv, Q = G Pn G^T and the predicted camera state, CTA-collective: thread 0 does the short serial part (quaternion
+// product, the 4 x 3 block dq3_by_dq1 * dqomegadt_by_domega) into shared memory, then every thread fills its entries of F and Q
+// (the serial version cost a fifth of the kernel on the single-filter path: 169 x 6 products out of a locally indexed array).
+__device__ void build_F_Q(const double* x, const ParDev& par, double* Fm /*13x13 row-major*/, double* Q /*13x13*/, double* xv_new /*13*/,
+                          double* sG /*13x6 scratch*/) {
     const double dt = 1.0;
-    for (int i = 0; i < 169; i++) {
-        Fm[i] = 0.0;
-        Q[i] = 0.0;
+    __shared__ double s_qd[16], s_ab[12];
+    if (threadIdx.x == 0) {
+        double wdt[3] = {x[10] * dt, x[11] * dt, x[12] * dt}, qwt[4];
+        v2q_dev(wdt, qwt);
+        // qprod (src/ExtendKF.cpp:416-427)
+        const double* q = x + 3;
+        const double cr0 = q[2] * qwt[3] - q[3] * qwt[2], cr1 = q[3] * qwt[1] - q[1] * qwt[3], cr2 = q[1] * qwt[2] - q[2] * qwt[1];
+        for (int i = 0; i < 3; i++) xv_new[i] = x[i] + x[7 + i] * dt;
+        xv_new[3] = q[0] * qwt[0] - (q[1] * qwt[1] + q[2] * qwt[2] + q[3] * qwt[3]);
+        xv_new[4] = (q[0] * qwt[1] + qwt[0] * q[1]) + cr0;
+        xv_new[5] = (q[0] * qwt[2] + qwt[0] * q[2]) + cr1;
+        xv_new[6] = (q[0] * qwt[3] + qwt[0] * q[3]) + cr2;
+        for (int i = 7; i < 13; i++) xv_new[i] = x[i];
+        // dfv_by_dxv (src/ExtendKF.cpp:444-481)
+        const double qd[16] = {qwt[0], -qwt[1], -qwt[2], -qwt[3], qwt[1], qwt[0], qwt[3], -qwt[2],
+                               qwt[2], -qwt[3], qwt[0], qwt[1], qwt[3], qwt[2], -qwt[1], qwt[0]};
+#pragma unroll
+        for (int i = 0; i < 16; i++) s_qd[i] = qd[i];
+        // dq3_by_dq1(qOld) * dqomegadt_by_domega(omegaOld, dt)   (src/ExtendKF.cpp:482-529)
+        const double a[16] = {q[0], -q[1], -q[2], -q[3], q[1], q[0], -q[3], q[2], q[2], q[3], q[0], -q[1], q[3], -q[2], q[1], q[0]};
+        const double* w = x + 10;
+        const double om = sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+        double b[12];
+        const double sh = sin(om * dt / 2.0), ch = cos(om * dt / 2.0);
+#pragma unroll
+        for (int j = 0; j < 3; j++) b[j] = (-dt / 2.0) * (w[j] / om) * sh;
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                if (i == j)
+                    b[(i + 1) * 3 + j] = (dt / 2.0) * w[i] * w[i] / (om * om) * ch + (1.0 / om) * (1.0 - w[i] * w[i] / (om * om)) * sh;
+                else
+                    b[(i + 1) * 3 + j] = (w[i] * w[j] / (om * om)) * ((dt / 2.0) * ch - (1.0 / om) * sh);
+            }
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                double sacc = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) sacc += a[4 * i + k] * b[3 * k + j];
+                s_ab[3 * i + j] = sacc;
+            }
     }
-    for (int i = 0; i < 13; i++) Fm[i * 13 + i] = 1.0;
-    double wdt[3] = {x[10] * dt, x[11] * dt, x[12] * dt}, qwt[4];
-    v2q_dev(wdt, qwt);
-    // qprod (src/ExtendKF.cpp:416-427)
-    const double* q = x + 3;
-    const double cr0 = q[2] * qwt[3] - q[3] * qwt[2], cr1 = q[3] * qwt[1] - q[1] * qwt[3], cr2 = q[1] * qwt[2] - q[2] * qwt[1];
-    for (int i = 0; i < 3; i++) xv_new[i] = x[i] + x[7 + i] * dt;
-    xv_new[3] = q[0] * qwt[0] - (q[1] * qwt[1] + q[2] * qwt[2] + q[3] * qwt[3]);
-    xv_new[4] = (q[0] * qwt[1] + qwt[0] * q[1]) + cr0;
-    xv_new[5] = (q[0] * qwt[2] + qwt[0] * q[2]) + cr1;
-    xv_new[6] = (q[0] * qwt[3] + qwt[0] * q[3]) + cr2;
-    for (int i = 7; i < 13; i++) xv_new[i] = x[i];
-    // dfv_by_dxv (src/ExtendKF.cpp:444-481)
-    const double qd[16] = {qwt[0], -qwt[1], -qwt[2], -qwt[3], qwt[1], qwt[0], qwt[3], -qwt[2],
-                           qwt[2], -qwt[3], qwt[0], qwt[1], qwt[3], qwt[2], -qwt[1], qwt[0]};
-    for (int i = 0; i < 4; i++)
-        for (int j = 0; j < 4; j++) Fm[(3 + i) * 13 + 3 + j] = qd[4 * i + j];
-    for (int i = 0; i < 3; i++) Fm[i * 13 + 7 + i] = dt;
-    // dq3_by_dq1(qOld) * dqomegadt_by_domega(omegaOld, dt)   (src/ExtendKF.cpp:482-529)
-    const double a[16] = {q[0], -q[1], -q[2], -q[3], q[1], q[0], -q[3], q[2], q[2], q[3], q[0], -q[1], q[3], -q[2], q[1], q[0]};
-    const double* w = x + 10;
-    const double om = sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
-    double b[12];
-    const double sh = sin(om * dt / 2.0), ch = cos(om * dt / 2.0);
-    for (int j = 0; j < 3; j++) b[j] = (-dt / 2.0) * (w[j] / om) * sh;
-    for (int i = 0; i < 3; i++)
-        for (int j = 0; j < 3; j++) {
-            if (i == j)
-                b[(i + 1) * 3 + j] = (dt / 2.0) * w[i] * w[i] / (om * om) * ch + (1.0 / om) * (1.0 - w[i] * w[i] / (om * om)) * sh;
-            else
-                b[(i + 1) * 3 + j] = (w[i] * w[j] / (om * om)) * ((dt / 2.0) * ch - (1.0 / om) * sh);
-        }
-    double ab[12];
-    for (int i = 0; i < 4; i++)
-        for (int j = 0; j < 3; j++) {
-            double s = 0;
-            for (int k = 0; k < 4; k++) s += a[4 * i + k] * b[3 * k + j];
-            ab[3 * i + j] = s;
-            Fm[(3 + i) * 13 + 10 + j] = s;
-        }
-    // Q = G Pn G^T with G(7:10,0:3)=I, G(10:13,3:6)=I, G(0:3,0:3)=I*dt, G(3:7,3:6)=ab  (src/ExtendKF.cpp:347-376)
-    double G[13 * 6];
-    for (int i = 0; i < 78; i++) G[i] = 0.0;
-    for (int i = 0; i < 3; i++) {
-        G[(7 + i) * 6 + i] = 1.0;
-        G[(10 + i) * 6 + 3 + i] = 1.0;
-        G[i * 6 + i] = dt;
+    __syncthreads();
+    // G(7:10,0:3)=I, G(10:13,3:6)=I, G(0:3,0:3)=I*dt, G(3:7,3:6)=ab  (src/ExtendKF.cpp:347-376)
+    for (int e = threadIdx.x; e < 78; e += blockDim.x) {
+        const int i = e / 6, k = e % 6;
+        double g = 0.0;
+        if (i < 3) g = (k == i) ? dt : 0.0;
+        else if (i < 7) g = (k >= 3) ? s_ab[3 * (i - 3) + (k - 3)] : 0.0;
+        else if (i < 10) g = (k == i - 7) ? 1.0 : 0.0;
+        else g = (k == 3 + (i - 10)) ? 1.0 : 0.0;
+        sG[e] = g;
     }
-    for (int i = 0; i < 4; i++)
-        for (int j = 0; j < 3; j++) G[(3 + i) * 6 + 3 + j] = ab[3 * i + j];
-    for (int i = 0; i < 13; i++)
-        for (int j = 0; j < 13; j++) {
-            double s = 0;
-            for (int k = 0; k < 6; k++) s += (G[i * 6 + k] * (k < 3 ? par.la : par.aa)) * G[j * 6 + k];
-            Q[i * 13 + j] = s;
-        }
+    for (int e = threadIdx.x; e < 169; e += blockDim.x) {
+        const int i = e / 13, j = e % 13;
+        double f = (i == j) ? 1.0 : 0.0;
+        if (i >= 3 && i < 7 && j >= 3 && j < 7) f = s_qd[4 * (i - 3) + (j - 3)];
+        if (i < 3 && j == 7 + i) f = dt;
+        if (i >= 3 && i < 7 && j >= 10) f = s_ab[3 * (i - 3) + (j - 10)];
+        Fm[e] = f;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < 169; e += blockDim.x) {
+        const int i = e / 13, j = e % 13;
+        double sacc = 0;
+#pragma unroll
+        for (int k = 0; k < 6; k++) sacc += (sG[i * 6 + k] * (k < 3 ? par.la : par.aa)) * sG[j * 6 + k];
+        Q[e] = sacc;
+    }
 }
 
 __global__ void __launch_bounds__(128) k_ekf_prediction(DevFilter* Fs, ParDev par, int with_begin) {
@@ -109,7 +125,7 @@ __global__ void __launch_bounds__(128) k_ekf_prediction(DevFilter* Fs, ParDev pa
     __shared__ double sF[169], sQ[169], sX[13], sP[169], sT[169];
     const int n = F.n;
     if (blockIdx.x * blockDim.x >= (unsigned)n && blockIdx.x != 0) return;
-    if (threadIdx.x == 0) build_F_Q(F.x_kk, par, sF, sQ, sX);
+    build_F_Q(F.x_kk, par, sF, sQ, sX, sT);  // sT doubles as the 13 x 6 scratch for G (free until the camera block below)
     __syncthreads();
     const int ld = F.ldp;
     if (blockIdx.x == 0) {
@@ -835,23 +851,46 @@ __global__ void __launch_bounds__(128) k_ransac_hyp(DevFilter* Fs, int q1) {
     {
         const int m = F.ctl[CTL_MID];
         const int ntile = (m + kSupTile - 1) / kSupTile;
-        for (int e = t; e < ntile * 6 * kSupTile; e += gridDim.x * blockDim.x) {
-            const int J0 = (e / (6 * kSupTile)) * kSupTile, k = e % (6 * kSupTile);
-            int row = -1;
-            if (q1) {
-                if (k < 4 * kSupTile) {
-                    const int jj = J0 + (k >> 2), c = k & 3;
-                    if (jj < m) row = F.foff[F.id_list[jj]] + (c < 3 ? c : 5);
+        const int total = ntile * 6 * kSupTile, stride = gridDim.x * blockDim.x;
+        for (int e0 = t; e0 < total; e0 += 4 * stride) {  // four entries per pass: their two dependent index loads overlap
+            int feat[4], add[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int e = e0 + u * stride;
+                feat[u] = -1;
+                add[u] = 0;
+                if (e >= total) continue;
+                const int J0 = (e / (6 * kSupTile)) * kSupTile, k = e % (6 * kSupTile);
+                if (q1) {
+                    if (k < 4 * kSupTile) {
+                        const int jj = J0 + (k >> 2), c = k & 3;
+                        if (jj < m) {
+                            feat[u] = jj;
+                            add[u] = c < 3 ? c : 5;
+                        }
+                    } else {
+                        const int tt = 2 * J0 + (k - 4 * kSupTile);  // index into the stacked position vector ri_v
+                        if (tt / 3 < m && (tt >> 1) < m) {
+                            feat[u] = tt / 3;
+                            add[u] = tt % 3;
+                        }
+                    }
                 } else {
-                    const int tt = 2 * J0 + (k - 4 * kSupTile);  // index into the stacked position vector ri_v
-                    const int feat = tt / 3;
-                    if (feat < m && (tt >> 1) < m) row = F.foff[F.id_list[feat]] + tt % 3;
+                    const int jj = J0 + k / 6;
+                    if (jj < m) {
+                        feat[u] = jj;
+                        add[u] = k % 6;
+                    }
                 }
-            } else {
-                const int jj = J0 + k / 6;
-                if (jj < m) row = F.foff[F.id_list[jj]] + k % 6;
             }
-            F.sup_rows[e] = row;
+            int idf[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) idf[u] = feat[u] >= 0 ? F.id_list[feat[u]] : 0;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int e = e0 + u * stride;
+                if (e < total) F.sup_rows[e] = feat[u] >= 0 ? F.foff[idf[u]] + add[u] : -1;
+            }
         }
     }
     if (t >= F.ctl[CTL_NIC]) return;
@@ -874,12 +913,28 @@ __global__ void __launch_bounds__(128) k_ransac_hyp(DevFilter* Fs, int q1) {
     F.hyp_ab[(size_t)t * 16 + 13] = __longlong_as_double((long long)off * ld);
     F.hyp_ab[(size_t)t * 16 + 14] = (double)fs;
     F.hyp_ab[(size_t)t * 16 + 15] = 0.0;
+    // all 7 x 13 entries of P are fetched as one batch (compile-time trip counts, columns beyond fs predicated off): on the
+    // single-filter path this kernel is nothing but memory latency
+    double pc[7][13];
+#pragma unroll
+    for (int r = 0; r < 7; r++) {
+#pragma unroll
+        for (int c = 0; c < 7; c++) pc[r][c] = F.P[r + (size_t)c * ld];
+#pragma unroll
+        for (int c = 0; c < 6; c++) pc[r][7 + c] = c < fs ? F.P[r + (size_t)(off + c) * ld] : 0.0;
+    }
+    double xr[7];
+#pragma unroll
+    for (int r = 0; r < 7; r++) xr[r] = F.x_km1[r];
+#pragma unroll
     for (int r = 0; r < 7; r++) {
         double s = 0;
 #pragma unroll
-        for (int c = 0; c < 7; c++) s += F.P[r + (size_t)c * ld] * ab[c];
-        for (int c = 0; c < fs; c++) s += F.P[r + (size_t)(off + c) * ld] * ab[7 + c];
-        F.hyp_xcam[(size_t)t * 7 + r] = F.x_km1[r] + s;
+        for (int c = 0; c < 7; c++) s += pc[r][c] * ab[c];
+#pragma unroll
+        for (int c = 0; c < 6; c++)
+            if (c < fs) s += pc[r][7 + c] * ab[7 + c];
+        F.hyp_xcam[(size_t)t * 7 + r] = xr[r] + s;
     }
 }
 
