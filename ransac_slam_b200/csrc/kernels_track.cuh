@@ -621,12 +621,29 @@ __global__ void __launch_bounds__(kSearchThreads) k_search(DevFilter* Fs, CamDev
     const int nsy = (ncy + kStrip - 1) / kStrip;
     const int ww = ncx + 2 * kHalfPatch, wh = nsy * kStrip + 2 * kHalfPatch;  // rows padded to whole strips (zeros)
     const int wx0 = x_lo - kHalfPatch, wy0 = y_lo - kHalfPatch;
-    for (int e = threadIdx.x; e < ww * wh; e += blockDim.x) {
-        const int wy = e / ww, wx = e % ww;
-        const int gx = wx0 + wx, gy = wy0 + wy;
-        unsigned char v = 0;
-        if (gx >= 0 && gx < F.img_cols && gy >= 0 && gy < F.img_rows) v = F.image[(size_t)gy * F.img_stride + gx];
-        win[e] = (double)v;
+    {   // window load: a warp per row, lanes along x (coalesced bytes, no integer divisions), four rows x two 32-pixel chunks in flight
+        const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5, nwrp = blockDim.x >> 5;
+        const unsigned char* img = F.image;
+        const int icols = F.img_cols, irows = F.img_rows, istride = F.img_stride;
+        for (int wyb = wrp * 4; wyb < wh; wyb += 4 * nwrp) {
+            unsigned char v[4][2];
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+#pragma unroll
+                for (int hh = 0; hh < 2; hh++) {
+                    const int wy = wyb + u, wx = lane + 32 * hh;
+                    const int gx = wx0 + wx, gy = wy0 + wy;
+                    v[u][hh] = 0;
+                    if (wy < wh && wx < ww && gx >= 0 && gx < icols && gy >= 0 && gy < irows) v[u][hh] = img[(size_t)gy * istride + gx];
+                }
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+#pragma unroll
+                for (int hh = 0; hh < 2; hh++) {
+                    const int wy = wyb + u, wx = lane + 32 * hh;
+                    if (wy < wh && wx < ww) win[wy * ww + wx] = (double)v[u][hh];
+                }
+        }
     }
     for (int e = threadIdx.x; e < kPatchPix; e += blockDim.x) pa[e] = (double)F.patch[(size_t)i * kPatchPix + e];
     __syncthreads();
