@@ -94,21 +94,38 @@ __global__ void __launch_bounds__(256) k_upd_W(DevFilter* Fs) {
     double pc[7];
 #pragma unroll
     for (int c = 0; c < 7; c++) pc[c] = P[r + (size_t)c * ld];
-    for (int tt = 0; tt < t1 - t0; tt++) {
-        double w0 = 0, w1 = 0;
+    // two measurements per pass, feature columns with compile-time trip counts (columns beyond fs predicated off): 12 independent
+    // loads in flight per thread instead of one (same summation order as before)
+    for (int tt0 = 0; tt0 < t1 - t0; tt0 += 2) {
+        double pf[2][6];
 #pragma unroll
-        for (int c = 0; c < 7; c++) {
-            w0 += pc[c] * sH[tt][c];
-            w1 += pc[c] * sH[tt][7 + c];
+        for (int u = 0; u < 2; u++) {
+            const int tt = tt0 + u;
+            const bool live = tt < t1 - t0;
+            const int off = live ? sOff[tt] : 0, fs = live ? sFs[tt] : 0;
+#pragma unroll
+            for (int c = 0; c < 6; c++) pf[u][c] = c < fs ? P[r + (size_t)(off + c) * ld] : 0.0;
         }
-        const int off = sOff[tt], fs = sFs[tt];
-        for (int c = 0; c < fs; c++) {
-            const double p = P[r + (size_t)(off + c) * ld];
-            w0 += p * sH[tt][14 + c];
-            w1 += p * sH[tt][20 + c];
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int tt = tt0 + u;
+            if (tt >= t1 - t0) break;
+            double w0 = 0, w1 = 0;
+#pragma unroll
+            for (int c = 0; c < 7; c++) {
+                w0 += pc[c] * sH[tt][c];
+                w1 += pc[c] * sH[tt][7 + c];
+            }
+            const int fs = sFs[tt];
+#pragma unroll
+            for (int c = 0; c < 6; c++)
+                if (c < fs) {
+                    w0 += pf[u][c] * sH[tt][14 + c];
+                    w1 += pf[u][c] * sH[tt][20 + c];
+                }
+            F.W[r + (size_t)(2 * (t0 + tt)) * F.ldw] = w0;
+            F.W[r + (size_t)(2 * (t0 + tt) + 1) * F.ldw] = w1;
         }
-        F.W[r + (size_t)(2 * (t0 + tt)) * F.ldw] = w0;
-        F.W[r + (size_t)(2 * (t0 + tt) + 1) * F.ldw] = w1;
     }
 }
 
