@@ -273,7 +273,8 @@ constexpr int kTld = 260;          // panel storage is k-major: entry (row i, co
                                    // fragment loads, thread-per-row accesses and column stores are all bank-conflict free
 constexpr int kPanRowsMax = 256;   // diagonal block (rows 0..63) + up to 192 rows below it
 // smem carve-up shared by the panel kernels: sT[64][260] panel, sX[64][65] inverse of the diagonal block, sRd[64] (1 / l_jj)
-constexpr int kPanelDoubles = kNB * kTld + kNB * (kNB + 1) + kNB;
+constexpr int kInvLd = 33;  // leading dimension of the 32 x 32 scratch of the blocked triangular inverse
+constexpr int kPanelDoubles = kNB * kTld + kNB * (kNB + 1) + kNB + 32 * kInvLd;
 constexpr int kPanelSmemBytes = kPanelDoubles * (int)sizeof(double);
 constexpr int kCholSmallMaxK = 256;
 constexpr int kCholSmallSmemBytes = kPanelSmemBytes;
@@ -282,12 +283,14 @@ struct PanelSmem {
     double* sT;
     double (*sX)[kNB + 1];
     double* sRd;
+    double* sW;  // [32][kInvLd]
 };
 __device__ __forceinline__ PanelSmem panel_carve(double* base) {
     PanelSmem p;
     p.sT = base;
     p.sX = reinterpret_cast<double(*)[kNB + 1]>(base + kNB * kTld);
     p.sRd = base + kNB * kTld + kNB * (kNB + 1);
+    p.sW = p.sRd + kNB;
     return p;
 }
 
@@ -398,27 +401,95 @@ __device__ __forceinline__ void smem_panel_factor(const PanelSmem& ps, int R, in
 }
 
 // explicit inverse of the 64 x 64 lower-triangular diagonal block (rows 0..63 of sT, identity padded) -> sX (full 64 x 64, zeros
-// above the diagonal).  Column c of the inverse solves L x = e_c by forward substitution with running updates of the right-hand
-// side.  FOUR adjacent lanes share a column (8 columns per warp, all 8 warps busy): lane part p keeps rows i = 4 q + p in
-// registers, the owner of row t forms x_t = b_t / l_tt and hands it to its three neighbours with a shuffle, then every part
-// updates its rows behind t.  (A lone warp sustains only one shared-load-fed DFMA per ~7 cycles, so the 2016 updates of a
-// column-per-thread version cost ~24 k cycles on two warps; spread over 256 threads they take ~4 k.)  CTA-collective.
+// above the diagonal), BLOCKED:  inv [A 0; B C] = [inv A 0; -inv C * (B * inv A)  inv C].
+//   level 0: the four 16 x 16 diagonal blocks, concurrently.  Column c of a block's inverse solves L x = e_c by forward
+//            substitution with running updates of the right-hand side; FOUR adjacent lanes share a column (two warps per block, all
+//            8 warps busy): lane part p keeps rows 4 q + p, the owner of row t forms x_t = b_t / l_tt and hands it to its three
+//            neighbours with a shuffle.  The chain is multiply -> shuffle -> FMA, ~180 cycles per step: 16 steps here instead of the
+//            64 of an unblocked substitution (which cost 11.6 k cycles, a quarter of the single-CTA factorisation).
+//   level 1 / 2: the off-diagonal 16 x 16 and 32 x 32 blocks from two small products each on the fp64 tensor cores.
+// CTA-collective (256 threads).
 __device__ __forceinline__ void smem_trinv64(const PanelSmem& ps) {
     const unsigned fm = 0xffffffffu;
-    const int lane = threadIdx.x & 31, p = lane & 3;
-    const int c = (threadIdx.x >> 5) * 8 + (lane >> 2);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double* sT = ps.sT;
-    double b[kNB / 4];
+    {   // level 0
+        const int r0 = 16 * (warp >> 1), cl = (warp & 1) * 8 + (lane >> 2), p = lane & 3;
+        double b[4];
 #pragma unroll
-    for (int q = 0; q < kNB / 4; q++) b[q] = (4 * q + p == c) ? 1.0 : 0.0;
+        for (int q = 0; q < 4; q++) b[q] = (4 * q + p == cl) ? 1.0 : 0.0;
 #pragma unroll
-    for (int t = 0; t < kNB; t++) {
-        const double x = __shfl_sync(fm, b[t / 4] * ps.sRd[t], (lane & ~3) | (t & 3));
-        if (p == (t & 3)) ps.sX[t][c] = x;
-        // rows 4 q + p behind t; entries of rows <= t are already final (or were stored above) and may be clobbered
+        for (int t = 0; t < 16; t++) {
+            const double x = __shfl_sync(fm, b[t / 4] * ps.sRd[r0 + t], (lane & ~3) | (t & 3));
+            if (p == (t & 3)) ps.sX[r0 + t][r0 + cl] = x;
+            // rows 4 q + p behind t; entries of rows <= t are already final (or were stored above) and may be clobbered
 #pragma unroll
-        for (int q = t / 4; q < kNB / 4; q++) b[q] = fma(-sT[t * kTld + 4 * q + p], x, b[q]);
+            for (int q = t / 4; q < 4; q++) b[q] = fma(-sT[(r0 + t) * kTld + r0 + 4 * q + p], x, b[q]);
+        }
+        // blocks above the block diagonal are zero
+        for (int e = tid; e < 6 * 256; e += 256) {
+            const int blk = e >> 8, i = (e >> 4) & 15, j = e & 15;
+            const int bi = blk < 3 ? 0 : (blk < 5 ? 1 : 2), bj = blk < 3 ? blk + 1 : (blk < 5 ? blk - 1 : 3);
+            ps.sX[16 * bi + i][16 * bj + j] = 0.0;
+        }
     }
+    __syncthreads();
+    // C (8 x 8 per warp) = A * B with A(i, k) = a_at(i, k), B(k, j) = b_at(k, j), K a multiple of 4
+    const int fr = lane >> 2, fk = lane & 3;
+    {   // level 1: for each 32 x 32 half h: X21 = -X22 * (L21 * X11), 16 x 16 blocks; 2 halves x 4 output tiles = one tile per warp
+        const int h = warp >> 2, mi = (warp >> 1) & 1, ni = warp & 1, base = 32 * h;
+        double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < 4; ks++) {  // T = L21 * X11
+            const int k = base + ks * 4 + fk;
+            dmma8x8x4(c0, c1, sT[k * kTld + base + 16 + mi * 8 + fr], ps.sX[k][base + ni * 8 + fr]);
+        }
+        double* T = ps.sW + h * 16 * kInvLd;  // [16][kInvLd] per half
+        T[(mi * 8 + fr) * kInvLd + ni * 8 + 2 * fk] = c0;
+        T[(mi * 8 + fr) * kInvLd + ni * 8 + 2 * fk + 1] = c1;
+        __syncthreads();
+        c0 = c1 = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < 4; ks++) {  // X21 = -X22 * T
+            const int k = ks * 4 + fk;
+            dmma8x8x4(c0, c1, ps.sX[base + 16 + mi * 8 + fr][base + 16 + k], T[k * kInvLd + ni * 8 + fr]);
+        }
+        ps.sX[base + 16 + mi * 8 + fr][base + ni * 8 + 2 * fk] = -c0;
+        ps.sX[base + 16 + mi * 8 + fr][base + ni * 8 + 2 * fk + 1] = -c1;
+    }
+    __syncthreads();
+    {   // level 2: X21 (rows 32..63, cols 0..31) = -X22 * (L21 * X11), 32 x 32 blocks; 16 output tiles, two per warp
+        const int mi = warp >> 1, nj = (warp & 1) * 2;
+        double c[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+        for (int ks = 0; ks < 8; ks++) {  // T = L21 * X11
+            const int k = ks * 4 + fk;
+            const double a = sT[k * kTld + 32 + mi * 8 + fr];
+#pragma unroll
+            for (int u = 0; u < 2; u++) dmma8x8x4(c[u][0], c[u][1], a, ps.sX[k][(nj + u) * 8 + fr]);
+        }
+        __syncthreads();  // level 1 is done reading sW
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            ps.sW[(mi * 8 + fr) * kInvLd + (nj + u) * 8 + 2 * fk] = c[u][0];
+            ps.sW[(mi * 8 + fr) * kInvLd + (nj + u) * 8 + 2 * fk + 1] = c[u][1];
+            c[u][0] = c[u][1] = 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int ks = 0; ks < 8; ks++) {  // X21 = -X22 * T
+            const int k = ks * 4 + fk;
+            const double a = ps.sX[32 + mi * 8 + fr][32 + k];
+#pragma unroll
+            for (int u = 0; u < 2; u++) dmma8x8x4(c[u][0], c[u][1], a, ps.sW[k * kInvLd + (nj + u) * 8 + fr]);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            ps.sX[32 + mi * 8 + fr][(nj + u) * 8 + 2 * fk] = -c[u][0];
+            ps.sX[32 + mi * 8 + fr][(nj + u) * 8 + 2 * fk + 1] = -c[u][1];
+        }
+    }
+    __syncthreads();
 }
 
 __device__ __forceinline__ void store_linv(const double (*sX)[kNB + 1], double* out, int t0, int nt) {  // 64 x 64 column-major
