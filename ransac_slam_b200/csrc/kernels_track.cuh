@@ -1208,13 +1208,24 @@ __global__ void __launch_bounds__(256) k_ransac_select(DevFilter* Fs, ParDev par
     const double* u01 = F.u01;
     const int* support = F.support;
     // the first 2048 draws are resolved to supports by the whole CTA up front (parallel, latency paid once)
-    for (int i = threadIdx.x; i < 2048; i += blockDim.x) {
-        int s = -1;
-        if (i < n_u01 && nIC > 0) {
-            const int pos = (int)floor(u01[i] * (double)nIC);
-            s = support[pos < nIC ? pos : nIC - 1];
+    {   // 8 draws per thread (256 threads): all uniforms first, then all supports -- two round trips instead of sixteen
+        double u[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int i = threadIdx.x + k * 256;
+            u[k] = (i < n_u01 && nIC > 0) ? u01[i] : -1.0;
         }
-        s_sup[i] = s;
+        int sv[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            sv[k] = -1;
+            if (u[k] >= 0.0) {
+                const int pos = (int)floor(u[k] * (double)nIC);
+                sv[k] = support[pos < nIC ? pos : nIC - 1];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) s_sup[threadIdx.x + k * 256] = sv[k];
     }
     __syncthreads();
     if (threadIdx.x < 32) {
