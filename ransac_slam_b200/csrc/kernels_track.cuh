@@ -802,35 +802,37 @@ __global__ void __launch_bounds__(kSearchThreads) k_search(DevFilter* Fs, CamDev
 constexpr int kSupTile = 64;  // == SJT of k_ransac_support
 __global__ void __launch_bounds__(256) k_ransac_compact(DevFilter* Fs) {
     DevFilter& F = Fs[blockIdx.y];
-    __shared__ int s_scan[2][256];
+    // flags are 0 / 1: ordered positions from one ballot per warp + the warp totals (three barriers per 256 features instead of the
+    // 34 of a shared-memory scan)
+    __shared__ int s_wa[8], s_wb[8], s_wc[8];
     __shared__ int s_base[3];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (threadIdx.x == 0) s_base[0] = s_base[1] = s_base[2] = 0;
     __syncthreads();
     for (int base = 0; base < F.N; base += 256) {
         const int i = base + threadIdx.x;
-        int a = 0, b = 0, c = 0;
+        bool a = false, b = false, c = false;
         if (i < F.N) {
-            a = F.ic[i] ? 1 : 0;
-            b = (a && F.ftype[i] == 0) ? 1 : 0;
-            c = (a && F.ftype[i] != 0) ? 1 : 0;
+            a = F.ic[i] != 0;
+            const bool idp = F.ftype[i] == 0;
+            b = a && idp;
+            c = a && !idp;
         }
-        s_scan[0][threadIdx.x] = a;
-        s_scan[1][threadIdx.x] = b;
+        const unsigned ba = __ballot_sync(0xffffffffu, a), bb = __ballot_sync(0xffffffffu, b), bc = __ballot_sync(0xffffffffu, c);
+        if (lane == 0) {
+            s_wa[wid] = __popc(ba);
+            s_wb[wid] = __popc(bb);
+            s_wc[wid] = __popc(bc);
+        }
         __syncthreads();
-        // Hillis-Steele inclusive scan over 256 entries (two arrays at once)
-        for (int o = 1; o < 256; o <<= 1) {
-            int va = 0, vb = 0;
-            if (threadIdx.x >= o) {
-                va = s_scan[0][threadIdx.x - o];
-                vb = s_scan[1][threadIdx.x - o];
-            }
-            __syncthreads();
-            s_scan[0][threadIdx.x] += va;
-            s_scan[1][threadIdx.x] += vb;
-            __syncthreads();
+        int pa = s_base[0], pb = s_base[1];
+        for (int w2 = 0; w2 < wid; w2++) {
+            pa += s_wa[w2];
+            pb += s_wb[w2];
         }
-        const int pa = s_base[0] + s_scan[0][threadIdx.x] - a;
-        const int pb = s_base[1] + s_scan[1][threadIdx.x] - b;
+        const unsigned lt = (1u << lane) - 1u;
+        pa += __popc(ba & lt);
+        pb += __popc(bb & lt);
         if (i < F.N) {
             if (a) F.ic_list[pa] = i;
             if (b) {
@@ -840,12 +842,17 @@ __global__ void __launch_bounds__(256) k_ransac_compact(DevFilter* Fs) {
                 F.id_pos[i] = -1;
             }
         }
-        const int csum = __syncthreads_count(c);
         __syncthreads();
-        if (threadIdx.x == 255) {
-            s_base[0] += s_scan[0][255];
-            s_base[1] += s_scan[1][255];
-            s_base[2] += csum;
+        if (threadIdx.x == 0) {
+            int ta = 0, tb = 0, tc = 0;
+            for (int w2 = 0; w2 < 8; w2++) {
+                ta += s_wa[w2];
+                tb += s_wb[w2];
+                tc += s_wc[w2];
+            }
+            s_base[0] += ta;
+            s_base[1] += tb;
+            s_base[2] += tc;
         }
         __syncthreads();
     }

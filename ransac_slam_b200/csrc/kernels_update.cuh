@@ -1300,6 +1300,14 @@ __global__ void __launch_bounds__(256) k_upd_jnorm(DevFilter* Fs, ParDev par) {
     const int ld = F.ldp;
     double* P = F.P;
     const double r = F.x_kk[3], x = F.x_kk[4], y = F.x_kk[5], z = F.x_kk[6];
+    // rows 3..6 of the first 768 columns are fetched now (they do not depend on Jn), so their latency hides behind the serial part
+    double v0[3][4];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const int c = threadIdx.x + 256 * k;
+#pragma unroll
+        for (int l = 0; l < 4; l++) v0[k][l] = (c < F.n && !(c >= 3 && c < 7)) ? P[(3 + l) + (size_t)c * ld] : 0.0;
+    }
     __syncthreads();  // everybody has read the un-normalised quaternion
     if (threadIdx.x == 0) {
         const double s = r * r + x * x + y * y + z * z;
@@ -1331,8 +1339,20 @@ __global__ void __launch_bounds__(256) k_upd_jnorm(DevFilter* Fs, ParDev par) {
             P[(3 + j) + (size_t)(3 + i) * ld] = s;
         }
     }
-    for (int c = threadIdx.x; c < F.n; c += blockDim.x) {
-        if (c >= 3 && c < 7) continue;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const int c = threadIdx.x + 256 * k;
+        if (c >= F.n || (c >= 3 && c < 7)) continue;
+        double o[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) o[i] = sJ[i * 4] * v0[k][0] + sJ[i * 4 + 1] * v0[k][1] + sJ[i * 4 + 2] * v0[k][2] + sJ[i * 4 + 3] * v0[k][3];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            P[(3 + i) + (size_t)c * ld] = o[i];
+            P[c + (size_t)(3 + i) * ld] = o[i];
+        }
+    }
+    for (int c = threadIdx.x + 768; c < F.n; c += blockDim.x) {
         double v[4], o[4];
 #pragma unroll
         for (int l = 0; l < 4; l++) v[l] = P[(3 + l) + (size_t)c * ld];
