@@ -795,11 +795,77 @@ __global__ void __launch_bounds__(kSearchThreads) k_search(DevFilter* Fs, CamDev
     }
 }
 
+// one (match, hypothesis) pair of compute_hypothesis_support_fast (src/Tracking.cpp:443-477): re-projection of the hypothesised feature,
+// Newton distortion, squared residual against the squared threshold.  xi: the hypothesis' x_i rows of the tile (SJT matches, tile
+// layout of sup_rows).  Dead lanes run the arithmetic on zeros (it converges at once) so that the warp-uniform early exit stays uniform.
+constexpr int kSupTile = 64;  // matches per scoring tile
+__device__ __forceinline__ bool support_pair_inlier(const DevFilter& F, const CamDev& cam, bool q1, bool live, const double* xi, int jl, int jj,
+                                                    const double* xc, const double* Rm, double fku, double idx, double idy, double thr2) {
+    double r3[3] = {0, 0, 0}, a0 = 0, a1 = 0, rho = 0;
+    if (live) {
+        if (q1) {
+            r3[0] = xi[4 * jl];
+            r3[1] = xi[4 * jl + 1];
+            r3[2] = xi[4 * jl + 2];
+            rho = xi[4 * jl + 3];
+            a0 = xi[4 * kSupTile + 2 * jl];
+            a1 = xi[4 * kSupTile + 2 * jl + 1];
+        } else {
+            r3[0] = xi[6 * jl];
+            r3[1] = xi[6 * jl + 1];
+            r3[2] = xi[6 * jl + 2];
+            a0 = xi[6 * jl + 3];
+            a1 = xi[6 * jl + 4];
+            rho = xi[6 * jl + 5];
+        }
+    }
+    double s0, c0, s1, c1;
+    sincos_fast(a0, &s0, &c0);
+    sincos_fast(a1, &s1, &c1);
+    const double mi[3] = {c1 * s0, -s1, c1 * c0};
+    double v3[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) v3[k] = (r3[k] - xc[k]) * rho + mi[k];
+    double hc[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) hc[k] = Rm[k] * v3[0] + Rm[3 + k] * v3[1] + Rm[6 + k] * v3[2];  // R^T v
+    const double ihz = fast_rcp(hc[2]);
+    const double u = fku * (hc[0] * ihz) + cam.Cx;
+    const double v = fku * (hc[1] * ihz) + cam.Cy;  // ku for both rows (src/Tracking.cpp:471)
+    // distort_fm (src/ExtendKF.cpp:175-204) with the refined-reciprocal Newton step of distort_fast_dev
+    const double xu = (u - cam.Cx) * cam.dx;
+    const double yu = (v - cam.Cy) * cam.dy;
+    const double ru = sqrt(xu * xu + yu * yu);
+    const double ru2 = ru * ru;
+    double rd = ru * fast_rcp(1 + cam.k1 * ru2 + cam.k2 * (ru2 * ru2));
+#pragma unroll 1
+    for (int it = 0; it < 10; it++) {
+        const double rd2 = rd * rd;
+        const double rd4 = rd2 * rd2;
+        const double f = rd + cam.k1 * (rd2 * rd) + cam.k2 * (rd4 * rd) - ru;
+        const double fp = 1 + 3 * cam.k1 * rd2 + 5 * cam.k2 * rd4;
+        const double rn = fma(-f, fast_rcp(fp), rd);
+        const bool same = !(rn != rd) || !live;  // NaN counts as settled
+        rd = rn;
+        if (__all_sync(0xffffffffu, same)) break;
+    }
+    const double rdd = rd * rd;
+    const double iD = fast_rcp(1 + cam.k1 * rdd + cam.k2 * (rdd * rdd));
+    const double ud = xu * iD * idx + cam.Cx;
+    const double vd = yu * iD * idy + cam.Cy;
+    bool inl = false;
+    if (live) {
+        const int fj = F.id_list[jj];
+        const double n0 = F.z[2 * fj] - ud, n1 = F.z[2 * fj + 1] - vd;
+        inl = n0 * n0 + n1 * n1 < thr2;
+    }
+    return inl;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // (c) 1-point RANSAC (src/Tracking.cpp:352-539)
 // ---------------------------------------------------------------------------------------------------------------
 // c.1 ordered compaction of the individually-compatible list and the matched inverse-depth list (z_id columns, :361-397)
-constexpr int kSupTile = 64;  // == SJT of k_ransac_support
 __global__ void __launch_bounds__(256) k_ransac_compact(DevFilter* Fs) {
     DevFilter& F = Fs[blockIdx.y];
     // flags are 0 / 1: ordered positions from one ballot per warp + the warp totals (three barriers per 256 features instead of the
@@ -1122,65 +1188,7 @@ __global__ void __launch_bounds__(SUP_THREADS, RSLAM_SUP_MINB) k_ransac_support(
         const int jj = J0 + jl;
         const int t = s_t[pl];
         const bool live = t >= 0 && jj < m;
-        // dead lanes run the arithmetic on zeros (converges at once) so that the warp-uniform early exit below stays uniform
-        double r3[3] = {0, 0, 0}, a0 = 0, a1 = 0, rho = 0;
-        if (live) {
-            if (q1) {
-                r3[0] = xi[pl][4 * jl];
-                r3[1] = xi[pl][4 * jl + 1];
-                r3[2] = xi[pl][4 * jl + 2];
-                rho = xi[pl][4 * jl + 3];
-                a0 = xi[pl][4 * SJT + 2 * jl];
-                a1 = xi[pl][4 * SJT + 2 * jl + 1];
-            } else {
-                r3[0] = xi[pl][6 * jl];
-                r3[1] = xi[pl][6 * jl + 1];
-                r3[2] = xi[pl][6 * jl + 2];
-                a0 = xi[pl][6 * jl + 3];
-                a1 = xi[pl][6 * jl + 4];
-                rho = xi[pl][6 * jl + 5];
-            }
-        }
-        double s0, c0, s1, c1;
-        sincos_fast(a0, &s0, &c0);
-        sincos_fast(a1, &s1, &c1);
-        const double mi[3] = {c1 * s0, -s1, c1 * c0};
-        double v3[3];
-#pragma unroll
-        for (int k = 0; k < 3; k++) v3[k] = (r3[k] - s_xc[pl][k]) * rho + mi[k];
-        double hc[3];
-#pragma unroll
-        for (int k = 0; k < 3; k++) hc[k] = s_R[pl][k] * v3[0] + s_R[pl][3 + k] * v3[1] + s_R[pl][6 + k] * v3[2];  // R^T v
-        const double ihz = fast_rcp(hc[2]);
-        const double u = fku * (hc[0] * ihz) + cam.Cx;
-        const double v = fku * (hc[1] * ihz) + cam.Cy;  // ku for both rows (src/Tracking.cpp:471)
-        // distort_fm (src/ExtendKF.cpp:175-204) with the refined-reciprocal Newton step of distort_fast_dev
-        const double xu = (u - cam.Cx) * cam.dx;
-        const double yu = (v - cam.Cy) * cam.dy;
-        const double ru = sqrt(xu * xu + yu * yu);
-        const double ru2 = ru * ru;
-        double rd = ru * fast_rcp(1 + cam.k1 * ru2 + cam.k2 * (ru2 * ru2));
-#pragma unroll 1
-        for (int it = 0; it < 10; it++) {
-            const double rd2 = rd * rd;
-            const double rd4 = rd2 * rd2;
-            const double f = rd + cam.k1 * (rd2 * rd) + cam.k2 * (rd4 * rd) - ru;
-            const double fp = 1 + 3 * cam.k1 * rd2 + 5 * cam.k2 * rd4;
-            const double rn = fma(-f, fast_rcp(fp), rd);
-            const bool same = !(rn != rd) || !live;  // NaN counts as settled
-            rd = rn;
-            if (__all_sync(0xffffffffu, same)) break;
-        }
-        const double rdd = rd * rd;
-        const double iD = fast_rcp(1 + cam.k1 * rdd + cam.k2 * (rdd * rdd));
-        const double ud = xu * iD * idx + cam.Cx;
-        const double vd = yu * iD * idy + cam.Cy;
-        bool inl = false;
-        if (live) {
-            const int fj = F.id_list[jj];
-            const double n0 = F.z[2 * fj] - ud, n1 = F.z[2 * fj + 1] - vd;
-            inl = n0 * n0 + n1 * n1 < thr2;
-        }
+        const bool inl = support_pair_inlier(F, cam, q1, live, xi[pl], jl, jj, s_xc[pl], s_R[pl], fku, idx, idy, thr2);
         const unsigned bal = __ballot_sync(0xffffffffu, inl);
         if ((tid & 31) == 0 && t >= 0 && (jj >> 5) < F.mwords) {
             F.masks[(size_t)t * F.mwords + (jj >> 5)] = bal;
