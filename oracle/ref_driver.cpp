@@ -364,7 +364,8 @@ int ref_eigen_probe(const double* A_colmajor, const double* v_in, int n, double*
         for (Index j = 0; j < m.cols(); j++)
             for (Index i = 0; i < m.rows(); i++) o.push_back(m(i, j));
     };
-    MatrixXd A = Eigen::Map<MatrixXd>(A_colmajor, n, n);
+    std::vector<double> a_buf(A_colmajor, A_colmajor + (size_t)n * n);  // Eigen::Map<MatrixXd> wants a non-const pointer
+    MatrixXd A = Eigen::Map<MatrixXd>(a_buf.data(), n, n);
     VectorXd v(n);
     for (int i = 0; i < n; i++) v(i) = v_in[i];
     // 1. comma initialiser fills row by row, whatever the storage order (the Q16 pattern, src/Map.cpp:379)
