@@ -866,8 +866,7 @@ __device__ __forceinline__ bool support_pair_inlier(const DevFilter& F, const Ca
 // (c) 1-point RANSAC (src/Tracking.cpp:352-539)
 // ---------------------------------------------------------------------------------------------------------------
 // c.1 ordered compaction of the individually-compatible list and the matched inverse-depth list (z_id columns, :361-397)
-__global__ void __launch_bounds__(256) k_ransac_compact(DevFilter* Fs) {
-    DevFilter& F = Fs[blockIdx.y];
+__device__ __forceinline__ void ransac_compact_cta(DevFilter& F) {  // CTA-collective, 256 threads
     // flags are 0 / 1: ordered positions from one ballot per warp + the warp totals (three barriers per 256 features instead of the
     // 34 of a shared-memory scan)
     __shared__ int s_wa[8], s_wb[8], s_wc[8];
@@ -929,19 +928,18 @@ __global__ void __launch_bounds__(256) k_ransac_compact(DevFilter* Fs) {
     }
     for (int i = threadIdx.x; i < F.N; i += blockDim.x) F.support[i] = 0;  // accumulated with atomics by k_ransac_support
 }
+__global__ void __launch_bounds__(256) k_ransac_compact(DevFilter* Fs) { ransac_compact_cta(Fs[blockIdx.y]); }
 
 // c.2 one thread per distinct 1-point hypothesis t (match p = ic_list[t]): partial EKF state update restricted to the camera
 //     (src/Tracking.cpp:419-422):  g = S_p^-1 (z_p - h_p);  a = Hc_p^T g;  b = Hf_p^T g;  x_i[0..6] = x[0..6] + P[0..6,nz] [a;b]
-__global__ void __launch_bounds__(128) k_ransac_hyp(DevFilter* Fs, int q1) {
-    DevFilter& F = Fs[blockIdx.y];
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void ransac_hyp_thread(DevFilter& F, int q1, int t, int nthreads) {
     // state rows read by the support-scoring tiles, in tile order (one coalesced load per thread there instead of a dependent
     // id_list -> foff chain): kSupTile matches per tile, 6 rows per match, spread over the whole grid.  Quirk Q1 (reference): 3
     // position rows + rho per match, and the two "angle" rows are entries (2jj, 2jj+1) of the stacked POSITION vector of all matches.
     {
         const int m = F.ctl[CTL_MID];
         const int ntile = (m + kSupTile - 1) / kSupTile;
-        const int total = ntile * 6 * kSupTile, stride = gridDim.x * blockDim.x;
+        const int total = ntile * 6 * kSupTile, stride = nthreads;
         for (int e0 = t; e0 < total; e0 += 4 * stride) {  // four entries per pass: their two dependent index loads overlap
             int feat[4], add[4];
 #pragma unroll
@@ -1026,6 +1024,16 @@ __global__ void __launch_bounds__(128) k_ransac_hyp(DevFilter* Fs, int q1) {
             if (c < fs) s += pc[r][7 + c] * ab[7 + c];
         F.hyp_xcam[(size_t)t * 7 + r] = xr[r] + s;
     }
+}
+__global__ void __launch_bounds__(128) k_ransac_hyp(DevFilter* Fs, int q1) {
+    ransac_hyp_thread(Fs[blockIdx.y], q1, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+}
+// single-CTA fusion of the two for maps of up to 256 features (one dependent launch less on the single-filter path)
+__global__ void __launch_bounds__(256) k_ransac_compact_hyp(DevFilter* Fs, int q1) {
+    DevFilter& F = Fs[blockIdx.y];
+    ransac_compact_cta(F);
+    __syncthreads();  // lists and counts written by this CTA are visible to it
+    ransac_hyp_thread(F, q1, threadIdx.x, blockDim.x);
 }
 
 // c.3 support scoring (compute_hypothesis_support_fast, inlined at src/Tracking.cpp:424-503).

@@ -280,8 +280,13 @@ int run_update(rslam_filter* f, int which, bool gathered = false) {
 int run_ransac_core(rslam_filter* f, bool select, bool gather_li = false) {
     const int B = f->B, N = f->hN;
     if (N == 0) return 0;
-    LAUNCH(f, k_ransac_compact, dim3(1, B), 256, 0, f->dF);
-    LAUNCH(f, k_ransac_hyp, dim3(cdiv(N, 128), B), 128, 0, f->dF, (int)((f->par.quirks & RSLAM_Q1_ANGLES_FROM_POSITIONS) != 0));
+    const int q1 = (int)((f->par.quirks & RSLAM_Q1_ANGLES_FROM_POSITIONS) != 0);
+    if (N <= 256) {
+        LAUNCH(f, k_ransac_compact_hyp, dim3(1, B), 256, 0, f->dF, q1);
+    } else {
+        LAUNCH(f, k_ransac_compact, dim3(1, B), 256, 0, f->dF);
+        LAUNCH(f, k_ransac_hyp, dim3(cdiv(N, 128), B), 128, 0, f->dF, q1);
+    }
     if (select) {
         LAUNCH(f, k_ransac_support, dim3(cdiv(N, SJT), cdiv(N, SHB), B), SUP_THREADS, kSupSmemBytes, f->dF, f->camd, f->pard, (const int*)nullptr, 0, N, 0, N, (const int*)nullptr,
                (int*)nullptr, (unsigned long long*)nullptr);
