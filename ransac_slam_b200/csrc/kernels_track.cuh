@@ -198,11 +198,18 @@ __device__ __forceinline__ void predict_feature(DevFilter& F, const CamDev& cam,
 
 // fuse_gather (mode 1, single-CTA grids only): the ordered high-innovation inlier list + innovation (gather_inliers, the first step
 // of ekf_update_hi_inliers) is built by the same CTA right behind the gate, saving a dependent launch on the single-filter path.
-__global__ void __launch_bounds__(128) k_predict(DevFilter* Fs, CamDev cam, ParDev par, int mode, int fuse_gather) {
+__device__ __forceinline__ void upd_jnorm_cta(DevFilter& F, const ParDev& par);  // kernels_update.cuh
+// fuse_jnorm (mode 1, single-CTA grids only): the quaternion normalisation that closes the preceding low-innovation update
+// (src/ExtendKF.cpp:611-634) runs at the head of this launch instead of as its own.
+__global__ void __launch_bounds__(128) k_predict(DevFilter* Fs, CamDev cam, ParDev par, int mode, int fuse_gather, int fuse_jnorm) {
     DevFilter& F = Fs[blockIdx.y];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     __shared__ double sPcc[49];
     __shared__ int s_scan[32], s_base;
+    if (fuse_jnorm) {
+        upd_jnorm_cta(F, par);
+        __syncthreads();  // P rows / columns 3..6 and the normalised quaternion are visible to this CTA
+    }
     const int ld = F.ldp;
     if (threadIdx.x < 49) sPcc[threadIdx.x] = F.P[(threadIdx.x / 7) + (size_t)(threadIdx.x % 7) * ld];
     __syncthreads();

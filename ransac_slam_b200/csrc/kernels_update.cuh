@@ -1292,19 +1292,19 @@ __global__ void __launch_bounds__(SR_THREADS, 1) k_syrk_rows(DevFilter* Fs, int 
 // ---- U7: x+ = x + V y is fused into the SYRK kernel (row n of V V^T); the empty-set copy of the prior happens in gather_inliers ----
 
 // ---- U9: quaternion normalisation and its Jacobian applied to P (src/ExtendKF.cpp:611-634).  One CTA per filter. -----------
-__global__ void __launch_bounds__(256) k_upd_jnorm(DevFilter* Fs, ParDev par) {
-    DevFilter& F = Fs[blockIdx.y];
-    if (F.ctl[CTL_K] <= 0) return;  // no measurements: x_k_k = x, p_k_k = P untouched (:635-638)
+// CTA-collective, any block size (every thread of the CTA must call it)
+__device__ __forceinline__ void upd_jnorm_cta(DevFilter& F, const ParDev& par) {
+    if (F.ctl[CTL_K] <= 0) return;  // no measurements: x_k_k = x, p_k_k = P untouched (:635-638); uniform over the CTA
     __shared__ double sJ[16];
     __shared__ double sB[16], sT[16];
     const int ld = F.ldp;
     double* P = F.P;
     const double r = F.x_kk[3], x = F.x_kk[4], y = F.x_kk[5], z = F.x_kk[6];
-    // rows 3..6 of the first 768 columns are fetched now (they do not depend on Jn), so their latency hides behind the serial part
+    // rows 3..6 of the first 3 * blockDim columns are fetched now (they do not depend on Jn): their latency hides behind the serial part
     double v0[3][4];
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-        const int c = threadIdx.x + 256 * k;
+        const int c = threadIdx.x + (int)blockDim.x * k;
 #pragma unroll
         for (int l = 0; l < 4; l++) v0[k][l] = (c < F.n && !(c >= 3 && c < 7)) ? P[(3 + l) + (size_t)c * ld] : 0.0;
     }
@@ -1341,7 +1341,7 @@ __global__ void __launch_bounds__(256) k_upd_jnorm(DevFilter* Fs, ParDev par) {
     }
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-        const int c = threadIdx.x + 256 * k;
+        const int c = threadIdx.x + (int)blockDim.x * k;
         if (c >= F.n || (c >= 3 && c < 7)) continue;
         double o[4];
 #pragma unroll
@@ -1352,7 +1352,7 @@ __global__ void __launch_bounds__(256) k_upd_jnorm(DevFilter* Fs, ParDev par) {
             P[c + (size_t)(3 + i) * ld] = o[i];
         }
     }
-    for (int c = threadIdx.x + 768; c < F.n; c += blockDim.x) {
+    for (int c = threadIdx.x + 3 * (int)blockDim.x; c < F.n; c += blockDim.x) {
         double v[4], o[4];
 #pragma unroll
         for (int l = 0; l < 4; l++) v[l] = P[(3 + l) + (size_t)c * ld];
@@ -1365,5 +1365,7 @@ __global__ void __launch_bounds__(256) k_upd_jnorm(DevFilter* Fs, ParDev par) {
         }
     }
 }
+__global__ void __launch_bounds__(256) k_upd_jnorm(DevFilter* Fs, ParDev par) { upd_jnorm_cta(Fs[blockIdx.y], par); }
+
 
 }  // namespace rslam

@@ -78,6 +78,7 @@ struct rslam_filter {
     bool graph_enabled = true;
     bool capturing = false;
     // side stream for work that is independent of the critical path of a single small filter (W = P H^T beside S + Cholesky)
+    bool jnorm_pending = false;  // rslam_frame only: the li update's k_upd_jnorm was deferred into the next rescue launch
     bool hi_gathered = false;  // the last rslam_rescue_hi also built the hi inlier list (single-CTA grids)
     cudaStream_t side = nullptr;
     // what k_set_inputs last wrote into the device descriptors (rslam_frame skips the launch when unchanged)
@@ -202,7 +203,7 @@ int check_launch() {
     return 0;
 }
 
-int run_update(rslam_filter* f, int which, bool gathered = false) {
+int run_update(rslam_filter* f, int which, bool gathered = false, bool defer_jnorm = false) {
     int rc = ensure_update_ws(f);
     if (rc) return rc;
     const int B = f->B, N = f->hN, n = f->hn;
@@ -273,7 +274,7 @@ int run_update(rslam_filter* f, int which, bool gathered = false) {
             LAUNCH_N(f, "k_gemm_dmma/syrk_P", (k_gemm_dmma<64, 64>), dim3(ts * (ts + 1) / 2, 1, B), (GemmCfg<64, 64>::kThreads), (GemmCfg<64, 64>::kSmemBytes), f->dF, smode, 0);
         }
     }
-    LAUNCH(f, k_upd_jnorm, dim3(1, B), 256, 0, f->dF, f->pard);
+    if (!defer_jnorm) LAUNCH(f, k_upd_jnorm, dim3(1, B), 256, 0, f->dF, f->pard);  // deferred: fused into the head of the rescue kernel
     return check_launch();
 }
 
@@ -716,7 +717,7 @@ int rslam_search_ic_matches(rslam_filter* f) {
     if (!f) return fail(RSLAM_ERR_INVALID, "null handle");
     CK(cudaSetDevice(f->device));
     if (f->hN == 0) return RSLAM_OK;
-    LAUNCH(f, k_predict, dim3(cdiv(f->hN, 128), f->B), 128, 0, f->dF, f->camd, f->pard, 0, 0);
+    LAUNCH(f, k_predict, dim3(cdiv(f->hN, 128), f->B), 128, 0, f->dF, f->camd, f->pard, 0, 0, 0);
     if (f->warp_patches) LAUNCH(f, k_pred_patch, dim3(f->hN, f->B), 192, 0, f->dF, f->camd);
     if (f->have_image) LAUNCH(f, k_search, dim3(f->hN, f->B), kSearchThreads, 0, f->dF, f->camd, f->pard);
     return check_launch();
@@ -785,7 +786,8 @@ int rslam_rescue_hi(rslam_filter* f) {
         int rc = ensure_update_ws(f);  // gather_inliers writes the innovation into W
         if (rc) return rc;
     }
-    LAUNCH(f, k_predict, dim3(cdiv(f->hN, 128), f->B), 128, 0, f->dF, f->camd, f->pard, 1, fuse);
+    LAUNCH(f, k_predict, dim3(cdiv(f->hN, 128), f->B), 128, 0, f->dF, f->camd, f->pard, 1, fuse, (fuse && f->jnorm_pending) ? 1 : 0);
+    f->jnorm_pending = false;
     f->hi_gathered = fuse != 0;
     return check_launch();
 }
@@ -841,7 +843,10 @@ static int run_frame_stages(rslam_filter* f, int flags) {
     if ((rc = rslam_search_ic_matches(f))) return rc;
     if ((rc = ensure_update_ws(f))) return rc;
     if ((rc = run_ransac_core(f, true, true))) return rc;
-    if ((rc = run_update(f, 0, true))) return rc;
+    // single-CTA rescue kernel: the li update's closing quaternion normalisation rides at its head (one dependent launch less)
+    const bool defer = cdiv(f->hN, 128) == 1 && f->hN > 0;
+    if ((rc = run_update(f, 0, true, defer))) return rc;
+    f->jnorm_pending = defer;
     if ((rc = rslam_rescue_hi(f))) return rc;
     const bool gathered = f->hi_gathered;
     f->hi_gathered = false;
