@@ -391,8 +391,8 @@ def bench_c2(args, world, rank, local):
     else:
         roof.update(bound="hbm", achieved=(amount or 0.0) / (per_launch_us * 1e-6) / 1e9, peak=pk["hbm_gbs"], unit="GB/s", note="peak: " + pk["source"])
     roof["frac"] = roof["achieved"] / roof["peak"] if roof.get("peak") else None
-    # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (profiles/r01_s4_chol_small_c2.md)
-    roof["traffic"] = {"k_chol_small": 160512}.get(top)
+    # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (profiles/r01_s5_chol_small_c2.md)
+    roof["traffic"] = {"k_chol_small": 158208}.get(top)
     roof["launch_us"] = per_launch_us
     # ---- end to end: host (pinned) inputs copied in, pose copied out, every frame -------------------------------------
     ge = new_gpu_filter(scene, device=local)
