@@ -209,6 +209,34 @@ __device__ __forceinline__ void distort_fast_dev(const CamDev& cam, double u, do
     vd = yu * iD / cam.dy + cam.Cy;
 }
 
+// distort_fm for the latency path (one call per feature, on a kernel that is a single dependent chain per thread): the Newton
+// iteration of src/ExtendKF.cpp:191-196 converges to a fixed point of its update in 3-5 steps and the reference's remaining steps
+// leave rd unchanged, so iterating until rd stops changing (at most the reference's 10 steps) returns the same rd -- up to the last
+// bit where the reciprocal-based step and the reference's division round differently (|d rd| <= 1 ulp, far inside the 1e-9 bar).
+// The final undistorted -> distorted scaling keeps the reference's exact divisions.
+__device__ __forceinline__ void distort_fixpoint_dev(const CamDev& cam, double u, double v, double& ud, double& vd) {
+    const double xu = (u - cam.Cx) * cam.dx;
+    const double yu = (v - cam.Cy) * cam.dy;
+    const double ru = sqrt(xu * xu + yu * yu);
+    const double ru2 = ru * ru;
+    double rd = ru * fast_rcp(1 + cam.k1 * ru2 + cam.k2 * (ru2 * ru2));
+#pragma unroll 1
+    for (int k = 0; k < 10; k++) {
+        const double rd2 = rd * rd;
+        const double rd4 = rd2 * rd2;
+        const double f = rd + cam.k1 * (rd2 * rd) + cam.k2 * (rd4 * rd) - ru;
+        const double fp = 1 + 3 * cam.k1 * rd2 + 5 * cam.k2 * rd4;
+        const double rn = fma(-f, fast_rcp(fp), rd);
+        const bool same = !(rn != rd);
+        rd = rn;
+        if (same) break;
+    }
+    const double rd2 = rd * rd;
+    const double D = 1 + cam.k1 * rd2 + cam.k2 * (rd2 * rd2);
+    ud = xu / D / cam.dx + cam.Cx;
+    vd = yu / D / cam.dy + cam.Cy;
+}
+
 // Jacobian of the undistortion (src/ExtendKF.cpp:312-332), row-major 2x2
 __device__ __forceinline__ void jacob_undistort_dev(const CamDev& cam, double ud, double vd, double J[4]) {
     const double a = ud - cam.Cx, b = vd - cam.Cy;
