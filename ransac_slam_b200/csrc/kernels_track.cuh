@@ -125,12 +125,30 @@ __global__ void __launch_bounds__(128) k_ekf_prediction(DevFilter* Fs, ParDev pa
     __shared__ double sF[169], sQ[169], sX[13], sP[169], sT[169];
     const int n = F.n;
     if (blockIdx.x * blockDim.x >= (unsigned)n && blockIdx.x != 0) return;
+    // everything this thread reads from P is fetched before F and Q are built (none of it depends on them): the loads fly while
+    // thread 0 runs the serial quaternion part
+    const int ld = F.ldp;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    double v[13];
+#pragma unroll
+    for (int c = 0; c < 13; c++) v[c] = (j >= 13 && j < n) ? F.P[j + (size_t)c * ld] : 0.0;  // row j (== column j by symmetry), coalesced
+    double pcam[2] = {0.0, 0.0};
+    if (blockIdx.x == 0) {
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int e = threadIdx.x + u * 128;
+            if (e < 169) pcam[u] = F.P[(e / 13) + (size_t)(e % 13) * ld];
+        }
+    }
     build_F_Q(F.x_kk, par, sF, sQ, sX, sT);  // sT doubles as the 13 x 6 scratch for G (free until the camera block below)
     __syncthreads();
-    const int ld = F.ldp;
     if (blockIdx.x == 0) {
         // camera block: F Pcc F^T + Q  (left to right)
-        for (int e = threadIdx.x; e < 169; e += blockDim.x) sP[e] = F.P[(e / 13) + (size_t)(e % 13) * ld];
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int e = threadIdx.x + u * 128;
+            if (e < 169) sP[e] = pcam[u];
+        }
         __syncthreads();
         for (int e = threadIdx.x; e < 169; e += blockDim.x) {
             const int i = e / 13, j = e % 13;
@@ -150,7 +168,6 @@ __global__ void __launch_bounds__(128) k_ekf_prediction(DevFilter* Fs, ParDev pa
         }
         if (threadIdx.x < 13) F.x_km1[threadIdx.x] = sX[threadIdx.x];
     }
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (with_begin && j < F.N) {  // Map::map_management step 2 (src/Map.cpp:34-55): counters + per-frame flag reset
         if (F.has_h[j]) F.times_predicted[j] += 1;
         if (F.li[j] || F.hi[j]) F.times_measured[j] += 1;
@@ -161,9 +178,7 @@ __global__ void __launch_bounds__(128) k_ekf_prediction(DevFilter* Fs, ParDev pa
     }
     if (j >= 13 && j < n) {
         F.x_km1[j] = F.x_kk[j];
-        double v[13], o[13];
-#pragma unroll
-        for (int c = 0; c < 13; c++) v[c] = F.P[j + (size_t)c * ld];  // row j (== column j by symmetry), coalesced
+        double o[13];
 #pragma unroll
         for (int i = 0; i < 13; i++) {
             double s = 0;
