@@ -157,6 +157,32 @@ int rslam_support_sweep(rslam_filter* f, const int* hyp_match_idx, int n_hyp, in
 /* inlier mask of one hypothesis id after a sweep that covered it (for the rank that owns the all-reduced winner) */
 int rslam_sweep_mask(rslam_filter* f, int match_idx, uint8_t* mask);
 
+/* --- the sweep sharded over GPUs: NCCL inside the library, on the handles' own streams ------------------------------
+ * Every GPU holds a replica of (x_k_km1, P, matches) in its own handle and scores a shard of the hypothesis list; one MAX all-reduce of
+ * the packed 8-byte key gives every rank the winner (highest support, ties -> lowest hypothesis id, the reference's strict '>' at
+ * src/Tracking.cpp:507), and, when the mask is wanted, the rank that scored the winner hands its inlier mask to all ranks (a second,
+ * ceil(m/32)-word all-reduce whose root is resolved on the device: no host round trip between the two).  NCCL (libnccl.so.2) is loaded
+ * at the first rslam_comm_* call; the rest of the library works without it. */
+typedef struct rslam_comm rslam_comm; /* opaque */
+/* single process driving ndev local GPUs (ncclCommInitAll): local rank i = CUDA device devs[i] (devs == NULL: 0 .. ndev-1) */
+int rslam_comm_init(int ndev, const int* devs, rslam_comm** out);
+/* one process per GPU: rank 0 obtains a 128-byte id (rslam_comm_unique_id), every rank receives it by any means (MPI, a file,
+ * torch.distributed) and calls rslam_comm_init_rank (collective) */
+int rslam_comm_unique_id(void* id128);
+int rslam_comm_init_rank(int nranks, int rank, const void* id128, int device, rslam_comm** out);
+int rslam_comm_destroy(rslam_comm* c);
+int rslam_comm_size(const rslam_comm* c);       /* ranks in the communicator */
+int rslam_comm_local_size(const rslam_comm* c); /* GPUs driven by this process */
+#define RSLAM_SHARD_BY_HYPOTHESIS 0 /* contiguous hypothesis-id ranges: every hypothesis scored ("no reuse" convention) */
+#define RSLAM_SHARD_BY_MATCH 1      /* contiguous match-index ranges: with dedupe_hypotheses each distinct hypothesis is scored once, on one GPU */
+/* filters[rslam_comm_local_size]: one batch-1 handle per local GPU, created on that GPU, all holding the same state and matches.
+ * hyp_match_idx[n_hyp]: host memory, or device memory readable by every local GPU.  best_key: host (the call returns after the result
+ * has arrived) or, with one local GPU, device memory (the call only enqueues: the key is valid in stream order).  best_mask (host,
+ * optional): the winner's inlier bit per matched feature, ceil(m/8) bytes.  n_pairs_scored (host, optional): pairs scored by the local
+ * GPUs. */
+int rslam_support_sweep_multi(rslam_comm* c, rslam_filter* const* filters, const int* hyp_match_idx, int n_hyp, int shard, uint64_t* best_key,
+                              uint8_t* best_mask, long long* n_pairs_scored);
+
 /* --- map management with the covariance resident on the device (src/Map.cpp) -------------------------- */
 /* All of these act on x_k_k / p_k_k of filter b, like the reference between two frames (src/System.cpp:111).  Each rewrites the
  * covariance once, out of place, into a spare buffer owned by the handle and swaps the two (16 n^2 bytes of HBM traffic). */

@@ -42,6 +42,8 @@ EXPORTS = [
     "rslam_download_features", "rslam_upload_feature_init", "rslam_set_patch_warp", "rslam_download_patches", "rslam_debug_scratch", "rslam_download_H", "rslam_set_matches", "rslam_set_image", "rslam_begin_frame", "rslam_ekf_prediction",
     "rslam_search_ic_matches", "rslam_ransac_hypotheses", "rslam_ransac_result_get", "rslam_update_li", "rslam_rescue_hi", "rslam_update_hi",
     "rslam_frame", "rslam_set_graph", "rslam_profile_enable", "rslam_profile_read", "rslam_download_pose", "rslam_support_sweep", "rslam_sweep_mask",
+    "rslam_comm_init", "rslam_comm_unique_id", "rslam_comm_init_rank", "rslam_comm_destroy", "rslam_comm_size", "rslam_comm_local_size",
+    "rslam_support_sweep_multi",
 ]
 
 _lib = None
@@ -90,6 +92,13 @@ def load():
     L.rslam_profile_read.argtypes = [vp, C.c_char_p, C.c_size_t]
     L.rslam_support_sweep.argtypes = [vp, vp, ci, ci, ci, ci, ci, vp, vp, vp]
     L.rslam_sweep_mask.argtypes = [vp, ci, vp]
+    L.rslam_comm_init.argtypes = [ci, vp, C.POINTER(vp)]
+    L.rslam_comm_unique_id.argtypes = [vp]
+    L.rslam_comm_init_rank.argtypes = [ci, ci, vp, ci, C.POINTER(vp)]
+    L.rslam_comm_destroy.argtypes = [vp]
+    L.rslam_comm_size.argtypes = [vp]
+    L.rslam_comm_local_size.argtypes = [vp]
+    L.rslam_support_sweep_multi.argtypes = [vp, vp, vp, ci, ci, vp, vp, vp]
     L.rslam_map_delete_feature.argtypes = [vp, ci, ci]
     L.rslam_map_delete_features.argtypes = [vp, ci, ci, vp]
     L.rslam_map_inversedepth_to_cartesian.argtypes = [vp, ci, vp]
@@ -409,3 +418,87 @@ class Filter:
 
 def decode_key(key):
     return int(key >> 32), int(0xFFFFFFFF - (key & 0xFFFFFFFF))
+
+
+SHARD_BY_HYPOTHESIS = 0
+SHARD_BY_MATCH = 1
+
+
+class Comm:
+    """NCCL communicator(s) of the sharded sweep, owned by the library (rslam_comm_*)."""
+
+    def __init__(self, handle):
+        self.L = load()
+        self.h = handle
+
+    @staticmethod
+    def _ck(L, rc):
+        if rc != 0:
+            raise RslamError(f"rslam error {rc}: {L.rslam_last_error().decode()}")
+
+    @classmethod
+    def single_process(cls, devices):
+        """one host thread driving len(devices) GPUs (ncclCommInitAll)"""
+        L = load()
+        devs = np.ascontiguousarray(devices, dtype=np.int32)
+        h = C.c_void_p()
+        cls._ck(L, L.rslam_comm_init(devs.size, _p(devs), C.byref(h)))
+        return cls(h)
+
+    @staticmethod
+    def unique_id():
+        L = load()
+        buf = np.zeros(128, dtype=np.uint8)
+        Comm._ck(L, L.rslam_comm_unique_id(_p(buf)))
+        return buf
+
+    @classmethod
+    def from_rank(cls, nranks, rank, uid, device):
+        """one process per GPU: uid = the 128 bytes rank 0 obtained from unique_id(), delivered by the caller"""
+        L = load()
+        uid = np.ascontiguousarray(uid, dtype=np.uint8)
+        assert uid.size == 128
+        h = C.c_void_p()
+        cls._ck(L, L.rslam_comm_init_rank(nranks, rank, _p(uid), device, C.byref(h)))
+        return cls(h)
+
+    @property
+    def size(self):
+        return self.L.rslam_comm_size(self.h)
+
+    @property
+    def local_size(self):
+        return self.L.rslam_comm_local_size(self.h)
+
+    def support_sweep(self, filters, hyp_idx, shard=SHARD_BY_MATCH, want_mask=True, key_device_ptr=None, n_hyp=None, want_pairs=False):
+        """filters: list of Filter (one per local GPU).  hyp_idx: int32 host array or device pointer (int, with n_hyp).
+        Returns (key, mask bits or None, pairs scored locally or None); with key_device_ptr the call only enqueues and returns None."""
+        arr = (C.c_void_p * len(filters))(*[f.h for f in filters])
+        if isinstance(hyp_idx, int):
+            hp = C.c_void_p(hyp_idx)
+            assert n_hyp is not None
+        else:
+            hi = np.ascontiguousarray(hyp_idx, dtype=np.int32)
+            n_hyp = hi.size
+            hp = _p(hi)
+            self._keep = hi
+        if key_device_ptr is not None:
+            self._ck(self.L, self.L.rslam_support_sweep_multi(self.h, arr, hp, n_hyp, shard, C.c_void_p(key_device_ptr), None, None))
+            return None
+        key = np.zeros(1, dtype=np.uint64)
+        pairs = C.c_longlong(0)
+        mask = np.zeros((filters[0].max_features + 7) // 8, dtype=np.uint8) if want_mask else None
+        self._ck(self.L, self.L.rslam_support_sweep_multi(self.h, arr, hp, n_hyp, shard, _p(key), _p(mask), C.byref(pairs) if want_pairs else None))
+        bits = np.unpackbits(mask, bitorder="little").astype(bool) if want_mask else None
+        return int(key[0]), bits, (int(pairs.value) if want_pairs else None)
+
+    def close(self):
+        if self.h:
+            self.L.rslam_comm_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

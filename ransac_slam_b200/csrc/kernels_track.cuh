@@ -289,8 +289,16 @@ __device__ __forceinline__ void predict_feature(DevFilter& F, const CamDev& cam,
         distort_fixpoint_dev(cam, uu, vu, hd[0], hd[1]);
         vis = (hd[0] > 0) && (hd[0] < cam.nCols) && (hd[1] > 0) && (hd[1] < cam.nRows);
     }
+    // calculate_derivatives (src/Tracking.cpp:540-573) rebuilds H_i at THIS state for every feature whose h is non-empty -- also for a
+    // feature that fails the gates now but still carries the h of an earlier prediction (predict_camera_measurements leaves it in
+    // place, src/ExtendKF.cpp:77-78): its Jacobian is taken at the new state with zi = the stale h.
+    const bool have = vis || F.has_h[i];
+    if (!vis && have) {
+        hd[0] = F.h[2 * i];
+        hd[1] = F.h[2 * i + 1];
+    }
     double Hc[14], Hf[12];
-    if (vis) {
+    if (have) {
         // Jacobian at zi = h
         double Ju[4];
         jacob_undistort_dev(cam, hd[0], hd[1], Ju);
@@ -350,9 +358,11 @@ __device__ __forceinline__ void predict_feature(DevFilter& F, const CamDev& cam,
         for (int a = 0; a < 2; a++)
 #pragma unroll
             for (int c = 0; c < 6; c++) Hf[a * 6 + c] = A[a * 3] * c0[c] + A[a * 3 + 1] * c0[6 + c] + A[a * 3 + 2] * c0[12 + c];
-        F.has_h[i] = 1;
-        F.h[2 * i] = hd[0];
-        F.h[2 * i + 1] = hd[1];
+        if (vis) {
+            F.has_h[i] = 1;
+            F.h[2 * i] = hd[0];
+            F.h[2 * i + 1] = hd[1];
+        }
 #pragma unroll
         for (int e = 0; e < 14; e++) F.Hc[14 * i + e] = Hc[e];
 #pragma unroll
@@ -360,10 +370,10 @@ __device__ __forceinline__ void predict_feature(DevFilter& F, const CamDev& cam,
     }
     bool need_S;
     if (mode == 0) {
-        need_S = vis;
+        need_S = have;  // every feature with a non-empty h (src/Tracking.cpp:41)
     } else {
         need_S = F.ic[i] && !F.li[i];
-        if (need_S && !vis) {  // stale linearisation from x_k_km1 stays in force (src/ExtendKF.cpp:77-78)
+        if (need_S && !have) {  // a match injected without any prediction (rslam_set_matches): whatever the arrays hold
 #pragma unroll
             for (int e = 0; e < 14; e++) Hc[e] = F.Hc[14 * i + e];
 #pragma unroll
@@ -958,7 +968,10 @@ __global__ void __launch_bounds__(256) k_ransac_compact(DevFilter* Fs) { ransac_
 
 // c.2 one thread per distinct 1-point hypothesis t (match p = ic_list[t]): partial EKF state update restricted to the camera
 //     (src/Tracking.cpp:419-422):  g = S_p^-1 (z_p - h_p);  a = Hc_p^T g;  b = Hf_p^T g;  x_i[0..6] = x[0..6] + P[0..6,nz] [a;b]
-__device__ __forceinline__ void ransac_hyp_thread(DevFilter& F, int q1, int t, int nthreads) {
+// tid / nthreads index the tile-ordered row table (always built in full); the hypothesis handled by this thread is t_lo + tid,
+// restricted to [t_lo, t_hi) -- a sweep sharded by match index only needs the constants of its own distinct hypotheses.
+__device__ __forceinline__ void ransac_hyp_thread(DevFilter& F, int q1, int tid_, int nthreads, int t_lo = 0, int t_hi = 0x7fffffff) {
+    int t = tid_;
     // state rows read by the support-scoring tiles, in tile order (one coalesced load per thread there instead of a dependent
     // id_list -> foff chain): kSupTile matches per tile, 6 rows per match, spread over the whole grid.  Quirk Q1 (reference): 3
     // position rows + rho per match, and the two "angle" rows are entries (2jj, 2jj+1) of the stacked POSITION vector of all matches.
@@ -1007,7 +1020,8 @@ __device__ __forceinline__ void ransac_hyp_thread(DevFilter& F, int q1, int t, i
             }
         }
     }
-    if (t >= F.ctl[CTL_NIC]) return;
+    t = t_lo + tid_;
+    if (t >= F.ctl[CTL_NIC] || t >= t_hi) return;
     const int p = F.ic_list[t];
     const int off = F.foff[p];
     const int fs = F.ftype[p] == 0 ? 6 : 3;
@@ -1398,14 +1412,45 @@ __global__ void __launch_bounds__(256) k_sweep_reduce(DevFilter* Fs, const int* 
     if ((threadIdx.x & 31) == 0 && best) atomicMax(out_key, best);
 }
 
-// mark which distinct hypotheses are referenced by hyp_idx[h0, h1) (dedupe), then compact them
-__global__ void k_sweep_mark(DevFilter* Fs, const int* hyp_idx, int h0, int h1, int t_lo, int t_hi, int* used) {
+// sweep set-up in two launches instead of five (the fixed per-sweep cost is what limits the sharded sweep's scaling):
+//   k_sweep_compact : ordered match lists (k_ransac_compact) + zeroing of the dedupe marks and of the key / pair counter
+//   k_sweep_prep    : blocks [0, nb_hyp) build the hypothesis constants of the distinct hypotheses [t_lo, t_hi) and the row table;
+//                     the remaining blocks mark which distinct hypotheses the id range [h0, h1) references (k_sweep_mark)
+__global__ void __launch_bounds__(256) k_sweep_compact(DevFilter* Fs, int* used, int n_used, unsigned long long* key2) {
+    ransac_compact_cta(Fs[0]);
+    for (int i = threadIdx.x; i < n_used; i += blockDim.x) used[i] = 0;
+    if (threadIdx.x < 2) key2[threadIdx.x] = 0ull;
+}
+__global__ void __launch_bounds__(128) k_sweep_prep(DevFilter* Fs, int q1, int t_lo, int t_hi, int nb_hyp, const int* hyp_idx, int h0, int h1, int m_lo, int m_hi,
+                                                    int* used) {
     DevFilter& F = Fs[0];
-    const int nIC = min(F.ctl[CTL_NIC], t_hi);
-    for (int i = h0 + blockIdx.x * blockDim.x + threadIdx.x; i < h1; i += gridDim.x * blockDim.x) {
-        const int t = hyp_idx[i];
-        if (t >= t_lo && t < nIC) used[t] = 1;
+    if ((int)blockIdx.x < nb_hyp) {
+        ransac_hyp_thread(F, q1, blockIdx.x * blockDim.x + threadIdx.x, nb_hyp * blockDim.x, t_lo, t_hi);
+        return;
     }
+    if (!used) return;
+    const int nIC = min(F.ctl[CTL_NIC], m_hi);
+    const int nb = gridDim.x - nb_hyp;
+    for (int i = h0 + (blockIdx.x - nb_hyp) * blockDim.x + threadIdx.x; i < h1; i += nb * blockDim.x) {
+        const int t = hyp_idx[i];
+        if (t >= m_lo && t < nIC) used[t] = 1;
+    }
+}
+// After the MAX all-reduce of the key every rank knows the winner; the rank that scored it (its inlier mask row is valid) publishes the
+// mask words, every other rank zeros -- a MAX all-reduce of the words then hands the mask to everybody without a host round trip
+// (the "broadcast from the owner" of SURVEY 8e with the root resolved on the device).
+__global__ void k_sweep_winner_mask(DevFilter* Fs, const unsigned long long* key, const int* hyp_idx, int h0, int h1, int m_lo, int m_hi, unsigned* out_words, int nwords) {
+    DevFilter& F = Fs[0];
+    const unsigned long long k = *key;
+    bool mine = false;
+    int t = -1;
+    if (k != 0ull) {
+        const int id = (int)(0xFFFFFFFFu - (unsigned)(k & 0xFFFFFFFFull));
+        t = hyp_idx[id];
+        mine = id >= h0 && id < h1 && t >= m_lo && t < min(F.ctl[CTL_NIC], m_hi);
+    }
+    for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += gridDim.x * blockDim.x)
+        out_words[w] = (mine && w < F.mwords) ? F.masks[(size_t)t * F.mwords + w] : 0u;
 }
 
 }  // namespace rslam

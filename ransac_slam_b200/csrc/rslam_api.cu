@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <dlfcn.h>
 #include <string>
 #include <vector>
 
@@ -343,19 +344,28 @@ int rslam_create(const rslam_camera* cam, const rslam_params* par, int max_featu
     f->camd = CamDev{cam->k1, cam->k2, cam->Cx, cam->Cy, cam->f, cam->dx, cam->dy, cam->f * (1.0 / cam->dx), cam->f * (1.0 / cam->dy), cam->nRows, cam->nCols};
     f->pard = ParDev{f->par.std_z, f->par.chi2_095_2, f->par.corr_threshold, f->par.p_spurious_free, f->par.max_ellipse_eig,
                      (f->par.std_a * 1.0) * (f->par.std_a * 1.0), (f->par.std_alpha * 1.0) * (f->par.std_alpha * 1.0), f->par.n_hyp_initial, f->par.quirks};
-    CK(cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&f->side, cudaStreamNonBlocking));
-    CK(cudaEventCreateWithFlags(&f->ev_fork, cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&f->ev_join, cudaEventDisableTiming));
-    CK(cudaFuncSetAttribute(k_gemm_dmma<128, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<128, 64>::kSmemBytes));
-    CK(cudaFuncSetAttribute(k_gemm_dmma<64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<64, 64>::kSmemBytes));
-    CK(cudaFuncSetAttribute(k_trsm_ll<48, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TrsmCfg<48, 2>::kSmemBytes));
-    CK(cudaFuncSetAttribute(k_trsm_ll<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TrsmCfg<32, 2>::kSmemBytes));
-    CK(cudaFuncSetAttribute(k_ransac_support, cudaFuncAttributeMaxDynamicSharedMemorySize, kSupSmemBytes));
-    CK(cudaFuncSetAttribute(k_chol_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPanelSmemBytes));
-    CK(cudaFuncSetAttribute(k_chol_small, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholSmallSmemBytes));
-    CK(cudaFuncSetAttribute(k_trsm_small, cudaFuncAttributeMaxDynamicSharedMemorySize, trsm_small_smem_bytes(SR_KMAX)));
-    CK(cudaFuncSetAttribute(k_syrk_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, syrk_rows_smem_bytes(SR_KMAX)));
+    // a failure from here on releases the handle, its streams and its events (rslam_destroy copes with a half-built handle)
+#define CKF(call)                                                                                                         \
+    do {                                                                                                                  \
+        cudaError_t e__ = (call);                                                                                         \
+        if (e__ != cudaSuccess) {                                                                                         \
+            rslam_destroy(f);                                                                                             \
+            return fail(RSLAM_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__);     \
+        }                                                                                                                 \
+    } while (0)
+    CKF(cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking));
+    CKF(cudaStreamCreateWithFlags(&f->side, cudaStreamNonBlocking));
+    CKF(cudaEventCreateWithFlags(&f->ev_fork, cudaEventDisableTiming));
+    CKF(cudaEventCreateWithFlags(&f->ev_join, cudaEventDisableTiming));
+    CKF(cudaFuncSetAttribute(k_gemm_dmma<128, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<128, 64>::kSmemBytes));
+    CKF(cudaFuncSetAttribute(k_gemm_dmma<64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<64, 64>::kSmemBytes));
+    CKF(cudaFuncSetAttribute(k_trsm_ll<48, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TrsmCfg<48, 2>::kSmemBytes));
+    CKF(cudaFuncSetAttribute(k_trsm_ll<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TrsmCfg<32, 2>::kSmemBytes));
+    CKF(cudaFuncSetAttribute(k_ransac_support, cudaFuncAttributeMaxDynamicSharedMemorySize, kSupSmemBytes));
+    CKF(cudaFuncSetAttribute(k_chol_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPanelSmemBytes));
+    CKF(cudaFuncSetAttribute(k_chol_small, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholSmallSmemBytes));
+    CKF(cudaFuncSetAttribute(k_trsm_small, cudaFuncAttributeMaxDynamicSharedMemorySize, trsm_small_smem_bytes(SR_KMAX)));
+    CKF(cudaFuncSetAttribute(k_syrk_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, syrk_rows_smem_bytes(SR_KMAX)));
 
     const int B = batch, N = max_features, n = f->nmax;
     f->hF.assign(B, DevFilter{});
@@ -440,7 +450,8 @@ int rslam_create(const rslam_camera* cam, const rslam_params* par, int max_featu
         rslam_destroy(f);
         return rc;
     }
-    CK(cudaStreamSynchronize(f->stream));
+    CKF(cudaStreamSynchronize(f->stream));
+#undef CKF
     *out = f;
     return RSLAM_OK;
 }
@@ -491,6 +502,8 @@ int rslam_upload_state(rslam_filter* f, int b, int which, const double* x, const
         off += types[i] == 0 ? 6 : 3;
     }
     if (off != n) return fail(RSLAM_ERR_INVALID, "rslam_upload_state: n = %d does not match 13 + sum(feature sizes) = %d", n, off);
+    if (P && ldp < n) return fail(RSLAM_ERR_INVALID, "rslam_upload_state: ldp < n");
+    if (which != 0 && which != 1) return fail(RSLAM_ERR_INVALID, "rslam_upload_state: which must be 0 (x_k_k) or 1 (x_k_km1)");
     DevFilter& D = f->hF[b];
     f->htype[b] = types;
     const bool shape_changed = (D.n != n) || (D.N != N);
@@ -508,7 +521,6 @@ int rslam_upload_state(rslam_filter* f, int b, int which, const double* x, const
     }
     CK(cudaMemcpyAsync(which ? D.x_km1 : D.x_kk, x, sizeof(double) * n, cudaMemcpyDefault, f->stream));
     if (P) {
-        if (ldp < n) return fail(RSLAM_ERR_INVALID, "rslam_upload_state: ldp < n");
         CK(cudaMemcpy2DAsync(D.P, sizeof(double) * f->ldp, P, sizeof(double) * ldp, sizeof(double) * n, n, cudaMemcpyDefault, f->stream));
     }
     if (shape_changed) {
@@ -990,51 +1002,76 @@ int rslam_profile_read(rslam_filter* f, char* buf, size_t buflen) {
     return RSLAM_OK;
 }
 
-int rslam_support_sweep(rslam_filter* f, const int* hyp_match_idx, int n_hyp, int hyp_begin, int hyp_end, int match_begin, int match_end,
-                        uint64_t* best_key, uint8_t* best_mask, long long* n_pairs_scored) {
-    if (!f || !hyp_match_idx || n_hyp <= 0 || hyp_begin < 0 || hyp_end > n_hyp || hyp_begin > hyp_end || match_begin < 0 || match_end < match_begin || !best_key)
-        return fail(RSLAM_ERR_INVALID, "rslam_support_sweep: bad arguments");
-    CK(cudaSetDevice(f->device));
+// enqueue one (shard of a) sweep on the handle's stream; the packed key lands in f->d_key[0], the pair count in f->d_key[1]
+static int sweep_local(rslam_filter* f, const int* hyp_match_idx, int n_hyp, int hyp_begin, int hyp_end, int match_begin, int match_end, const int** d_idx_out) {
     const int N = f->hN;
     if (N == 0) return fail(RSLAM_ERR_INVALID, "rslam_support_sweep: no features uploaded");
+    if (f->B != 1) return fail(RSLAM_ERR_INVALID, "rslam_support_sweep: the sweep acts on a single filter (batch == 1)");
     int rc;
     const int* d_idx = hyp_match_idx;
     if (!is_device_ptr(hyp_match_idx)) {
         if ((size_t)n_hyp > f->hyp_cap) {
             if (f->d_hyp_idx) CK(cudaFree(f->d_hyp_idx));
+            f->d_hyp_idx = nullptr;
+            f->hyp_cap = 0;
             CK(cudaMalloc((void**)&f->d_hyp_idx, sizeof(int) * (size_t)n_hyp));
             f->hyp_cap = n_hyp;
         }
         CK(cudaMemcpyAsync(f->d_hyp_idx + hyp_begin, hyp_match_idx + hyp_begin, sizeof(int) * (size_t)(hyp_end - hyp_begin), cudaMemcpyHostToDevice, f->stream));
         d_idx = f->d_hyp_idx;
     }
-    if ((rc = run_ransac_core(f, false))) return rc;
-    CK(cudaMemsetAsync(f->d_key, 0, 2 * sizeof(unsigned long long), f->stream));
+    if (d_idx_out) *d_idx_out = d_idx;
+    const int q1 = (int)((f->par.quirks & RSLAM_Q1_ANGLES_FROM_POSITIONS) != 0);
     const int nh = hyp_end - hyp_begin;
+    const bool dedupe = f->par.dedupe_hypotheses != 0;
+    const int tlo = match_begin < N ? match_begin : N, thi = match_end < N ? match_end : N;
+    // launch 1: ordered match lists; zeroes the dedupe marks, the key and the pair counter
+    LAUNCH(f, k_sweep_compact, 1, 256, 0, f->dF, f->d_used, f->Nmax, f->d_key);
+    // launch 2: hypothesis constants of the distinct hypotheses this shard can score + the row table + the dedupe marks
+    {
+        const int nt = dedupe ? (thi - tlo) : N;
+        int nb_hyp = cdiv(nt > 0 ? nt : 1, 128);
+        const int nb_tab = cdiv(cdiv(N, kSupTile) * 6 * kSupTile, 4 * 128);  // four table entries per thread
+        if (nb_hyp < (nb_tab < 148 ? nb_tab : 148)) nb_hyp = nb_tab < 148 ? nb_tab : 148;  // enough threads for the row table
+        int nb_mark = 0;
+        if (dedupe && nh > 0) nb_mark = cdiv(nh, 4 * 128) < 592 ? cdiv(nh, 4 * 128) : 592;
+        LAUNCH(f, k_sweep_prep, nb_hyp + nb_mark, 128, 0, f->dF, q1, dedupe ? tlo : 0, dedupe ? thi : N, nb_hyp, d_idx, hyp_begin, hyp_end, match_begin, match_end,
+               nb_mark ? f->d_used : (int*)nullptr);
+    }
     if (nh > 0) {
-        if (f->par.dedupe_hypotheses) {
-            CK(cudaMemsetAsync(f->d_used, 0, sizeof(int) * (size_t)f->Nmax, f->stream));
-            const int tlo = match_begin < N ? match_begin : N, thi = match_end < N ? match_end : N;
-            LAUNCH(f, k_sweep_mark, cdiv(nh, 256) < 1024 ? cdiv(nh, 256) : 1024, 256, 0, f->dF, d_idx, hyp_begin, hyp_end, match_begin, match_end, f->d_used);
+        if (dedupe) {
             if (thi > tlo)
                 LAUNCH(f, k_ransac_support, dim3(cdiv(N, SJT), cdiv(thi - tlo, SHB), 1), SUP_THREADS, kSupSmemBytes, f->dF, f->camd, f->pard, (const int*)nullptr, tlo, thi, tlo, thi,
                        (const int*)f->d_used, (int*)nullptr, f->d_key + 1);
-            LAUNCH(f, k_sweep_reduce, cdiv(nh, 256) < 512 ? cdiv(nh, 256) : 512, 256, 0, f->dF, d_idx, hyp_begin, hyp_end, match_begin, match_end, (const int*)nullptr,
+            LAUNCH(f, k_sweep_reduce, cdiv(nh, 4 * 256) < 296 ? cdiv(nh, 4 * 256) : 296, 256, 0, f->dF, d_idx, hyp_begin, hyp_end, match_begin, match_end, (const int*)nullptr,
                    f->d_key);
         } else {
             if ((size_t)n_hyp > f->sup_h_cap) {
                 if (f->d_sup_h) CK(cudaFree(f->d_sup_h));
+                f->d_sup_h = nullptr;
+                f->sup_h_cap = 0;
                 CK(cudaMalloc((void**)&f->d_sup_h, sizeof(int) * (size_t)n_hyp));
                 f->sup_h_cap = n_hyp;
             }
             CK(cudaMemsetAsync(f->d_sup_h + hyp_begin, 0, sizeof(int) * (size_t)nh, f->stream));
             LAUNCH(f, k_ransac_support, dim3(cdiv(N, SJT), cdiv(nh, SHB), 1), SUP_THREADS, kSupSmemBytes, f->dF, f->camd, f->pard, d_idx, hyp_begin, hyp_end, match_begin, match_end,
                    (const int*)nullptr, f->d_sup_h, f->d_key + 1);
-            LAUNCH(f, k_sweep_reduce, cdiv(nh, 256) < 512 ? cdiv(nh, 256) : 512, 256, 0, f->dF, d_idx, hyp_begin, hyp_end, match_begin, match_end, (const int*)f->d_sup_h,
+            LAUNCH(f, k_sweep_reduce, cdiv(nh, 4 * 256) < 296 ? cdiv(nh, 4 * 256) : 296, 256, 0, f->dF, d_idx, hyp_begin, hyp_end, match_begin, match_end, (const int*)f->d_sup_h,
                    f->d_key);
         }
     }
-    if ((rc = check_launch())) return rc;
+    (void)rc;
+    return check_launch();
+}
+
+int rslam_support_sweep(rslam_filter* f, const int* hyp_match_idx, int n_hyp, int hyp_begin, int hyp_end, int match_begin, int match_end,
+                        uint64_t* best_key, uint8_t* best_mask, long long* n_pairs_scored) {
+    if (!f || !hyp_match_idx || n_hyp <= 0 || hyp_begin < 0 || hyp_end > n_hyp || hyp_begin > hyp_end || match_begin < 0 || match_end < match_begin || !best_key)
+        return fail(RSLAM_ERR_INVALID, "rslam_support_sweep: bad arguments");
+    CK(cudaSetDevice(f->device));
+    int rc;
+    const int* d_idx = nullptr;
+    if ((rc = sweep_local(f, hyp_match_idx, n_hyp, hyp_begin, hyp_end, match_begin, match_end, &d_idx))) return rc;
     CK(cudaMemcpyAsync(best_key, f->d_key, sizeof(uint64_t), cudaMemcpyDefault, f->stream));
     const bool key_on_host = !is_device_ptr(best_key);
     if (key_on_host || best_mask || n_pairs_scored) CK(cudaStreamSynchronize(f->stream));
@@ -1155,6 +1192,17 @@ int map_erase_info(rslam_filter* f, int b, int p) {
     if ((rc = erase_entry(f, D.patch, sizeof(float) * kPatchPix, N, p))) return rc;
     if ((rc = erase_entry(f, D.patch_init, 1681, N, p))) return rc;
     if ((rc = erase_entry(f, D.init_pose, sizeof(double) * 14, N, p))) return rc;
+    // the per-frame outputs are members of the same Feature record (ExtendKF.h:14-42) and move with it: the flags decide the
+    // counters of the next Map::map_management step 2 (src/Map.cpp:34-47) and its `measured` count (:57-66)
+    if ((rc = erase_entry(f, D.has_h, 1, N, p))) return rc;
+    if ((rc = erase_entry(f, D.ic, 1, N, p))) return rc;
+    if ((rc = erase_entry(f, D.li, 1, N, p))) return rc;
+    if ((rc = erase_entry(f, D.hi, 1, N, p))) return rc;
+    if ((rc = erase_entry(f, D.h, sizeof(double) * 2, N, p))) return rc;
+    if ((rc = erase_entry(f, D.z, sizeof(double) * 2, N, p))) return rc;
+    if ((rc = erase_entry(f, D.S, sizeof(double) * 4, N, p))) return rc;
+    if ((rc = erase_entry(f, D.Hc, sizeof(double) * 14, N, p))) return rc;
+    if ((rc = erase_entry(f, D.Hf, sizeof(double) * 12, N, p))) return rc;
     f->htype[b].erase(f->htype[b].begin() + p);
     D.N = N - 1;
     return 0;
@@ -1450,6 +1498,258 @@ int rslam_map_management(rslam_filter* f, int b, int step, int min_features, int
         info4[3] = attempts;
     }
     return rc;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The sweep sharded over GPUs: NCCL inside the library.  libnccl.so.2 is opened at run time (a process that already
+// carries an NCCL -- e.g. torch's -- gets that same copy by soname), so the library itself has no link-time dependency on it.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+typedef struct ncclComm* nccl_comm_t;
+struct nccl_uid {
+    char internal[128];
+};
+enum { kNcclUint32 = 3, kNcclUint64 = 5, kNcclMax = 2 };  // ncclDataType_t / ncclRedOp_t values of nccl.h (stable since NCCL 2.0)
+struct NcclApi {
+    void* so = nullptr;
+    int (*GetUniqueId)(nccl_uid*) = nullptr;
+    int (*CommInitRank)(nccl_comm_t*, int, nccl_uid, int) = nullptr;
+    int (*CommInitAll)(nccl_comm_t*, int, const int*) = nullptr;
+    int (*CommDestroy)(nccl_comm_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    int (*GetVersion)(int*) = nullptr;
+};
+NcclApi g_nccl;
+int nccl_load() {
+    if (g_nccl.so) return 0;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    void* so = nullptr;
+    for (const char* nm : names)
+        if ((so = dlopen(nm, RTLD_NOW | RTLD_GLOBAL))) break;
+    if (!so) return fail(RSLAM_ERR_CUDA, "rslam_comm: cannot load libnccl.so.2 (%s)", dlerror());
+#define SYM(field, name)                                                                           \
+    *(void**)(&g_nccl.field) = dlsym(so, name);                                                    \
+    if (!g_nccl.field) return fail(RSLAM_ERR_CUDA, "rslam_comm: libnccl has no symbol %s", name);
+    SYM(GetUniqueId, "ncclGetUniqueId")
+    SYM(CommInitRank, "ncclCommInitRank")
+    SYM(CommInitAll, "ncclCommInitAll")
+    SYM(CommDestroy, "ncclCommDestroy")
+    SYM(AllReduce, "ncclAllReduce")
+    SYM(GroupStart, "ncclGroupStart")
+    SYM(GroupEnd, "ncclGroupEnd")
+    SYM(GetErrorString, "ncclGetErrorString")
+    SYM(GetVersion, "ncclGetVersion")
+#undef SYM
+    g_nccl.so = so;
+    return 0;
+}
+#define NCK(call)                                                                                                                       \
+    do {                                                                                                                                \
+        int r__ = (call);                                                                                                               \
+        if (r__ != 0) return fail(RSLAM_ERR_CUDA, "%s failed: %s (%s:%d)", #call, g_nccl.GetErrorString(r__), __FILE__, __LINE__);      \
+    } while (0)
+}  // namespace
+
+struct rslam_comm {
+    int nranks = 0, rank0 = 0, nlocal = 0;
+    std::vector<int> devs;
+    std::vector<nccl_comm_t> comms;
+    std::vector<unsigned long long*> d_key;  // all-reduced key per local GPU
+    std::vector<unsigned*> d_words;          // winner's mask words per local GPU
+    std::vector<int> words_cap;
+};
+
+extern "C" {
+
+int rslam_comm_unique_id(void* id128) {
+    if (!id128) return fail(RSLAM_ERR_INVALID, "rslam_comm_unique_id: null buffer");
+    int rc = nccl_load();
+    if (rc) return rc;
+    nccl_uid id;
+    NCK(g_nccl.GetUniqueId(&id));
+    memcpy(id128, &id, sizeof(id));
+    return RSLAM_OK;
+}
+
+static int comm_alloc_buffers(rslam_comm* c) {
+    c->d_key.assign(c->nlocal, nullptr);
+    c->d_words.assign(c->nlocal, nullptr);
+    c->words_cap.assign(c->nlocal, 0);
+    for (int i = 0; i < c->nlocal; i++) {
+        CK(cudaSetDevice(c->devs[i]));
+        CK(cudaMalloc((void**)&c->d_key[i], 2 * sizeof(unsigned long long)));
+        CK(cudaMemset(c->d_key[i], 0, 2 * sizeof(unsigned long long)));
+    }
+    return 0;
+}
+
+int rslam_comm_init(int ndev, const int* devs, rslam_comm** out) {
+    if (ndev < 1 || !out) return fail(RSLAM_ERR_INVALID, "rslam_comm_init: bad arguments");
+    int have = 0;
+    if (cudaGetDeviceCount(&have) != cudaSuccess || have < ndev) {
+        cudaGetLastError();
+        return fail(RSLAM_ERR_CUDA, "rslam_comm_init: %d GPUs requested, %d visible", ndev, have);
+    }
+    int rc = nccl_load();
+    if (rc) return rc;
+    rslam_comm* c = new rslam_comm();
+    c->nranks = c->nlocal = ndev;
+    c->rank0 = 0;
+    for (int i = 0; i < ndev; i++) c->devs.push_back(devs ? devs[i] : i);
+    c->comms.assign(ndev, nullptr);
+    int r = g_nccl.CommInitAll(c->comms.data(), ndev, c->devs.data());
+    if (r != 0) {
+        delete c;
+        return fail(RSLAM_ERR_CUDA, "ncclCommInitAll failed: %s", g_nccl.GetErrorString(r));
+    }
+    if ((rc = comm_alloc_buffers(c))) {
+        rslam_comm_destroy(c);
+        return rc;
+    }
+    *out = c;
+    return RSLAM_OK;
+}
+
+int rslam_comm_init_rank(int nranks, int rank, const void* id128, int device, rslam_comm** out) {
+    if (nranks < 1 || rank < 0 || rank >= nranks || !id128 || !out) return fail(RSLAM_ERR_INVALID, "rslam_comm_init_rank: bad arguments");
+    int rc = nccl_load();
+    if (rc) return rc;
+    CK(cudaSetDevice(device));
+    rslam_comm* c = new rslam_comm();
+    c->nranks = nranks;
+    c->rank0 = rank;
+    c->nlocal = 1;
+    c->devs.push_back(device);
+    c->comms.assign(1, nullptr);
+    nccl_uid id;
+    memcpy(&id, id128, sizeof(id));
+    int r = g_nccl.CommInitRank(&c->comms[0], nranks, id, rank);
+    if (r != 0) {
+        delete c;
+        return fail(RSLAM_ERR_CUDA, "ncclCommInitRank failed: %s", g_nccl.GetErrorString(r));
+    }
+    if ((rc = comm_alloc_buffers(c))) {
+        rslam_comm_destroy(c);
+        return rc;
+    }
+    *out = c;
+    return RSLAM_OK;
+}
+
+int rslam_comm_destroy(rslam_comm* c) {
+    if (!c) return RSLAM_OK;
+    for (int i = 0; i < c->nlocal; i++) {
+        cudaSetDevice(c->devs[i]);
+        if (i < (int)c->d_key.size() && c->d_key[i]) cudaFree(c->d_key[i]);
+        if (i < (int)c->d_words.size() && c->d_words[i]) cudaFree(c->d_words[i]);
+        if (c->comms[i] && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comms[i]);
+    }
+    delete c;
+    return RSLAM_OK;
+}
+int rslam_comm_size(const rslam_comm* c) { return c ? c->nranks : -1; }
+int rslam_comm_local_size(const rslam_comm* c) { return c ? c->nlocal : -1; }
+
+int rslam_support_sweep_multi(rslam_comm* c, rslam_filter* const* filters, const int* hyp_match_idx, int n_hyp, int shard, uint64_t* best_key,
+                              uint8_t* best_mask, long long* n_pairs_scored) {
+    if (!c || !filters || !hyp_match_idx || n_hyp <= 0 || !best_key || (shard != RSLAM_SHARD_BY_HYPOTHESIS && shard != RSLAM_SHARD_BY_MATCH))
+        return fail(RSLAM_ERR_INVALID, "rslam_support_sweep_multi: bad arguments");
+    const int L = c->nlocal, G = c->nranks;
+    const bool key_on_device = is_device_ptr(best_key);
+    if (key_on_device && L != 1) return fail(RSLAM_ERR_INVALID, "rslam_support_sweep_multi: a device best_key needs exactly one local GPU");
+    for (int i = 0; i < L; i++) {
+        if (!filters[i] || filters[i]->device != c->devs[i] || filters[i]->B != 1)
+            return fail(RSLAM_ERR_INVALID, "rslam_support_sweep_multi: filters[%d] must be a batch-1 handle on device %d", i, c->devs[i]);
+        if (filters[i]->hN != filters[0]->hN) return fail(RSLAM_ERR_INVALID, "rslam_support_sweep_multi: the replicas hold different maps");
+    }
+    const int N = filters[0]->hN;
+    int rc;
+    std::vector<const int*> d_idx(L, nullptr);
+    std::vector<int> h0(L), h1(L), t0(L), t1(L);
+    for (int i = 0; i < L; i++) {
+        rslam_filter* f = filters[i];
+        CK(cudaSetDevice(f->device));
+        const long long r = c->rank0 + i;
+        if (shard == RSLAM_SHARD_BY_HYPOTHESIS) {
+            h0[i] = (int)(r * n_hyp / G);
+            h1[i] = (int)((r + 1) * n_hyp / G);
+            t0[i] = 0;
+            t1[i] = N;
+        } else {
+            h0[i] = 0;
+            h1[i] = n_hyp;
+            t0[i] = (int)(r * N / G);
+            t1[i] = (int)((r + 1) * N / G);
+        }
+        if ((rc = sweep_local(f, hyp_match_idx, n_hyp, h0[i], h1[i], t0[i], t1[i], &d_idx[i]))) return rc;
+    }
+    NCK(g_nccl.GroupStart());
+    for (int i = 0; i < L; i++) {
+        int r = g_nccl.AllReduce(filters[i]->d_key, c->d_key[i], 1, kNcclUint64, kNcclMax, c->comms[i], filters[i]->stream);
+        if (r != 0) {
+            g_nccl.GroupEnd();
+            return fail(RSLAM_ERR_CUDA, "ncclAllReduce(key) failed: %s", g_nccl.GetErrorString(r));
+        }
+    }
+    NCK(g_nccl.GroupEnd());
+    const int nwords = filters[0]->mwords;
+    if (best_mask) {
+        for (int i = 0; i < L; i++) {
+            rslam_filter* f = filters[i];
+            CK(cudaSetDevice(f->device));
+            if (c->words_cap[i] < nwords) {
+                if (c->d_words[i]) CK(cudaFree(c->d_words[i]));
+                c->d_words[i] = nullptr;
+                CK(cudaMalloc((void**)&c->d_words[i], sizeof(unsigned) * (size_t)nwords));
+                c->words_cap[i] = nwords;
+            }
+            LAUNCH(f, k_sweep_winner_mask, cdiv(nwords, 256), 256, 0, f->dF, (const unsigned long long*)c->d_key[i], d_idx[i], h0[i], h1[i], t0[i], t1[i], c->d_words[i], nwords);
+        }
+        if ((rc = check_launch())) return rc;
+        NCK(g_nccl.GroupStart());
+        for (int i = 0; i < L; i++) {
+            int r = g_nccl.AllReduce(c->d_words[i], c->d_words[i], (size_t)nwords, kNcclUint32, kNcclMax, c->comms[i], filters[i]->stream);
+            if (r != 0) {
+                g_nccl.GroupEnd();
+                return fail(RSLAM_ERR_CUDA, "ncclAllReduce(mask) failed: %s", g_nccl.GetErrorString(r));
+            }
+        }
+        NCK(g_nccl.GroupEnd());
+    }
+    CK(cudaSetDevice(filters[0]->device));
+    CK(cudaMemcpyAsync(best_key, c->d_key[0], sizeof(uint64_t), cudaMemcpyDefault, filters[0]->stream));
+    if (key_on_device && !best_mask && !n_pairs_scored) return RSLAM_OK;  // enqueue only
+    std::vector<unsigned> words;
+    if (best_mask) {
+        words.resize(nwords);
+        CK(cudaMemcpyAsync(words.data(), c->d_words[0], sizeof(unsigned) * (size_t)nwords, cudaMemcpyDeviceToHost, filters[0]->stream));
+    }
+    long long pairs = 0;
+    for (int i = 0; i < L; i++) {
+        CK(cudaSetDevice(filters[i]->device));
+        CK(cudaStreamSynchronize(filters[i]->stream));
+        if (n_pairs_scored) {
+            unsigned long long cnt = 0;
+            CK(cudaMemcpy(&cnt, filters[i]->d_key + 1, sizeof(cnt), cudaMemcpyDeviceToHost));
+            pairs += (long long)cnt;
+        }
+    }
+    if (n_pairs_scored) *n_pairs_scored = pairs;
+    if (best_mask) {
+        int ctl[CTL_SIZE];
+        CK(cudaSetDevice(filters[0]->device));
+        CK(cudaMemcpy(ctl, filters[0]->hF[0].ctl, sizeof(ctl), cudaMemcpyDeviceToHost));
+        const int m = ctl[CTL_MID];
+        memset(best_mask, 0, (size_t)(m + 7) / 8);
+        for (int j = 0; j < m; j++)
+            if ((words[j >> 5] >> (j & 31)) & 1u) best_mask[j >> 3] |= (uint8_t)(1u << (j & 7));
+    }
+    return RSLAM_OK;
 }
 
 }  // extern "C"

@@ -1,9 +1,13 @@
-"""Host-side logic of the sharded 1-point RANSAC hypothesis sweep.
+"""Host-side helpers of the sharded 1-point RANSAC hypothesis sweep.
 
-Hypotheses [0, H) are split in contiguous ranges over the ranks; every rank scores its range on its own GPU (state, matches and
-P replicated) and produces ONE packed 64-bit key; a single MAX all-reduce of that key (NCCL on the GPUs, gloo in the CPU tests)
-gives every rank the same winner: highest support, ties -> lowest hypothesis id (the reference keeps the FIRST best hypothesis:
-strict '>' at src/Tracking.cpp:507).  Nothing else crosses the links.
+The sharded sweep itself lives in the library (include/rslam.h: rslam_comm_init / rslam_comm_init_rank / rslam_support_sweep_multi --
+NCCL on the handles' own streams).  This module only (a) states the sharding and key conventions in Python for the CPU tests
+(world-size-2 gloo) and (b) carries the 128-byte NCCL id from rank 0 to the other ranks of a torchrun job.
+
+Hypotheses [0, H) are split in contiguous ranges over the ranks (or, with deduplication, the match indices are); every rank scores its
+shard on its own GPU (state, matches and P replicated) and produces ONE packed 64-bit key; a MAX all-reduce of that key gives every
+rank the same winner: highest support, ties -> lowest hypothesis id (the reference keeps the FIRST best hypothesis: strict '>' at
+src/Tracking.cpp:507).  The winner's inlier mask follows from the rank that scored it.
 """
 import numpy as np
 
@@ -42,3 +46,20 @@ def allreduce_key(key_tensor):
 def shard_filters(n_filters, world, rank):
     """batched independent filters: contiguous block of filters per rank, no collective on the data path"""
     return rank * n_filters // world, (rank + 1) * n_filters // world
+
+
+def comm_from_torch_distributed(device):
+    """one process per GPU under torchrun: rank 0's NCCL id reaches the other ranks through torch.distributed (plumbing only);
+    the communicator itself is the library's (rslam_comm_init_rank)."""
+    import torch
+    import torch.distributed as dist
+
+    from ransac_slam_b200 import capi
+
+    world, rank = dist.get_world_size(), dist.get_rank()
+    uid = capi.Comm.unique_id() if rank == 0 else np.zeros(128, dtype=np.uint8)
+    t = torch.from_numpy(uid.copy())
+    if dist.get_backend() == "nccl":
+        t = t.cuda(device)
+    dist.broadcast(t, src=0)
+    return capi.Comm.from_rank(world, rank, t.cpu().numpy(), device)
