@@ -24,6 +24,39 @@ inline double opA(bool t, const double* A, int lda, int i, int k) { return t ? A
 inline double opB(bool t, const double* B, int ldb, int k, int j) { return t ? B[(size_t)j + (size_t)k * ldb] : B[(size_t)k + (size_t)j * ldb]; }
 
 // micro kernel: acc[NR][MR] += sum_k a[k*MR+i] * b[k*NR+j]
+#if defined(__AVX2__) && defined(__FMA__)
+}  // namespace
+}  // namespace orc
+#include <immintrin.h>
+namespace orc {
+namespace {
+// 8 x 6 register tile: 12 ymm accumulators, two loads of A and one broadcast of B per k (what a BLAS / Eigen GEBP kernel does)
+inline void micro(int kc, const double* __restrict a, const double* __restrict b, double* __restrict C, int ldc, int mr, int nr,
+                  bool first) {
+    __m256d acc[NR][2];
+    for (int j = 0; j < NR; j++) acc[j][0] = acc[j][1] = _mm256_setzero_pd();
+    for (int k = 0; k < kc; k++) {
+        const __m256d a0 = _mm256_loadu_pd(a + (size_t)k * MR), a1 = _mm256_loadu_pd(a + (size_t)k * MR + 4);
+        const double* bk = b + (size_t)k * NR;
+#pragma GCC unroll 6
+        for (int j = 0; j < NR; j++) {
+            const __m256d bj = _mm256_broadcast_sd(bk + j);
+            acc[j][0] = _mm256_fmadd_pd(a0, bj, acc[j][0]);
+            acc[j][1] = _mm256_fmadd_pd(a1, bj, acc[j][1]);
+        }
+    }
+    double tmp[NR][MR];
+    for (int j = 0; j < NR; j++) {
+        _mm256_storeu_pd(&tmp[j][0], acc[j][0]);
+        _mm256_storeu_pd(&tmp[j][4], acc[j][1]);
+    }
+    for (int j = 0; j < nr; j++)
+        for (int i = 0; i < mr; i++) {
+            double* c = &C[(size_t)i + (size_t)j * ldc];
+            *c = first ? tmp[j][i] : *c + tmp[j][i];
+        }
+}
+#else
 inline void micro(int kc, const double* __restrict a, const double* __restrict b, double* __restrict C, int ldc, int mr, int nr,
                   bool first) {
     double acc[NR][MR];
@@ -43,6 +76,7 @@ inline void micro(int kc, const double* __restrict a, const double* __restrict b
             *c = first ? acc[j][i] : *c + acc[j][i];
         }
 }
+#endif
 
 void gemm_small_rows(bool tA, bool tB, int M, int N, int K, const double* A, int lda, const double* B, int ldb, double* C,
                      int ldc) {

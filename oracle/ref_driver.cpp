@@ -17,6 +17,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <ctime>
 #include <vector>
 
 #include "ransac_slam/System.h"
@@ -27,7 +28,16 @@ size_t g_rand_pos = 0;
 long g_rand_underflow = 0;
 }  // namespace
 
+// A frame of configuration C3 (2000 features) costs the reference ~9000 dense hypotheses; the bench times a BOUNDED number of them by
+// leaving Tracking::ransac_hypotheses through the draw that would start hypothesis number budget + 1.  libc declares rand() nothrow,
+// so the exit is a longjmp (the loop's Eigen temporaries of that one call are not destructed: a few MB per sample, timing runs only).
+#include <csetjmp>
+namespace {
+long g_rand_budget = -1;
+std::jmp_buf g_rand_jmp;
+}  // namespace
 extern "C" int __wrap_rand(void) {
+    if (g_rand_budget >= 0 && (long)g_rand_pos >= g_rand_budget) std::longjmp(g_rand_jmp, 1);
     if (g_rand_pos < g_rand.size()) return g_rand[g_rand_pos++];
     g_rand_underflow++;
     return 0;
@@ -156,6 +166,68 @@ void ref_reset_flags(void* h) {
         f.H.resize(0, 0);
         f.S.resize(0, 0);
     }
+}
+
+// ---- bounded samples of a frame that is too large to run whole (configuration C3, n = 12013; SURVEY 8d "per-stage sub-sampling") ----
+// The stages of Tracking::search_IC_matches one at a time (all public members of the reference's classes):
+void ref_predict_measurements(void* h) { ((Ref*)h)->kf->predict_camera_measurements(((Ref*)h)->kf->x_k_km1); }
+void ref_calculate_derivatives(void* h) { ((Ref*)h)->trk->calculate_derivatives(((Ref*)h)->kf->x_k_km1); }
+// the S_i statement of src/Tracking.cpp:41-43 for features [first, first + count) only; returns how many had a prediction
+int ref_S_subset(void* h, int first, int count) {
+    ExtendKF* k = ((Ref*)h)->kf;
+    int done = 0;
+    for (int i = first; i < first + count && i < (int)k->features_info.size(); i++)
+        if (k->features_info[i].h.cols()) {
+            k->features_info[i].S = (k->features_info[i].H) * (k->p_k_km1) * (k->features_info[i].H.transpose()) + (k->features_info[i].R);
+            done++;
+        }
+    return done;
+}
+// Tracking::ransac_hypotheses, left after `max_hyp` hypotheses (see __wrap_rand); returns the hypotheses completed
+int ref_ransac_limited(void* h, int max_hyp) {
+    const size_t before = g_rand_pos;
+    g_rand_budget = (long)before + max_hyp;
+    if (setjmp(g_rand_jmp) == 0) ((Ref*)h)->trk->ransac_hypotheses();
+    g_rand_budget = -1;
+    return (int)(g_rand_pos - before);
+}
+// overwrite the inlier flags (to time ExtendKF::ekf_update_li_inliers / ekf_update_hi_inliers on a chosen number of measurements)
+void ref_set_inlier_flags(void* h, const uint8_t* li, const uint8_t* hi) {
+    ExtendKF* k = ((Ref*)h)->kf;
+    for (size_t i = 0; i < k->features_info.size(); i++) {
+        k->features_info[i].low_innovation_inlier = li[i] != 0;
+        k->features_info[i].high_innovation_inlier = hi[i] != 0;
+    }
+}
+// dense products of the stand-in Eigen: 0 = plain loops (what the parity vectors were made with), 1 = packed cache-blocked kernel
+// (oracle/gemm.cpp, `threads` OpenMP threads) for products larger than 4 x 4 -- a fairer stand-in for Eigen's GEBP when timing
+extern "C++" {
+namespace orc {
+void dgemm(bool tA, bool tB, int M, int N, int K, const double* A, int lda, const double* B, int ldb, double* C, int ldc);
+void set_threads(int n);
+}  // namespace orc
+}
+static void blocked_hook(long M, long N, long K, const double* A, const double* B, double* C) {
+    orc::dgemm(false, false, (int)M, (int)N, (int)K, A, (int)M, B, (int)K, C, (int)M);
+}
+void ref_set_blocked_gemm(int on, int threads) {
+    orc::set_threads(threads < 1 ? 1 : threads);
+    Eigen::gemm_hook() = on ? blocked_hook : nullptr;
+}
+// seconds of one (m x k) * (k x n) product through the stand-in Eigen's operator* in the current product mode
+double ref_gemm_seconds(int m, int n, int k) {
+    Eigen::MatrixXd A = Eigen::MatrixXd::Zero(m, k), B = Eigen::MatrixXd::Zero(k, n);
+    for (int j = 0; j < k; j++)
+        for (int i = 0; i < m; i++) A(i, j) = 1.0 / (1 + i + j);
+    for (int j = 0; j < n; j++)
+        for (int i = 0; i < k; i++) B(i, j) = 1.0 / (2 + i + 2 * j);
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    Eigen::MatrixXd C = A * B;
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    volatile double sink = C(m - 1, n - 1);
+    (void)sink;
+    return (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
 }
 
 // ---- state access ---------------------------------------------------------------------------------------------------------------------

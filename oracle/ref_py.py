@@ -47,6 +47,15 @@ def lib():
                      "ref_reset_flags"):
             getattr(L, name).argtypes = [vp]
             getattr(L, name).restype = None
+        for name in ("ref_predict_measurements", "ref_calculate_derivatives"):
+            getattr(L, name).argtypes = [vp]
+            getattr(L, name).restype = None
+        L.ref_S_subset.argtypes = [vp, ci, ci]
+        L.ref_ransac_limited.argtypes = [vp, ci]
+        L.ref_set_inlier_flags.argtypes = [vp, vp, vp]
+        L.ref_set_blocked_gemm.argtypes = [ci, ci]
+        L.ref_gemm_seconds.argtypes = [ci, ci, ci]
+        L.ref_gemm_seconds.restype = C.c_double
         L.ref_set_rand.argtypes = [vp, ci]
         L.ref_get_camera.argtypes = [vp, vp]
         L.ref_get_params.argtypes = [vp, vp]
@@ -73,6 +82,15 @@ def lib():
 
 def _p(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def set_blocked_gemm(on, threads=1):
+    """timing runs only: route the stand-in Eigen's large dense products through the packed kernel of oracle/gemm.cpp"""
+    lib().ref_set_blocked_gemm(int(on), int(threads))
+
+
+def gemm_seconds(m, n, k):
+    return float(lib().ref_gemm_seconds(int(m), int(n), int(k)))
 
 
 def _f64(a):
@@ -190,6 +208,24 @@ class ReferenceFilter:
 
     def predict_only(self):
         self.L.ref_predict_only(self.h)
+
+    # ---- bounded samples of a frame too large to run whole (bench.py, configuration C3) ----
+    def predict_measurements(self):
+        self.L.ref_predict_measurements(self.h)
+
+    def calculate_derivatives(self):
+        self.L.ref_calculate_derivatives(self.h)
+
+    def S_subset(self, first, count):
+        return self.L.ref_S_subset(self.h, int(first), int(count))
+
+    def ransac_limited(self, max_hyp):
+        return self.L.ref_ransac_limited(self.h, int(max_hyp))
+
+    def set_inlier_flags(self, li, hi):
+        li = np.ascontiguousarray(li, dtype=np.uint8)
+        hi = np.ascontiguousarray(hi, dtype=np.uint8)
+        self.L.ref_set_inlier_flags(self.h, _p(li), _p(hi))
 
     def reset_flags(self):
         self.L.ref_reset_flags(self.h)

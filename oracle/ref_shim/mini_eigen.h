@@ -654,6 +654,15 @@ template <class A, class T> const Dyn<T>& as_dyn(const Ops<A, T>& a, Dyn<T>& tmp
         return tmp;
     }
 }
+// Optional dense-product kernel for TIMING runs: C (M x N, column-major, ld M) = A (M x K, ld M) * B (K x N, ld K).  When set (only
+// by the bench's reference arm, through ref_driver.cpp), large double products go through it -- a packed, cache-blocked kernel,
+// i.e. what a real Eigen's GEBP would do -- instead of the plain loops below.  Parity runs never set it: the per-entry summation
+// order of the plain loops is what the golden vectors were produced with.
+typedef void (*gemm_hook_t)(long M, long N, long K, const double* A, const double* B, double* C);
+inline gemm_hook_t& gemm_hook() {
+    static gemm_hook_t h = nullptr;
+    return h;
+}
 // every output entry is sum_k a(i,k) b(k,j) accumulated in ascending k (plain left-to-right sums, no blocking)
 template <class A, class B, class T> Dyn<T> operator*(const Ops<A, T>& a, const Ops<B, T>& b) {
     Dyn<T> ta, tb;
@@ -664,6 +673,12 @@ template <class A, class B, class T> Dyn<T> operator*(const Ops<A, T>& a, const 
     if (M == 0 || N == 0 || K == 0) return m;
     const T *xa = x.data(), *ya = y.data();
     T* ma = m.data();
+    if constexpr (std::is_same<T, double>::value) {
+        if (gemm_hook() && M > 4 && N > 4 && K >= 16) {
+            gemm_hook()((long)M, (long)N, (long)K, xa, ya, ma);
+            return m;
+        }
+    }
     if (M <= 4 && K >= 16) {  // short-and-wide left operand (H_i P): rows made contiguous, one dot product per output entry
         std::vector<T> xt((size_t)(M * K));
         for (Index k = 0; k < K; k++)

@@ -167,10 +167,25 @@ class Scene:
     std_z: float = 1.0
     seed: int = 1234
     meta: dict = field(default_factory=dict)
+    init_patches: np.ndarray = None  # N x 41 x 41 uint8 appearance at initialisation (texture="smooth" only)
+
+
+def smooth_patches(rng, N, size=41, sigma=1.6):
+    """Band-limited, full-contrast texture patches: white noise blurred by a separable Gaussian and stretched to 0..255 per patch.
+    Unlike white noise they survive the bilinear resampling of Tracking::pred_patch_fc (src/Tracking.cpp:164-278) with ZNCC > 0.8."""
+    r = int(np.ceil(3 * sigma))
+    k = np.exp(-0.5 * (np.arange(-r, r + 1) / sigma) ** 2)
+    k /= k.sum()
+    g = rng.standard_normal((N, size + 2 * r, size + 2 * r))
+    g = np.apply_along_axis(lambda v: np.convolve(v, k, mode="valid"), 1, g)
+    g = np.apply_along_axis(lambda v: np.convolve(v, k, mode="valid"), 2, g)
+    lo = g.min(axis=(1, 2), keepdims=True)
+    hi = g.max(axis=(1, 2), keepdims=True)
+    return np.rint(255.0 * (g - lo) / (hi - lo)).astype(np.uint8)
 
 
 def make_scene(N=100, seed=1234, cam=None, depth=(2.0, 20.0), margin=45, rho_rel_err=0.3, std_rho=1.0, std_z=1.0, dense_P=True,
-               min_sep=0, assemble_P=True, motion_scale=1.0):
+               min_sep=0, assemble_P=True, motion_scale=1.0, texture="noise"):
     """N landmarks in the frustum of the first camera, inverse-depth coded from the first pose."""
     cam = cam or Camera()
     rng = np.random.default_rng(seed)
@@ -181,8 +196,10 @@ def make_scene(N=100, seed=1234, cam=None, depth=(2.0, 20.0), margin=45, rho_rel
         ny = int(np.floor((cam.nRows - 2 * margin) / min_sep))
         assert nx * ny >= N, "image too small for N non-overlapping patches"
         cells = rng.permutation(nx * ny)[:N]
-        uv[:, 0] = margin + (cells % nx) * min_sep + rng.integers(0, max(1, min_sep - 13), N)
-        uv[:, 1] = margin + (cells // nx) * min_sep + rng.integers(0, max(1, min_sep - 13), N)
+        # pasted appearance is 13 x 13 (noise templates) or 15 x 15 with the matching window one pixel off-centre (smooth texture)
+        jit = max(1, min_sep - (16 if texture == "smooth" else 13))
+        uv[:, 0] = margin + (cells % nx) * min_sep + rng.integers(0, jit, N)
+        uv[:, 1] = margin + (cells // nx) * min_sep + rng.integers(0, jit, N)
     else:
         uv[:, 0] = rng.integers(margin, cam.nCols - margin, N)
         uv[:, 1] = rng.integers(margin, cam.nRows - margin, N)
@@ -213,8 +230,14 @@ def make_scene(N=100, seed=1234, cam=None, depth=(2.0, 20.0), margin=45, rho_rel
         J[6 * i:6 * i + 6] = dy_dxv
         blocks[i] = dy_dhd @ Padd @ dy_dhd.T
     templates = rng.integers(0, 256, size=(N, 13, 13), dtype=np.uint8)
+    init_patches = None
+    if texture == "smooth":
+        # what Map::initialize_a_features stores (src/Map.cpp:286-294): the 41 x 41 neighbourhood of the corner; the 13 x 13 matching
+        # template is its centre
+        init_patches = smooth_patches(np.random.default_rng(seed + 7919), N)
+        templates = np.ascontiguousarray(init_patches[:, 14:27, 14:27])
     if not assemble_P:
-        sc = Scene(cam=cam, N=N, landmarks=landmarks, uv0=uv, templates=templates, x0=x0, P0=None, std_z=std_z, seed=seed)
+        sc = Scene(cam=cam, N=N, landmarks=landmarks, uv0=uv, templates=templates, x0=x0, P0=None, std_z=std_z, seed=seed, init_patches=init_patches)
         sc.meta["P_factors"] = (J, Pxv, blocks)
         sc.meta["motion_scale"] = motion_scale
         return sc
@@ -228,7 +251,7 @@ def make_scene(N=100, seed=1234, cam=None, depth=(2.0, 20.0), margin=45, rho_rel
     for i in range(N):
         s = 13 + 6 * i
         P0[s:s + 6, s:s + 6] = (JP[6 * i:6 * i + 6] @ J[6 * i:6 * i + 6].T) + blocks[i]
-    sc = Scene(cam=cam, N=N, landmarks=landmarks, uv0=uv, templates=templates, x0=x0, P0=P0, std_z=std_z, seed=seed)
+    sc = Scene(cam=cam, N=N, landmarks=landmarks, uv0=uv, templates=templates, x0=x0, P0=P0, std_z=std_z, seed=seed, init_patches=init_patches)
     sc.meta["motion_scale"] = motion_scale
     return sc
 
@@ -286,11 +309,17 @@ def make_sequence(scene, T=20, noise_px=0.5, outlier_frac=0.2, seed=99, n_u01=10
         uv[is_out, 1] += mag[is_out] * np.sin(ang[is_out])
         zi = np.rint(uv).astype(np.int32)
         img = bg.copy()
+        # smooth scenes paste a 15 x 15 crop of the 41 x 41 initial appearance: the warped predicted patch carries the reference's
+        # one-pixel offset (quirk Q11), so its best match sits one pixel off the pasted centre and needs the surrounding texture
+        hp = 7 if scene.init_patches is not None else 6
         for i in range(scene.N):
             x, y = zi[i]
-            if depth[i] <= 0 or x - 6 < 0 or y - 6 < 0 or x + 7 > cam.nCols or y + 7 > cam.nRows:
+            if depth[i] <= 0 or x - hp < 0 or y - hp < 0 or x + hp + 1 > cam.nCols or y + hp + 1 > cam.nRows:
                 continue
-            img[y - 6:y + 7, x - 6:x + 7] = scene.templates[i]
+            if scene.init_patches is not None:
+                img[y - hp:y + hp + 1, x - hp:x + hp + 1] = scene.init_patches[i][20 - hp:21 + hp, 20 - hp:21 + hp]
+            else:
+                img[y - 6:y + 7, x - 6:x + 7] = scene.templates[i]
             z_true[k, i] = (x, y)
         images[k] = img
         outl[k] = is_out
@@ -328,6 +357,35 @@ def random_spd_state(N, seed=0, cam=None, corr_rank=8, corr_scale=0.05, t0=3, rh
     P = P + U @ U.T
     P = np.asfortranarray(0.5 * (P + P.T))
     return scene, x, P
+
+
+def assemble_P_numpy(scene):
+    """The same initial covariance as assemble_P_torch(scene, ...) without options, built with element-wise numpy only (no BLAS): the
+    camera prior Pxv is diagonal, so [I;J] Pxv [I;J]^T is a fixed-order sum of 13 outer products c c^T -- bit-reproducible on any
+    machine, which is what a committed full-size fixture needs.  Returns a Fortran-ordered n x n array."""
+    J, Pxv, blocks = scene.meta["P_factors"]
+    assert np.count_nonzero(Pxv - np.diag(np.diag(Pxv))) == 0
+    N = scene.N
+    n = 13 + 6 * N
+    Jf = np.zeros((n, 13))
+    Jf[:13] = np.eye(13)
+    Jf[13:] = J
+    P = np.zeros((n, n), order="F")
+    tmp = np.empty((n, n), order="F")
+    for k in range(13):
+        d = Pxv[k, k]
+        if d == 0.0:
+            continue
+        c = np.sqrt(d) * Jf[:, k]
+        np.multiply(c[:, None], c[None, :], out=tmp)  # exactly symmetric: c_i c_j == c_j c_i
+        P += tmp
+    del tmp
+    idx = 13 + 6 * np.arange(N)
+    bs = 0.5 * (blocks + blocks.transpose(0, 2, 1))
+    for a in range(6):
+        for b in range(6):
+            P[idx + a, idx + b] += bs[:, a, b]
+    return P
 
 
 def assemble_P_torch(scene, device, rho_std_rel=None, x=None, lowrank=0, lowrank_scale=0.05, seed=0):
