@@ -1,8 +1,8 @@
-"""Extra workloads reported next to the main bench line (BASELINE.json configs[2..4]):
-  C3  N = 2000 features (state dim 12013, P = 1.15 GB): frames/s + the fp64 DMMA covariance downdate against the fp64 peak
-  C4  1-point RANSAC support sweep, 1e5 hypotheses x 5000 matches, sharded over the ranks with one MAX all-reduce of the
-      packed (support, hypothesis id) key: hypothesis-matches/s + HBM roofline of the support kernel
-  C5  batch of independent 100-feature filters split over the ranks (no inter-GPU traffic): frames/s
+"""Extra workloads reported next to the main bench line (BASELINE.json configs[1], [3], [4]):
+  C2  ONE 100-feature filter (the latency-bound configuration): frames/s, end to end, kernel shares
+  C4  1-point RANSAC support sweep, 1e5 hypotheses x 5000 matches, sharded over the ranks inside the library (NCCL MAX all-reduce of
+      the packed (support, hypothesis id) key + the winner's mask): hypothesis-matches/s + HBM roofline of the support kernel
+  C5  batch of independent 100-feature filters (the main line when --gpus N > 1)
 Each returns a dict; failures are reported, never raised (the main line must survive)."""
 import os
 import time
@@ -41,58 +41,78 @@ def consistent_state(scene, device, t0=3, rho_err=0.02, seed=0, lowrank=8):
     return x, P
 
 
-def bench_c3(args, world, rank, local):
+def bench_c2(args, world, rank, local):
+    """C2: ONE 100-feature filter (BASELINE.json configs[1]) -- the latency-bound configuration (a frame touches ~3 MB and ~1e8 flop)."""
     import torch
 
-    from ransac_slam_b200 import capi
-
-    if world > 1:
-        return dict(skipped="a single filter's update stays on one GPU (replicas only); measured at N=1")
-    N = 2000
-    cam = synth.scaled_camera(4)
-    scene = synth.make_scene(N=N, seed=1234, cam=cam, margin=30, min_sep=18, assemble_P=False, motion_scale=0.25)
-    W, K = 2, 4
-    n_u01 = 8192
-    seq = synth.make_sequence(scene, T=W + K, seed=1235, n_u01=n_u01)
-    n = scene.x0.size
-    dev = torch.device("cuda", local)
-    P0 = synth.assemble_P_torch(scene, dev)
-    g = capi.Filter(cam.as9(), N, batch=1, device=local, std_a=0.007 * 0.25, std_alpha=0.007 * 0.25)
-    x0 = torch.from_numpy(scene.x0).to(dev)
-    g.upload_state_device(x0.data_ptr(), P0.data_ptr(), n, n, N)
-    g.upload_patches(scene.templates.astype(np.float64))
-    del P0
+    if rank != 0:
+        return None
+    K, W = 200, 10
+    T = W + K
+    scene, seq = B.make_c2(1234, T)
+    N, n = scene.N, scene.x0.size
+    rows, cols = seq.images.shape[1:]
+    g = B.new_gpu_filter(scene, device=local)
     stream = torch.cuda.ExternalStream(g.stream)
-    d_images = torch.from_numpy(seq.images).to(dev)
-    d_u01 = torch.from_numpy(seq.u01).to(dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    d_images = torch.from_numpy(seq.images).cuda()
+    d_u01 = torch.from_numpy(seq.u01).cuda()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     B.run_frames_resident(g, d_images, d_u01, range(W), False, flush, stream)
-    ms = B.run_frames_resident(g, d_images, d_u01, range(W, W + K), True, flush, stream)
-    # instrumented pass for the kernel breakdown (continues the same trajectory: frames W+K.. are not available, so re-run the last)
-    g.profile(True)
-    B.run_frames_resident(g, d_images, d_u01, [W + K - 1], False, flush, stream)
-    st = B.frame_stats(g)
-    prof = g.profile_read()
-    g.profile(False)
-    tot = sum(v[1] for v in prof.values())
-    breakdown = {k: dict(launches=v[0], ms=v[1], share=v[1] / tot) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
-    fp64_peak = B.fp64_gemm_peak()
-    kk = 2.0 * (st["m_li"] + st["m_hi"])
-    gemm_ms = sum(v[1] for kname, v in prof.items() if kname.startswith("k_gemm_dmma"))
-    syrk_ms = prof.get("k_gemm_dmma/syrk_P", (0, 0.0))[1]
-    # fp64 flops issued on DMMA tiles in that frame: SYRK n^2 k (lower triangle) + TRSM trailing n k^2 + Cholesky trailing k^3/3
-    k_li, k_hi = 2.0 * st["m_li"], 2.0 * st["m_hi"]
-    flops = sum(float(n) * n * k + float(n) * k * k + k**3 / 3.0 for k in (k_li, k_hi))
-    out = dict(workload="C3: synthetic 2000-feature map, 1280x960 camera (4x pixel density, motion and noise scaled 1/4), state dim 12013, P 1.15 GB fp64",
-               value=K / (ms * 1e-3), unit="frames/s", ms_per_frame=ms / K, steps=K, warmup=W, frame_stats=st, kernels=breakdown,
-               roofline=dict(kernel="k_gemm_dmma", bound="tensor", unit="TFLOP/s", achieved=flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms else None,
-                             peak=fp64_peak, frac=(flops / (gemm_ms * 1e-3) / 1e12 / fp64_peak) if gemm_ms else None,
-                             flops_per_frame=flops, gemm_ms_per_frame=gemm_ms, k_li=k_li, k_hi=k_hi,
-                             syrk=dict(ms=syrk_ms, tflops=(sum(float(n) * n * k for k in (k_li, k_hi)) / (syrk_ms * 1e-3) / 1e12) if syrk_ms else None),
-                             note="peak = cuBLAS fp64 GEMM (torch.matmul 6144^3) measured in the same process; flops = n^2 k + n k^2 + k^3/3 per update"),
-               cpu_baseline=dict(value=None, note="dense reference path at N=2000 is ~7e12 flop/frame plus up to ~9000 dense RANSAC hypotheses (SURVEY Appendix B): hours per frame on one core, not run"))
+    l0 = g.launches
+    ms = B.run_frames_resident(g, d_images, d_u01, range(W, T), True, flush, stream)
+    launches = g.launches - l0
+    pose_resident = g.download_pose()
     g.close()
-    return out
+    # per-kernel breakdown (instrumented pass)
+    gp = B.new_gpu_filter(scene, device=local)
+    sp = torch.cuda.ExternalStream(gp.stream)
+    B.run_frames_resident(gp, d_images, d_u01, range(W), False, flush, sp)
+    gp.profile(True)
+    stats = []
+    PF = 50
+    for k in range(W, W + PF):
+        with torch.cuda.stream(sp):
+            flush.zero_()
+        B.run_frames_resident(gp, d_images, d_u01, [k], False, flush, sp)
+        stats.append(B.frame_stats(gp))
+    prof = gp.profile_read()
+    gp.profile(False)
+    gp.close()
+    st = {k: float(np.mean([s_[k] for s_ in stats])) for k in stats[0]}
+    tot = sum(v[1] for v in prof.values())
+    breakdown = {k: dict(launches_per_frame=v[0] / PF, us_per_frame=1e3 * v[1] / PF, share=v[1] / tot) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
+    # end to end
+    ge = B.new_gpu_filter(scene, device=local)
+    h_images = torch.from_numpy(seq.images).pin_memory()
+    h_u01 = torch.from_numpy(seq.u01).pin_memory()
+    img_b, u_b = rows * cols, seq.u01.shape[1] * 8
+
+    def e2e_step(k):
+        ge.frame((h_images.data_ptr() + k * img_b, rows, cols, cols), (h_u01.data_ptr() + k * u_b, seq.u01.shape[1]), predict=True)
+        return ge.download_pose()
+
+    for k in range(W):
+        e2e_step(k)
+    t0 = time.perf_counter()
+    for k in range(W, T):
+        pose = e2e_step(k)
+    ge.sync()
+    t_e2e = time.perf_counter() - t0
+    assert np.allclose(pose, pose_resident, rtol=1e-9, atol=1e-12)
+    ge.close()
+    # the reference's own sources on the first frames of the same trajectory (whole frames: they take about a second each)
+    cpu = None
+    if not args.no_cpu:
+        try:
+            rc = B.RefC2(scene, seq)
+            dts = [rc.step() for _ in range(5)][1:]
+            cpu = dict(value=len(dts) / float(np.sum(dts)), unit="frames/s", cores=1, kind="reference", sample="frames 1-4 of the same trajectory, whole frames")
+        except Exception as e:
+            cpu = dict(error=repr(e))
+    return dict(workload="C2: ONE synthetic 100-feature filter, 320x240, bounded trajectory (latency-bound by construction); L2 flushed between frames",
+                value=K / (ms * 1e-3), unit="frames/s", ms_per_frame=ms / K, steps=K, warmup=W, gpu_launches_per_frame=launches / K,
+                e2e=dict(value=K / t_e2e, unit="frames/s", h2d_bytes_per_step=img_b + u_b, d2h_bytes_per_step=104), frame_stats=st, kernels=breakdown,
+                cpu_baseline=cpu)
 
 
 def make_c4(device, N=5000, seed=77):
@@ -110,158 +130,104 @@ def make_c4(device, N=5000, seed=77):
 
 
 def bench_c4(args, world, rank, local):
+    """C4: the support sweep sharded over the ranks INSIDE the library (rslam_support_sweep_multi: NCCL MAX all-reduce of the packed key on
+    the handle's own stream, the winner's mask handed to every rank)."""
     import torch
 
-    from ransac_slam_b200 import capi
+    from ransac_slam_b200 import capi, sweep
 
     N, H = 5000, 100000
     dev = torch.device("cuda", local)
     scene, x, P, z = make_c4(dev, N)
     n = x.size
     hyp = np.random.Generator(np.random.MT19937(99)).integers(0, N, H).astype(np.int32)
+    comm = sweep.comm_from_torch_distributed(local) if world > 1 else capi.Comm.single_process([local])
     res = {}
     for dedupe in (True, False):
-        g = capi.Filter(scene.cam.as9(), N, batch=1, device=local, dedupe=dedupe)
+        g = capi.Filter(scene.cam.as9(), N, batch=1, device=local, dedupe=dedupe, quirks=0x6)
         xd = torch.from_numpy(x).to(dev)
         g.upload_state_device(xd.data_ptr(), P.data_ptr(), n, n, N, prior=True)
-        g.set_matches(z, np.ones(N, dtype=np.uint8))
-        g.search_ic_matches()  # h, H, S at x_k_km1 (no image: matches were injected)
+        g.search_ic_matches()  # h, H, S at x_k_km1 (no image: matches are injected)
         g.set_matches(z, np.ones(N, dtype=np.uint8))
         d_hyp = torch.from_numpy(hyp).to(dev)
         d_key = torch.zeros(1, dtype=torch.int64, device=dev)
         # sharding axis: dedupe -> by match index (each distinct hypothesis scored on exactly one GPU); brute force -> by hypothesis id
-        if dedupe:
-            h0, h1, t0, t1 = 0, H, rank * N // world, (rank + 1) * N // world
-        else:
-            h0, h1, t0, t1 = rank * H // world, (rank + 1) * H // world, 0, N
+        shard = capi.SHARD_BY_MATCH if dedupe else capi.SHARD_BY_HYPOTHESIS
         stream = torch.cuda.ExternalStream(g.stream)
-        reps = 5 if dedupe else 2
+        reps = 10 if dedupe else 2
 
-        def sweep():
-            g.support_sweep(d_hyp.data_ptr(), h0, h1, want_mask=False, key_device_ptr=d_key.data_ptr(), n_hyp=H, match_begin=t0, match_end=t1)
-            if world > 1:
-                import torch.distributed as dist
+        def sweep_once():
+            comm.support_sweep([g], d_hyp.data_ptr(), shard=shard, key_device_ptr=d_key.data_ptr(), n_hyp=H)
 
-                torch.cuda.current_stream().wait_stream(stream)
-                dist.all_reduce(d_key, op=dist.ReduceOp.MAX)
-
-        sweep()
+        for _ in range(3):
+            sweep_once()
+        g.sync()
         B.barrier(world)
         e0, e1 = _events(stream)
         e0.record(stream)
         for _ in range(reps):
-            sweep()
-        if world > 1:
-            stream.wait_stream(torch.cuda.current_stream())
+            sweep_once()
         e1.record(stream)
         g.sync()
-        torch.cuda.synchronize()
         ms = B.max_over_ranks(e0.elapsed_time(e1) / reps, world)
-        key = int(d_key.item())
+        # the same sweep returning key AND the winner's mask to the host of every rank (wall clock around the blocking call)
+        B.barrier(world)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            comm.support_sweep([g], d_hyp.data_ptr(), shard=shard, want_mask=True, n_hyp=H)
+        ms_mask = B.max_over_ranks((time.perf_counter() - t0) / reps * 1e3, world)
+        key, mask, pairs = comm.support_sweep([g], hyp, shard=shard, want_mask=True, want_pairs=True)
+        assert key == (int(d_key.item()) & 0xFFFFFFFFFFFFFFFF)
         support, hid = capi.decode_key(key)
-        # distinct pairs actually scored (host read, outside the timed region) + kernel-only time of the support kernel (instrumented pass)
+        assert int(mask.sum()) == support, (int(mask.sum()), support)
+        # kernel-only time of the support kernel (instrumented pass)
         g.profile(True)
-        _, _, pairs = g.support_sweep(hyp, h0, h1, want_mask=False, match_begin=t0, match_end=t1)
+        comm.support_sweep([g], hyp, shard=shard, want_mask=False)
         prof = g.profile_read()
         g.profile(False)
         k_ms = B.max_over_ranks(prof.get("k_ransac_support", (1, 0.0))[1], world)
+        setup_ms = B.max_over_ranks(sum(v[1] for kname, v in prof.items() if kname != "k_ransac_support"), world)
         pairs_all = B.sum_over_ranks(float(pairs), world)
         pk = B.peaks()
         name = "dedupe" if dedupe else "brute_force"
         res[name] = dict(ms_per_sweep=ms, value=H * float(N) / (ms * 1e-3), unit="hypothesis-matches/s", winner=dict(support=support, hypothesis=hid),
-                         pairs_scored_on_device=pairs_all,
+                         mask_bits=int(mask.sum()), pairs_scored_on_device=pairs_all, ms_per_sweep_key_and_mask_on_host=ms_mask,
                          roofline=dict(kernel="k_ransac_support", bound="hbm", unit="GB/s", achieved=288.0 * pairs_all / world / (ms * 1e-3) / 1e9,
                                        peak=pk["hbm_gbs"], frac=288.0 * pairs_all / world / (ms * 1e-3) / 1e9 / pk["hbm_gbs"],
                                        kernel_only=dict(ms=k_ms, achieved=288.0 * pairs_all / world / (k_ms * 1e-3) / 1e9 if k_ms else None,
-                                                        frac=288.0 * pairs_all / world / (k_ms * 1e-3) / 1e9 / pk["hbm_gbs"] if k_ms else None),
-                                       note="288 B per scored (hypothesis, match) pair (SURVEY 8d), per GPU; whole sweep timed (compact + hyp + mark + support + reduce); peak " + pk["source"]))
+                                                        frac=288.0 * pairs_all / world / (k_ms * 1e-3) / 1e9 / pk["hbm_gbs"] if k_ms else None,
+                                                        other_kernels_ms=setup_ms,
+                                                        note="per-launch CUDA events of an instrumented sweep (not the timed region)"),
+                                       note="288 B per scored (hypothesis, match) pair (SURVEY 8d), per GPU; whole sweep timed (compact + hypotheses + marks + "
+                                            "support + reduce + the NCCL all-reduce of the key); peak " + pk["source"]))
         g.close()
-    return dict(workload="C4: support sweep 1e5 hypotheses x 5000 matches (n=30013, P 7.2 GB replicated per GPU), hypotheses sharded over ranks, MAX all-reduce of the packed key",
+    comm.close()
+    return dict(workload="C4: support sweep 1e5 hypotheses x 5000 matches (n=30013, P 7.2 GB replicated per GPU) on a consistent map (quirk Q1 off: real "
+                         "inlier sets), sharded over the ranks inside the library (rslam_support_sweep_multi, NCCL on the handle's stream)",
                 n_gpus=world, scaling="strong", **res)
 
 
 def bench_c5(args, world, rank, local):
-    import torch
-
-    from ransac_slam_b200 import capi
-
-    Btot = int(os.environ.get("RSLAM_C5_FILTERS", "4096"))
-    Bl = Btot // world
-    NS = 8  # distinct scenes cycled over the batch
-    W, K = 2, 4
-    scenes, seqs = [], []
-    for s in range(NS):
-        sc, sq = B.make_c2(1234 + s + NS * rank, W + K)
-        scenes.append(sc)
-        seqs.append(sq)
-    cam = scenes[0].cam
-    dev = torch.device("cuda", local)
-    g = capi.Filter(cam.as9(), 100, batch=Bl, device=local)
-    n = scenes[0].x0.size
-    for s in range(NS):
-        xd = torch.from_numpy(scenes[s].x0).to(dev)
-        Pd = torch.from_numpy(np.ascontiguousarray(scenes[s].P0)).to(dev)
-        for b in range(s, Bl, NS):
-            g.upload_state_device(xd.data_ptr(), Pd.data_ptr(), n, n, 100, b=b)
-            g.upload_patches(scenes[s].templates.astype(np.float64), b=b)
-    idx = torch.arange(Bl, device=dev) % NS
-    imgs = torch.stack([torch.from_numpy(sq.images) for sq in seqs]).to(dev)  # NS x T x r x c
-    u01s = torch.stack([torch.from_numpy(sq.u01) for sq in seqs]).to(dev)
-    d_images = imgs[idx].transpose(0, 1).contiguous()  # T x Bl x r x c
-    d_u01 = u01s[idx].transpose(0, 1).contiguous()  # T x Bl x n_u01
-    stream = torch.cuda.ExternalStream(g.stream)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    B.run_frames_resident(g, d_images, d_u01, range(W), False, flush, stream)
-    B.barrier(world)
-    ms = B.run_frames_resident(g, d_images, d_u01, range(W, W + K), False, flush, stream)
-    B.barrier(world)
-    ms = B.max_over_ranks(ms, world)
-    # instrumented pass (events around every launch, no graph): where the batch frame goes
-    g.profile(True)
-    B.run_frames_resident(g, d_images, d_u01, [W + K - 1], False, flush, stream)
-    prof = g.profile_read()
-    g.profile(False)
-    ft = [g.features(b=b) for b in range(0, Bl, max(1, Bl // 16))]
-    m_hi = float(np.mean([f["hi"].sum() for f in ft]))
-    m_li = float(np.mean([f["li"].sum() for f in ft]))
-    tot = sum(v[1] for v in prof.values())
-    breakdown = {k: dict(launches=v[0], ms=v[1], share=v[1] / tot) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
-    g.close()
-    # HBM roofline of the batch frame: every filter's P (n x ldp fp64) is read and written once per non-empty update (the SYRK
-    # downdate), and the 7 + 6 m columns of P that W = P H^T gathers are read once more; everything else is < 5 % of that
-    ldp = (n + 15) // 16 * 16
-    upd = (1 if m_li > 0 else 0) + (1 if m_hi > 0 else 0)
-    bytes_per_filter = upd * 2.0 * n * ldp * 8 + 8.0 * n * (7 * upd + 6 * (m_li + m_hi))
-    pk = B.peaks()
-    ach = Bl * bytes_per_filter / (ms / K * 1e-3) / 1e9
-    # the dominant kernel against ITS roofline: the covariance downdate P -= V V^T on the fp64 tensor pipe, (n + 1) n k flop per filter
-    # (lower triangle x 2 flop), against the cuBLAS fp64 GEMM rate measured live
-    top = next(iter(breakdown))
-    kroof = None
-    if top in ("k_syrk_rows", "k_gemm_dmma/syrk_P"):
-        flops = Bl * float(n + 1) * n * 2.0 * (m_li + m_hi)
-        tf = flops / (breakdown[top]["ms"] * 1e-3) / 1e12
-        fp64_peak = B.fp64_gemm_peak()
-        kroof = dict(kernel=top, bound="tensor", unit="TFLOP/s", achieved=tf, peak=fp64_peak, frac=tf / fp64_peak, share_of_step=breakdown[top]["share"],
-                     note="(n + 1) n k flop per filter / kernel time; peak = cuBLAS fp64 GEMM measured live")
-    return dict(workload=f"C5: {Btot} independent 100-feature filters, batch split over ranks, no inter-GPU traffic", n_gpus=world, scaling="strong",
-                value=Btot * K / (ms * 1e-3), unit="filter-frames/s", ms_per_batch_frame=ms / K, filters_per_gpu=Bl,
-                frame_stats=dict(m_li=m_li, m_hi=m_hi), kernels=breakdown,
-                roofline=dict(bound="hbm", unit="GB/s", achieved=ach, peak=pk["hbm_gbs"], frac=ach / pk["hbm_gbs"], bytes_per_filter_frame=bytes_per_filter,
-                              note="whole batch frame against HBM: P read+written once per non-empty update + the P columns gathered by W = P H^T; peak " + pk["source"]),
-                roofline_dominant_kernel=kroof,
-                note="working set (P 12.5 GB per 4096 filters) exceeds L2; no flush needed")
+    """C5 as an extra of the --gpus 1 line (at --gpus N > 1 it IS the main line: bench.c5_line)"""
+    if world > 1:
+        return dict(skipped="main line of this run")
+    r = B.bench_c5(args, world, rank, local, steps=6, warmup=3, with_e2e=True)
+    K = r["steps"]
+    return dict(workload=f"C5: {B.C5_FILTERS} independent 100-feature filters on one GPU", value=B.C5_FILTERS * K / (r["ms"] * 1e-3), unit="frames/s",
+                ms_per_batch_frame=r["ms"] / K, steps=K, warmup=r["warmup"], e2e=dict(value=B.C5_FILTERS * r["e2e_steps"] / r["e2e_seconds"], unit="frames/s",
+                                                                                   h2d_bytes_per_step=r["e2e_bytes"][0], d2h_bytes_per_step=r["e2e_bytes"][1]),
+                frame_stats=r["frame_stats"], kernels=r["kernels"], roofline=r["roofline"], whole_frame_hbm=r["whole_frame_hbm"])
 
 
 def run(args, world, rank, local):
     out = {}
     which = [w.strip() for w in args.extras.split(",") if w.strip()]
-    for name, fn in (("c3", bench_c3), ("c4", bench_c4), ("c5", bench_c5)):
+    for name, fn in (("c2", bench_c2), ("c4", bench_c4), ("c5", bench_c5)):
         if name not in which:
             continue
         t0 = time.time()
         try:
-            out[name] = fn(args, world, rank, local)
+            out[name] = fn(args, world, rank, local) or {}
         except Exception as e:
             import traceback
 
