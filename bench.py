@@ -181,14 +181,19 @@ def kernel_work(kernel, launches, N, n, st):
         return "hbm", launches * 2 * 4 * n * 8.0 * 2
     if kernel == "k_gemm_dmma/syrk_P" or kernel == "k_syrk_rows":
         return "tensor", sum(float(n + 1) * (n + 1) * k for k in ks)  # lower triangle x 2 flop
-    if kernel in ("k_trsm_ll", "k_trsm_small"):
+    if kernel == "k_trsm_small":
         return "tensor", sum(float(n + 1) * k * k for k in ks)
-    if kernel == "cholesky":  # k_chol_panel + k_gemm_dmma/chol_inner + k_gemm_dmma/chol_outer (or the single-CTA k_chol_small)
+    # large k: two-level TRSM -- the left-looking kernel solves inside 256-wide outer blocks, K = 256 GEMMs carry the rest
+    if kernel == "k_trsm_ll":
+        return "tensor", sum(float(n + 1) * min(256.0 * k, k * k) for k in ks)
+    if kernel == "k_gemm_dmma/trsm_outer":
+        return "tensor", sum(float(n + 1) * max(k * k - 256.0 * k, 0.0) for k in ks)
+    if kernel == "cholesky":  # k_chol_panel + k_gemm_dmma/chol_outer + k_chol_trinv (or the single-CTA k_chol_small)
         return "tensor", sum(k**3 / 3.0 for k in ks)
     return None, None
 
 
-CHOL_KERNELS = ("k_chol_panel", "k_gemm_dmma/chol_inner", "k_gemm_dmma/chol_outer", "k_chol_small", "k_chol_fused")
+CHOL_KERNELS = ("k_chol_panel", "k_gemm_dmma/chol_outer", "k_chol_trinv", "k_chol_small")
 
 # DRAM bytes (read + write) per launch of the dominant kernels from this round's `ncu --set full` captures (profiles/r02_*.md)
 NCU_TRAFFIC = {"k_gemm_dmma/syrk_P": None, "k_syrk_rows": None}

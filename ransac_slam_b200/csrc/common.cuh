@@ -57,6 +57,7 @@ struct DevFilter {
     // appearance at initialisation (only needed when the predicted patch is warped on the device, pred_patch_fc)
     unsigned char* patch_init;  // N x 41 x 41 row-major
     double* init_pose;          // N x 14: r_wc(3), R_wc row-major(9), uv(2)
+    double* pp_geom;            // N x 12: per-feature warp geometry of the current frame (k_pred_patch_setup): Hm (9), xs, ys, ok
     int* last_id;               // N: index of the latest inverse-depth feature <= i (-1 if none): XYZ_w actually used (quirk Q3)
     // image (may be shared between filters)
     const unsigned char* image;

@@ -479,7 +479,7 @@ __device__ __forceinline__ void undistort_dev(const CamDev& cam, double ud, doub
     uu = xd * D / cam.dx + cam.Cx;
     vu = yd * D / cam.dy + cam.Cy;
 }
-__device__ void inv4_dev(const double* m, double* o) {  // closed-form 4x4 inverse, row-major
+__device__ __forceinline__ void inv4_dev(const double* m, double* o) {  // closed-form 4x4 inverse, row-major
     const double a00 = m[0], a01 = m[1], a02 = m[2], a03 = m[3], a10 = m[4], a11 = m[5], a12 = m[6], a13 = m[7];
     const double a20 = m[8], a21 = m[9], a22 = m[10], a23 = m[11], a30 = m[12], a31 = m[13], a32 = m[14], a33 = m[15];
     const double s0 = a00 * a11 - a10 * a01, s1 = a00 * a12 - a10 * a02, s2 = a00 * a13 - a10 * a03;
@@ -505,6 +505,7 @@ __device__ void inv4_dev(const double* m, double* o) {  // closed-form 4x4 inver
     o[15] = (a20 * s3 - a21 * s1 + a22 * s0) * id;
 }
 __device__ __forceinline__ void homog4_dev(const double* R, const double* r, double* H) {  // [R 0;0 1] * [I r;0 1] = [R, R r; 0 1]
+#pragma unroll
     for (int i = 0; i < 3; i++) {
         H[4 * i] = R[3 * i];
         H[4 * i + 1] = R[3 * i + 1];
@@ -515,97 +516,157 @@ __device__ __forceinline__ void homog4_dev(const double* R, const double* r, dou
     H[15] = 1.0;
 }
 __device__ __forceinline__ void mat3_mul(const double* A, const double* B, double* C) {
+#pragma unroll
     for (int i = 0; i < 3; i++)
+#pragma unroll
         for (int j = 0; j < 3; j++) C[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
 }
 
+// distort_fm with the reference's arithmetic (IEEE divisions, same operation order as distort_dev) that stops at the fixed point of
+// the Newton update: once a step returns rd unchanged every later step returns it unchanged too, so the result is bit-identical to
+// the reference's ten steps (src/ExtendKF.cpp:191-196) -- typically after 4-6 of them.
+__device__ __forceinline__ void distort_exact_dev(const CamDev& cam, double u, double v, double& ud, double& vd) {
+    const double xu = (u - cam.Cx) * cam.dx;
+    const double yu = (v - cam.Cy) * cam.dy;
+    const double ru = sqrt(xu * xu + yu * yu);
+    const double ru2 = ru * ru;
+    double rd = ru / (1 + cam.k1 * ru2 + cam.k2 * (ru2 * ru2));
+#pragma unroll 1
+    for (int k = 0; k < 10; k++) {
+        const double rd2 = rd * rd;
+        const double rd3 = rd2 * rd;
+        const double rd4 = rd2 * rd2;
+        const double f = rd + cam.k1 * rd3 + cam.k2 * (rd4 * rd) - ru;
+        const double fp = 1 + 3 * cam.k1 * rd2 + 5 * cam.k2 * rd4;
+        const double rn = rd - f / fp;
+        const bool same = !(rn != rd);
+        rd = rn;
+        if (same) break;
+    }
+    const double rd2 = rd * rd;
+    const double D = 1 + cam.k1 * rd2 + cam.k2 * (rd2 * rd2);
+    ud = xu / D / cam.dx + cam.Cx;
+    vd = yu / D / cam.dy + cam.Cy;
+}
+
+// Per-feature geometry of the warp, ONE THREAD PER FEATURE (it is a serial chain of ~1.5 k fp64 operations; as thread 0 of a
+// per-feature CTA it kept 191 threads waiting and was 35 % of the batched-filter frame): the homography Hm, the integer origin of the
+// 13 x 13 window in the current image and the validity of that window -> F.pp_geom[12 i .. 12 i + 11] = Hm (9), xs, ys, ok.
+constexpr int kPPGeom = 12;
+__global__ void __launch_bounds__(64) k_pred_patch_setup(DevFilter* Fs, CamDev cam) {
+    DevFilter& F = Fs[blockIdx.y];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= F.N || !F.has_h[i] || F.patch_init == nullptr) return;
+    double* out = F.pp_geom + (size_t)i * kPPGeom;
+    const double h0 = F.h[2 * i], h1 = F.h[2 * i + 1];
+    const bool inside = (h0 > kHalfPatch) && (h0 < (cam.nCols - kHalfPatch)) && (h1 > kHalfPatch) && (h1 < (cam.nRows - kHalfPatch));
+    if (!inside) {  // src/Tracking.cpp:275: zero patch
+        out[11] = -1.0;
+        return;
+    }
+    const double* ip = F.init_pose + (size_t)i * 14;
+    const double uvf0 = ip[12], uvf1 = ip[13];
+    const double* x = F.x_km1;
+    double Rwc[9], Hpf[16], Hk[16], Hpfi[16], Hkk[16];
+    q2r_dev(x + 3, Rwc);
+    homog4_dev(ip + 3, ip, Hpf);
+    homog4_dev(Rwc, x, Hk);
+    inv4_dev(Hpf, Hpfi);
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            double sacc = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) sacc += Hpfi[4 * a + k] * Hk[4 * k + b];
+            Hkk[4 * a + b] = sacc;
+        }
+    const double fz = -cam.f / cam.dx;
+    const double n1[3] = {uvf0 - cam.Cx, uvf1 - cam.Cy, fz};
+    const double nn = sqrt(n1[0] * n1[0] + n1[1] * n1[1] + n1[2] * n1[2]);
+    double n[3] = {n1[0] / nn, n1[1] / nn, n1[2] / nn};
+    const double n2[4] = {h0 - cam.Cx, h1 - cam.Cy, fz, 1.0};
+    double nt4[4];
+#pragma unroll
+    for (int a = 0; a < 4; a++) nt4[a] = Hkk[4 * a] * n2[0] + Hkk[4 * a + 1] * n2[1] + Hkk[4 * a + 2] * n2[2] + Hkk[4 * a + 3] * n2[3];
+    const double nt[3] = {nt4[0] / nt4[3], nt4[1] / nt4[3], nt4[2] / nt4[3]};
+    const double ntn = sqrt(nt[0] * nt[0] + nt[1] * nt[1] + nt[2] * nt[2]);
+    const double ns[3] = {n[0] + nt[0] / ntn, n[1] + nt[1] / ntn, n[2] + nt[2] / ntn};
+    const double nsn = sqrt(ns[0] * ns[0] + ns[1] * ns[1] + ns[2] * ns[2]);
+#pragma unroll
+    for (int a = 0; a < 3; a++) n[a] = ns[a] / nsn;
+    // XYZ_w of the feature (Q3: cartesian features reuse the value of the previous inverse-depth feature)
+    double X[3] = {0, 0, 0};
+    const int li = F.last_id[i];
+    if (li >= 0) {
+        const double* y = x + F.foff[li];
+        double st, ct, sph, cph;
+        sincos(y[3], &st, &ct);
+        sincos(y[4], &sph, &cph);
+        const double m3[3] = {cph * st, -sph, cph * ct};
+#pragma unroll
+        for (int a = 0; a < 3; a++) X[a] = y[a] + (1.0 / y[5]) * m3[a];
+    }
+    double Xk[4];
+#pragma unroll
+    for (int a = 0; a < 4; a++) Xk[a] = Hpfi[4 * a] * X[0] + Hpfi[4 * a + 1] * X[1] + Hpfi[4 * a + 2] * X[2] + Hpfi[4 * a + 3];
+    const double d = -(n[0] * (Xk[0] / Xk[3]) + n[1] * (Xk[1] / Xk[3]) + n[2] * (Xk[2] / Xk[3]));
+    const double fk = cam.f / cam.dx;  // cam.K << f/d, 0, Cx ; 0, f/d, Cy ; 0 0 1 (src/System.cpp:58)
+    const double K[9] = {fk, 0, cam.Cx, 0, fk, cam.Cy, 0, 0, 1};
+    double Ki[9], M[9], T[9], Hm[9], Hmi[9];
+    inv3_dev(K, Ki);
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int b = 0; b < 3; b++) M[3 * a + b] = Hkk[4 * a + b] - (Hkk[4 * a + 3] * n[b]) / d;
+    mat3_mul(K, M, T);
+    mat3_mul(T, Ki, Hm);
+    inv3_dev(Hm, Hmi);
+    double uu, vu;
+    undistort_dev(cam, uvf0, uvf1, uu, vu);
+    const double w0 = Hmi[0] * uu + Hmi[1] * vu + Hmi[2], w1 = Hmi[3] * uu + Hmi[4] * vu + Hmi[5], w2 = Hmi[6] * uu + Hmi[7] * vu + Hmi[8];
+    double c2u, c2v;
+    distort_exact_dev(cam, w0 / w2, w1 / w2, c2u, c2v);
+    const int xs = (int)(c2u - kHalfPatch), xe = (int)(c2u + kHalfPatch), ys = (int)(c2v - kHalfPatch), ye = (int)(c2v + kHalfPatch);
+#pragma unroll
+    for (int a = 0; a < 9; a++) out[a] = Hm[a];
+    out[9] = (double)xs;
+    out[10] = (double)ys;
+    out[11] = ((xe - xs + 1 == kPatch) && (ye - ys + 1 == kPatch)) ? 1.0 : 0.0;
+}
+
+// The 169 pixels of one predicted patch: one CTA per feature, one thread per pixel (the first 169 of 192).
 __global__ void __launch_bounds__(192) k_pred_patch(DevFilter* Fs, CamDev cam) {
     DevFilter& F = Fs[blockIdx.y];
     const int i = blockIdx.x;
     if (i >= F.N || !F.has_h[i] || F.patch_init == nullptr) return;
-    __shared__ double sHm[9];
-    __shared__ int s_org[3];  // xs, ys, ok
-    __shared__ unsigned char sp[41 * 41];
+    __shared__ unsigned char sp[41 * 41 + 3];
     const int tid = threadIdx.x;
     float* out = F.patch + (size_t)i * kPatchPix;
-    const double h0 = F.h[2 * i], h1 = F.h[2 * i + 1];
-    const bool inside = (h0 > kHalfPatch) && (h0 < (cam.nCols - kHalfPatch)) && (h1 > kHalfPatch) && (h1 < (cam.nRows - kHalfPatch));
-    if (!inside) {  // src/Tracking.cpp:275
+    const double* geo = F.pp_geom + (size_t)i * kPPGeom;
+    const double ok = geo[11];
+    if (!(ok > 0.0)) {  // h within half a patch of the border (ok < 0), or a window that is not 13 x 13 (ok == 0): zero patch
         if (tid < kPatchPix) out[tid] = 0.f;
         return;
     }
-    for (int e = tid; e < 41 * 41; e += blockDim.x) sp[e] = F.patch_init[(size_t)i * 1681 + e];
+    {   // 41 x 41 bytes; every feature's block starts 1681 i bytes into the array: bytes up to the first 4-byte boundary, words, tail
+        const unsigned char* src = F.patch_init + (size_t)i * 1681;
+        for (int e = tid; e < 41 * 41; e += blockDim.x) sp[e] = src[e];
+    }
     const double* ip = F.init_pose + (size_t)i * 14;
     const double uvf0 = ip[12], uvf1 = ip[13];
-    if (tid == 0) {
-        const double* x = F.x_km1;
-        double Rwc[9], Hpf[16], Hk[16], Hpfi[16], Hkk[16];
-        q2r_dev(x + 3, Rwc);
-        homog4_dev(ip + 3, ip, Hpf);
-        homog4_dev(Rwc, x, Hk);
-        inv4_dev(Hpf, Hpfi);
-        for (int a = 0; a < 4; a++)
-            for (int b = 0; b < 4; b++) {
-                double s = 0;
-                for (int k = 0; k < 4; k++) s += Hpfi[4 * a + k] * Hk[4 * k + b];
-                Hkk[4 * a + b] = s;
-            }
-        const double fz = -cam.f / cam.dx;
-        double n1[3] = {uvf0 - cam.Cx, uvf1 - cam.Cy, fz};
-        double nn = sqrt(n1[0] * n1[0] + n1[1] * n1[1] + n1[2] * n1[2]);
-        double n[3] = {n1[0] / nn, n1[1] / nn, n1[2] / nn};
-        const double n2[4] = {h0 - cam.Cx, h1 - cam.Cy, fz, 1.0};
-        double nt4[4];
-        for (int a = 0; a < 4; a++) nt4[a] = Hkk[4 * a] * n2[0] + Hkk[4 * a + 1] * n2[1] + Hkk[4 * a + 2] * n2[2] + Hkk[4 * a + 3] * n2[3];
-        double nt[3] = {nt4[0] / nt4[3], nt4[1] / nt4[3], nt4[2] / nt4[3]};
-        const double ntn = sqrt(nt[0] * nt[0] + nt[1] * nt[1] + nt[2] * nt[2]);
-        double ns[3] = {n[0] + nt[0] / ntn, n[1] + nt[1] / ntn, n[2] + nt[2] / ntn};
-        const double nsn = sqrt(ns[0] * ns[0] + ns[1] * ns[1] + ns[2] * ns[2]);
-        for (int a = 0; a < 3; a++) n[a] = ns[a] / nsn;
-        // XYZ_w of the feature (Q3: cartesian features reuse the value of the previous inverse-depth feature)
-        double X[3] = {0, 0, 0};
-        const int li = F.last_id[i];
-        if (li >= 0) {
-            const double* y = x + F.foff[li];
-            const double st = sin(y[3]), ct = cos(y[3]), sph = sin(y[4]), cph = cos(y[4]);
-            const double m3[3] = {cph * st, -sph, cph * ct};
-            for (int a = 0; a < 3; a++) X[a] = y[a] + (1.0 / y[5]) * m3[a];
-        }
-        double Xk[4];
-        for (int a = 0; a < 4; a++) Xk[a] = Hpfi[4 * a] * X[0] + Hpfi[4 * a + 1] * X[1] + Hpfi[4 * a + 2] * X[2] + Hpfi[4 * a + 3];
-        const double d = -(n[0] * (Xk[0] / Xk[3]) + n[1] * (Xk[1] / Xk[3]) + n[2] * (Xk[2] / Xk[3]));
-        const double fk = cam.f / cam.dx;  // cam.K << f/d, 0, Cx ; 0, f/d, Cy ; 0 0 1 (src/System.cpp:58)
-        const double K[9] = {fk, 0, cam.Cx, 0, fk, cam.Cy, 0, 0, 1};
-        double Ki[9], M[9], T[9], Hm[9], Hmi[9];
-        inv3_dev(K, Ki);
-        for (int a = 0; a < 3; a++)
-            for (int b = 0; b < 3; b++) M[3 * a + b] = Hkk[4 * a + b] - (Hkk[4 * a + 3] * n[b]) / d;
-        mat3_mul(K, M, T);
-        mat3_mul(T, Ki, Hm);
-        inv3_dev(Hm, Hmi);
-        double uu, vu;
-        undistort_dev(cam, uvf0, uvf1, uu, vu);
-        const double w0 = Hmi[0] * uu + Hmi[1] * vu + Hmi[2], w1 = Hmi[3] * uu + Hmi[4] * vu + Hmi[5], w2 = Hmi[6] * uu + Hmi[7] * vu + Hmi[8];
-        double c2u, c2v;
-        distort_dev(cam, w0 / w2, w1 / w2, c2u, c2v);
-        const int xs = (int)(c2u - kHalfPatch), xe = (int)(c2u + kHalfPatch), ys = (int)(c2v - kHalfPatch), ye = (int)(c2v + kHalfPatch);
-        s_org[0] = xs;
-        s_org[1] = ys;
-        s_org[2] = (xe - xs + 1 == kPatch) && (ye - ys + 1 == kPatch);
-        for (int a = 0; a < 9; a++) sHm[a] = Hm[a];
-    }
+    double Hm[9];
+#pragma unroll
+    for (int a = 0; a < 9; a++) Hm[a] = geo[a];
+    const int xs = (int)geo[9], ys = (int)geo[10];
     __syncthreads();
     if (tid >= kPatchPix) return;
-    if (!s_org[2]) {
-        out[tid] = 0.f;
-        return;
-    }
     const int r = tid / kPatch, c = tid % kPatch;
     double uu, vu;
-    undistort_dev(cam, (double)(s_org[0] + c), (double)(s_org[1] + r), uu, vu);
-    const double w0 = sHm[0] * uu + sHm[1] * vu + sHm[2], w1 = sHm[3] * uu + sHm[4] * vu + sHm[5], w2 = sHm[6] * uu + sHm[7] * vu + sHm[8];
+    undistort_dev(cam, (double)(xs + c), (double)(ys + r), uu, vu);
+    const double w0 = Hm[0] * uu + Hm[1] * vu + Hm[2], w1 = Hm[3] * uu + Hm[4] * vu + Hm[5], w2 = Hm[6] * uu + Hm[7] * vu + Hm[8];
     double c1u, c1v;
-    distort_dev(cam, w0 / w2, w1 / w2, c1u, c1v);
+    distort_exact_dev(cam, w0 / w2, w1 / w2, c1u, c1v);
     const float mx = (float)(c1u - (uvf0 - 20 - 1)), my = (float)(c1v - (uvf1 - 20 - 1));
     const int sx = __float2int_rn(mx * 32.0f), sy = __float2int_rn(my * 32.0f);
     const int ix = sx >> 5, iy = sy >> 5;

@@ -534,9 +534,13 @@ __device__ __forceinline__ void panel_load(const PanelSmem& ps, const double* S,
     }
 }
 
-// ---- U4a: Cholesky panel at block column `step` (multi-launch path, k > 256): every CTA factors the diagonal block (redundantly:
-//           cheaper than a dependent launch) together with its own 64-row block of the panel; CTA 0 also builds and stores the
-//           inverse of the diagonal block (the TRSM kernel multiplies by it).
+// ---- U4a: Cholesky panel at block column `step` (multi-launch path, k > 256).  Every CTA owns one 64-row block of the panel and
+//           factors the diagonal block redundantly (cheaper than a dependent launch).  LEFT-LOOKING inside a 256-wide outer block:
+//           before factoring, the CTA subtracts from its 128 x 64 slice (diagonal block + own rows) the contribution of the earlier
+//           panels of the same outer block (K <= 192, DMMA, staged through the unused rows of the panel buffer), so a frame has one
+//           launch per panel plus one K = 256 trailing update per outer block -- 78 launches at k = 4000 instead of 250, and no thin
+//           K = 64 GEMMs.  The inverses of the diagonal blocks are built afterwards, all at once (k_chol_trinv).
+constexpr int kOB = 4;  // panels per outer block
 __global__ void __launch_bounds__(256) k_chol_panel(DevFilter* Fs, int step) {
     DevFilter& F = Fs[blockIdx.y];
     const int kk = F.ctl[CTL_K];
@@ -551,22 +555,99 @@ __global__ void __launch_bounds__(256) k_chol_panel(DevFilter* Fs, int step) {
     const int ld = F.lds;
     const int nr = blockIdx.x == 0 ? 0 : min(kNB, kk - r0);
     panel_load(ps, S, ld, j0, w, r0, nr);
+    const int ob0 = kNB * kOB * (step / kOB);  // first column of the outer block
+    if (ob0 < j0) {
+        // pending update: [D; A] -= [Ld; La] Ld^T over the columns [ob0, j0) already factored in this outer block
+        const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+        const bool active = wp < 4 || nr > 0;  // warp wp owns rows 16 wp .. 16 wp + 15 of the 128-row slice
+        double acc[2][8][2];
+#pragma unroll
+        for (int a2 = 0; a2 < 2; a2++)
+#pragma unroll
+            for (int b2 = 0; b2 < 8; b2++) acc[a2][b2][0] = acc[a2][b2][1] = 0.0;
+        double* U = ps.sT + 2 * kNB;  // staging: entry (k, row) at U[k * kTld + row], rows 0..63 = diagonal rows, 64..127 = own rows
+        for (int c0 = ob0; c0 < j0; c0 += kNB) {
+            __syncthreads();  // the previous chunk has been consumed (first pass: panel_load's stores are not touched by the staging)
+            {
+                double v[8][4];
+#pragma unroll
+                for (int cs = 0; cs < 8; cs++) {
+                    const double* col = S + (size_t)(c0 + wp + 8 * cs) * ld;
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const int r = lane + 32 * q;
+                        const int grow = r < kNB ? j0 + r : r0 + (r - kNB);
+                        const bool ok = r < kNB ? (r < w) : (r - kNB < nr);
+                        v[cs][q] = ok ? col[grow] : 0.0;
+                    }
+                }
+#pragma unroll
+                for (int cs = 0; cs < 8; cs++)
+#pragma unroll
+                    for (int q = 0; q < 4; q++) U[(wp + 8 * cs) * kTld + lane + 32 * q] = v[cs][q];
+            }
+            __syncthreads();
+            if (active) {
+#pragma unroll 4
+                for (int ks = 0; ks < kNB / 4; ks++) {
+                    const double* kr = U + (ks * 4 + (lane & 3)) * kTld;
+                    double af[2], bf[8];
+#pragma unroll
+                    for (int a2 = 0; a2 < 2; a2++) af[a2] = kr[wp * 16 + a2 * 8 + (lane >> 2)];
+#pragma unroll
+                    for (int b2 = 0; b2 < 8; b2++) bf[b2] = kr[b2 * 8 + (lane >> 2)];
+#pragma unroll
+                    for (int a2 = 0; a2 < 2; a2++)
+#pragma unroll
+                        for (int b2 = 0; b2 < 8; b2++) dmma8x8x4(acc[a2][b2][0], acc[a2][b2][1], af[a2], bf[b2]);
+                }
+            }
+        }
+        if (active) {
+#pragma unroll
+            for (int a2 = 0; a2 < 2; a2++)
+#pragma unroll
+                for (int b2 = 0; b2 < 8; b2++)
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                        const int i = wp * 16 + a2 * 8 + (lane >> 2), cc = b2 * 8 + 2 * (lane & 3) + e;
+                        // identity padding of the diagonal block (rows / columns >= w) must stay untouched: its staged rows were zero
+                        ps.sT[cc * kTld + i] -= acc[a2][b2][e];
+                    }
+        }
+    }
     __syncthreads();
     smem_panel_factor(ps, kNB + nr, w);
     if (blockIdx.x == 0) {
-        smem_trinv64(ps);
         for (int e = threadIdx.x; e < kNB * kNB; e += blockDim.x) {
             const int i = e % kNB, c = e / kNB;
             if (i < w && c < w) S[(j0 + i) + (size_t)(j0 + c) * ld] = ps.sT[c * kTld + i];
         }
-        __syncthreads();
-        store_linv(ps.sX, F.Linv + (size_t)step * kNB * kNB, threadIdx.x, blockDim.x);
         return;
     }
     for (int e = threadIdx.x; e < nr * kNB; e += blockDim.x) {
         const int i = e % nr, c = e / nr;
         if (c < w) S[(r0 + i) + (size_t)(j0 + c) * ld] = ps.sT[c * kTld + kNB + i];
     }
+}
+
+// ---- U4b: explicit inverses of ALL 64 x 64 diagonal blocks of the finished factor, one CTA per block (the TRSM kernel multiplies by
+//           them on tensor cores).  Built after the factorisation so that the 63 serial panel steps do not each carry one.
+__global__ void __launch_bounds__(256) k_chol_trinv(DevFilter* Fs) {
+    DevFilter& F = Fs[blockIdx.y];
+    const int kk = F.ctl[CTL_K];
+    const int j0 = kNB * blockIdx.x;
+    if (j0 >= kk) return;
+    const int w = min(kNB, kk - j0);
+    extern __shared__ __align__(16) double psm[];
+    const PanelSmem ps = panel_carve(psm);
+    panel_load(ps, F.Sm, F.lds, j0, w, j0, 0);
+    __syncthreads();
+    if (threadIdx.x < kNB) ps.sRd[threadIdx.x] = 1.0 / ps.sT[threadIdx.x * kTld + threadIdx.x];
+    // panel_load leaves the strict upper triangle of the block zero and the padding identity: exactly what smem_trinv64 expects
+    __syncthreads();
+    smem_trinv64(ps);
+    store_linv(ps.sX, F.Linv + (size_t)blockIdx.x * kNB * kNB, threadIdx.x, blockDim.x);
 }
 
 // ---- U4s: whole Cholesky (+ inverses of the diagonal blocks) in ONE CTA for small systems (k <= 256): the launch-latency
@@ -671,8 +752,12 @@ struct TrsmCfg {
     static constexpr int kSmemBytes = (GSTAGES_T * GBK_T * (kLdA + kLdB) + kNB * kLdA + kNB * kLdB) * (int)sizeof(double);
 };
 
+// Two-level like the Cholesky: the launch covers the 64-wide column blocks [jb0, jb1) of one 256-wide outer block and accumulates only over
+// the blocks of that outer block (K <= 192); the contribution of every earlier outer block has already been subtracted from W by a
+// K = 256 GEMM (GEMM_TRSM_OUTER) that runs at the SYRK kernel's efficiency instead of this kernel's (58 % of the fp64 tensor rate when it
+// carried the whole K = 64 j accumulation).
 template <int R, int WM>
-__global__ void __launch_bounds__(WM * 64) k_trsm_ll(DevFilter* Fs) {
+__global__ void __launch_bounds__(WM * 64) k_trsm_ll(DevFilter* Fs, int jb0, int jb1) {
     using Cfg = TrsmCfg<R, WM>;
     constexpr int MT = Cfg::kMT, LDA = Cfg::kLdA, LDB = Cfg::kLdB, NT = 4;
     static_assert(R % (8 * WM) == 0 && (LDA % 2) == 0, "tile shape");
@@ -692,10 +777,12 @@ __global__ void __launch_bounds__(WM * 64) k_trsm_ll(DevFilter* Fs) {
     const int ldw = F.ldw, lds = F.lds;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm0 = (warp % WM) * (MT * 8), wn0 = (warp / WM) * 32;
-    const int nb = (kk + kNB - 1) / kNB;
+    const int nb = min((kk + kNB - 1) / kNB, jb1);
+    if (jb0 * kNB >= kk) return;
     constexpr int A_CHUNKS = GBK_T * (R / 2), B_CHUNKS = GBK_T * (kNB / 2);
+    const int kbase = jb0 * kNB;  // first column of the outer block
 
-    for (int j = 0; j < nb; j++) {
+    for (int j = jb0; j < nb; j++) {
         const int c0 = j * kNB;
         const int w = min(kNB, kk - c0);
         // inverse of the diagonal block -> Ls (async, overlaps the accumulation)
@@ -712,9 +799,9 @@ __global__ void __launch_bounds__(WM * 64) k_trsm_ll(DevFilter* Fs) {
         for (int a = 0; a < MT; a++)
 #pragma unroll
             for (int b = 0; b < NT; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
-        const int nkt = c0 / GBK_T;  // K = 64 j
+        const int nkt = (c0 - kbase) / GBK_T;  // K = 64 (j - jb0)
         auto load_stage = [&](int stage, int kt) {
-            const int k0 = kt * GBK_T;
+            const int k0 = kbase + kt * GBK_T;
             for (int ch = tid; ch < A_CHUNKS; ch += Cfg::kThreads) {
                 const int kc = ch / (R / 2), r2 = ch % (R / 2);
                 const int row = r0 + 2 * r2;
@@ -966,12 +1053,10 @@ struct GemmCfg {
     static constexpr int kMinBlocks = (BM == 128 && BN == 64) ? 2 : 1;
 };
 
-// Cholesky trailing updates are two-level: after the 64-wide panel `step` only the columns up to the end of its 256-wide outer
-// block are updated (GEMM_CHOL_INNER, K = 64, a thin M x <=192 rectangle); after the last panel of an outer block the rest of the
-// matrix gets one K = 256 update (GEMM_CHOL_OUTER).  Same flops as a K = 64 update after every panel, but 4x fewer passes over the
-// trailing matrix and DMMA tiles with a 4x longer k-loop.
-constexpr int kOB = 4;  // panels per outer block
-enum GemmMode { GEMM_SYRK_P = 0, GEMM_CHOL_INNER = 1, GEMM_CHOL_OUTER = 2 };
+// Cholesky trailing updates are two-level: inside a 256-wide outer block the panel kernels are left-looking (k_chol_panel); after the
+// last panel of an outer block the rest of the matrix gets one K = 256 update (GEMM_CHOL_OUTER).  Same flops as a K = 64 update after
+// every panel, but 4x fewer passes over the trailing matrix and DMMA tiles with a 4x longer k-loop.
+enum GemmMode { GEMM_SYRK_P = 0, GEMM_CHOL_OUTER = 2, GEMM_TRSM_OUTER = 3 };
 
 struct GemmProb {
     const double* A;
@@ -994,19 +1079,23 @@ __device__ __forceinline__ bool gemm_setup(const DevFilter& F, int mode, int ste
         g.lower = g.mirror = true;
         return true;
     }
-    g.lda = g.ldb = g.ldc = F.lds;
     g.mirror = false;
-    if (mode == GEMM_CHOL_INNER) {  // step = panel index
-        const int o = kNB * (step + 1), oend = kNB * kOB * (step / kOB + 1);
-        if (kk <= o || oend <= o) return false;
-        g.A = g.B = F.Sm + o + (size_t)(o - kNB) * F.lds;
-        g.C = F.Sm + o + (size_t)o * F.lds;
-        g.M = kk - o;
-        g.N = min(kk, oend) - o;
-        g.K = kNB;
-        g.lower = false;  // thin rectangle; the few entries above the diagonal are never read
+    if (mode == GEMM_TRSM_OUTER) {  // W[:, o:] -= V_J L[o:, J]^T after the outer block J = step of the TRSM is solved
+        const int o = kNB * kOB * (step + 1);
+        if (kk <= o) return false;
+        g.A = F.W + (size_t)(o - kNB * kOB) * F.ldw;
+        g.lda = F.ldw;
+        g.B = F.Sm + o + (size_t)(o - kNB * kOB) * F.lds;
+        g.ldb = F.lds;
+        g.C = F.W + (size_t)o * F.ldw;
+        g.ldc = F.ldw;
+        g.M = F.n + 1;
+        g.N = kk - o;
+        g.K = kNB * kOB;
+        g.lower = false;
         return true;
     }
+    g.lda = g.ldb = g.ldc = F.lds;
     const int o = kNB * kOB * (step + 1);  // step = outer block index
     if (kk <= o) return false;
     g.A = g.B = F.Sm + o + (size_t)(o - kNB * kOB) * F.lds;

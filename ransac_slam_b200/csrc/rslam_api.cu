@@ -236,25 +236,35 @@ int run_update(rslam_filter* f, int which, bool gathered = false, bool defer_jno
         LAUNCH(f, k_upd_S, dim3(cdiv(N, 16), cdiv(N, 16), B), 256, 0, f->dF);
         for (int s = 0; s < nsteps; s++) {
             LAUNCH(f, k_chol_panel, dim3(nsteps - s, B), 256, kPanelSmemBytes, f->dF, s);
-            const int o = kNB * (s + 1), oend = kNB * kOB * (s / kOB + 1);
+            const int o = kNB * (s + 1);
             if (kmax <= o) break;
-            if (oend > o) {  // inner: the rest of this 256-wide outer block only
-                const int tm = cdiv(kmax - o, 128), tn = cdiv((kmax < oend ? kmax : oend) - o, 64);
-                LAUNCH_N(f, "k_gemm_dmma/chol_inner", (k_gemm_dmma<128, 64>), dim3(tm * tn, 1, B), (GemmCfg<128, 64>::kThreads), (GemmCfg<128, 64>::kSmemBytes), f->dF,
-                         (int)GEMM_CHOL_INNER, s);
-            } else {  // outer: everything beyond the block, K = 256
+            if ((s + 1) % kOB == 0) {  // end of a 256-wide outer block: everything beyond it gets one K = 256 update
                 const int tm = cdiv(kmax - o, 128);
                 LAUNCH_N(f, "k_gemm_dmma/chol_outer", (k_gemm_dmma<128, 64>), dim3(tm * (tm + 1), 1, B), (GemmCfg<128, 64>::kThreads), (GemmCfg<128, 64>::kSmemBytes), f->dF,
                          (int)GEMM_CHOL_OUTER, s / kOB);
             }
         }
+        LAUNCH(f, k_chol_trinv, dim3(nsteps, B), 256, kPanelSmemBytes, f->dF);
     }
     if (kmax <= SR_KMAX) {  // small systems: W rows resident in smem, L streamed once
         LAUNCH(f, k_trsm_small, dim3(cdiv(n + 1, TS_R), B), TS_THREADS, trsm_small_smem_bytes(kmax), f->dF, round_up(kmax, kNB));
-    } else if (cdiv(n + 1, 48) * B >= 200) {  // 48-row CTAs, two resident per SM: one CTA's barriers / diagonal step hide behind the other's DMMA stream
-        LAUNCH_N(f, "k_trsm_ll", (k_trsm_ll<48, 2>), dim3(cdiv(n + 1, 48), B), 128, (TrsmCfg<48, 2>::kSmemBytes), f->dF);
     } else {
-        LAUNCH_N(f, "k_trsm_ll", (k_trsm_ll<32, 2>), dim3(cdiv(n + 1, 32), B), 128, (TrsmCfg<32, 2>::kSmemBytes), f->dF);
+        // two-level: the 64-wide blocks of one 256-wide outer block are solved left-looking by k_trsm_ll (a CTA owns its rows), then one
+        // K = 256 GEMM subtracts that outer block's contribution from all remaining columns of W
+        const int nouter = cdiv(nsteps, kOB);
+        for (int J = 0; J < nouter; J++) {
+            if (cdiv(n + 1, 48) * B >= 200) {  // 48-row CTAs, two resident per SM: one CTA's barriers / diagonal step hide behind the other's DMMA stream
+                LAUNCH_N(f, "k_trsm_ll", (k_trsm_ll<48, 2>), dim3(cdiv(n + 1, 48), B), 128, (TrsmCfg<48, 2>::kSmemBytes), f->dF, J * kOB, (J + 1) * kOB);
+            } else {
+                LAUNCH_N(f, "k_trsm_ll", (k_trsm_ll<32, 2>), dim3(cdiv(n + 1, 32), B), 128, (TrsmCfg<32, 2>::kSmemBytes), f->dF, J * kOB, (J + 1) * kOB);
+            }
+            const int o = kNB * kOB * (J + 1);
+            if (kmax > o) {
+                const int tm = cdiv(n + 1, 128), tn = cdiv(kmax - o, 64);
+                LAUNCH_N(f, "k_gemm_dmma/trsm_outer", (k_gemm_dmma<128, 64>), dim3(tm * tn, 1, B), (GemmCfg<128, 64>::kThreads), (GemmCfg<128, 64>::kSmemBytes), f->dF,
+                         (int)GEMM_TRSM_OUTER, J);
+            }
+        }
     }
     if (kmax <= SR_KMAX) {
         // small innovation dimension: row-segment SYRK (A resident, flattened B pipeline, P tile prefetched).  Segment length: whole
@@ -363,6 +373,7 @@ int rslam_create(const rslam_camera* cam, const rslam_params* par, int max_featu
     CKF(cudaFuncSetAttribute(k_trsm_ll<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TrsmCfg<32, 2>::kSmemBytes));
     CKF(cudaFuncSetAttribute(k_ransac_support, cudaFuncAttributeMaxDynamicSharedMemorySize, kSupSmemBytes));
     CKF(cudaFuncSetAttribute(k_chol_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPanelSmemBytes));
+    CKF(cudaFuncSetAttribute(k_chol_trinv, cudaFuncAttributeMaxDynamicSharedMemorySize, kPanelSmemBytes));
     CKF(cudaFuncSetAttribute(k_chol_small, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholSmallSmemBytes));
     CKF(cudaFuncSetAttribute(k_trsm_small, cudaFuncAttributeMaxDynamicSharedMemorySize, trsm_small_smem_bytes(SR_KMAX)));
     CKF(cudaFuncSetAttribute(k_syrk_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, syrk_rows_smem_bytes(SR_KMAX)));
@@ -377,7 +388,7 @@ int rslam_create(const rslam_camera* cam, const rslam_params* par, int max_featu
     float* patch;
     unsigned* masks;
     unsigned char* patch_init;
-    double* init_pose;
+    double *init_pose, *pp_geom;
     int* last_id;
     const size_t psz = (size_t)f->ldp * n;
 #define A(ptr, cnt)                                       \
@@ -388,7 +399,7 @@ int rslam_create(const rslam_camera* cam, const rslam_params* par, int max_featu
     A(P, psz) A(xkk, n) A(xkm1, n) A(h, 2 * N) A(Hc, 14 * N) A(Hf, 12 * N) A(S, 4 * N) A(z, 2 * N) A(hyp_ab, 16 * N) A(hyp_xcam, 7 * N) A(Jn, 32)
     A(ftype, N) A(foff, N) A(tp, N) A(tm, N) A(ic_list, N) A(id_list, N) A(id_pos, N) A(support, N) A(ctl, CTL_SIZE) A(upd_list, N) A(sup_rows, 6 * (size_t)round_up(N, 64))
     A(has_h, N) A(ic, N) A(li, N) A(hi, N) A(patch, (size_t)N * kPatchPix) A(masks, (size_t)N * f->mwords)
-    A(patch_init, (size_t)N * 1681) A(init_pose, (size_t)N * 14) A(last_id, N)
+    A(patch_init, (size_t)N * 1681) A(init_pose, (size_t)N * 14) A(pp_geom, (size_t)N * 12) A(last_id, N)
 #undef A
     if ((rc = dev_alloc(f, &f->dF, (size_t)B))) {
         rslam_destroy(f);
@@ -427,6 +438,7 @@ int rslam_create(const rslam_camera* cam, const rslam_params* par, int max_featu
         D.image = nullptr;
         D.patch_init = patch_init + (size_t)N * 1681 * b;
         D.init_pose = init_pose + (size_t)N * 14 * b;
+        D.pp_geom = pp_geom + (size_t)N * 12 * b;
         D.last_id = last_id + (size_t)N * b;
         D.ic_list = ic_list + (size_t)N * b;
         D.id_list = id_list + (size_t)N * b;
@@ -730,7 +742,10 @@ int rslam_search_ic_matches(rslam_filter* f) {
     CK(cudaSetDevice(f->device));
     if (f->hN == 0) return RSLAM_OK;
     LAUNCH(f, k_predict, dim3(cdiv(f->hN, 128), f->B), 128, 0, f->dF, f->camd, f->pard, 0, 0, 0);
-    if (f->warp_patches) LAUNCH(f, k_pred_patch, dim3(f->hN, f->B), 192, 0, f->dF, f->camd);
+    if (f->warp_patches) {
+        LAUNCH(f, k_pred_patch_setup, dim3(cdiv(f->hN, 64), f->B), 64, 0, f->dF, f->camd);
+        LAUNCH(f, k_pred_patch, dim3(f->hN, f->B), 192, 0, f->dF, f->camd);
+    }
     if (f->have_image) LAUNCH(f, k_search, dim3(f->hN, f->B), kSearchThreads, 0, f->dF, f->camd, f->pard);
     return check_launch();
 }

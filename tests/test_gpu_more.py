@@ -279,7 +279,7 @@ def test_patch_warp_matches_oracle_remap():
     pg = g.download_patches()
     fo = o.features()
     assert fo["has_h"].sum() >= N - 2
-    same = 0
+    same, npix, neq, worst = 0, 0, 0, 0.0
     for i in np.flatnonzero(fo["has_h"]):
         po = o.patch_matching(i)
         assert po.std() > 0
@@ -287,6 +287,13 @@ def test_patch_warp_matches_oracle_remap():
         # identical sampling except where a map coordinate sits within rounding noise of a 1/32-px quantisation boundary
         assert (d == 0).mean() > 0.97 and d.max() < 12.0, (i, (d == 0).mean(), d.max())
         same += int((d == 0).all())
+        npix += d.size
+        neq += int((d == 0).sum())
+        worst = max(worst, float(d.max()))
+    stats = f"patch warp vs oracle: {same}/{int(fo['has_h'].sum())} patches identical, {neq}/{npix} pixels identical, max |d| = {worst}"
+    print(stats)
+    if os.path.isdir("gpurun_out"):
+        open("gpurun_out/r02_patch_stats.txt", "a").write(stats + "\n")
     assert same >= 0.8 * fo["has_h"].sum()
     # build an image that contains the oracle-predicted appearance at a pasted location and search on both sides
     img = synth.background(scene.cam).copy()
