@@ -566,27 +566,30 @@ __global__ void __launch_bounds__(256) k_chol_panel(DevFilter* Fs, int step) {
 #pragma unroll
             for (int b2 = 0; b2 < 8; b2++) acc[a2][b2][0] = acc[a2][b2][1] = 0.0;
         double* U = ps.sT + 2 * kNB;  // staging: entry (k, row) at U[k * kTld + row], rows 0..63 = diagonal rows, 64..127 = own rows
-        for (int c0 = ob0; c0 < j0; c0 += kNB) {
-            __syncthreads();  // the previous chunk has been consumed (first pass: panel_load's stores are not touched by the staging)
-            {
-                double v[8][4];
+        // chunk c0: 64 columns x 128 rows, 32 values per thread, fetched into registers one chunk ahead (in flight during the DMMA work)
+        double v[8][4];
+        auto fetch = [&](int c0) {
 #pragma unroll
-                for (int cs = 0; cs < 8; cs++) {
-                    const double* col = S + (size_t)(c0 + wp + 8 * cs) * ld;
+            for (int cs = 0; cs < 8; cs++) {
+                const double* col = S + (size_t)(c0 + wp + 8 * cs) * ld;
 #pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        const int r = lane + 32 * q;
-                        const int grow = r < kNB ? j0 + r : r0 + (r - kNB);
-                        const bool ok = r < kNB ? (r < w) : (r - kNB < nr);
-                        v[cs][q] = ok ? col[grow] : 0.0;
-                    }
+                for (int q = 0; q < 4; q++) {
+                    const int r = lane + 32 * q;
+                    const int grow = r < kNB ? j0 + r : r0 + (r - kNB);
+                    const bool ok = r < kNB ? (r < w) : (r - kNB < nr);
+                    v[cs][q] = ok ? col[grow] : 0.0;
                 }
-#pragma unroll
-                for (int cs = 0; cs < 8; cs++)
-#pragma unroll
-                    for (int q = 0; q < 4; q++) U[(wp + 8 * cs) * kTld + lane + 32 * q] = v[cs][q];
             }
+        };
+        fetch(ob0);
+        for (int c0 = ob0; c0 < j0; c0 += kNB) {
+            __syncthreads();  // the previous chunk has been consumed
+#pragma unroll
+            for (int cs = 0; cs < 8; cs++)
+#pragma unroll
+                for (int q = 0; q < 4; q++) U[(wp + 8 * cs) * kTld + lane + 32 * q] = v[cs][q];
             __syncthreads();
+            if (c0 + kNB < j0) fetch(c0 + kNB);
             if (active) {
 #pragma unroll 4
                 for (int ks = 0; ks < kNB / 4; ks++) {
@@ -1066,7 +1069,7 @@ struct GemmProb {
     bool lower, mirror;
 };
 
-__device__ __forceinline__ bool gemm_setup(const DevFilter& F, int mode, int step, GemmProb& g) {
+__device__ __forceinline__ bool gemm_setup(const DevFilter& F, int mode, int step, int ob, GemmProb& g) {
     const int kk = F.ctl[CTL_K];
     if (mode == GEMM_SYRK_P) {
         if (kk <= 0) return false;
@@ -1080,18 +1083,19 @@ __device__ __forceinline__ bool gemm_setup(const DevFilter& F, int mode, int ste
         return true;
     }
     g.mirror = false;
-    if (mode == GEMM_TRSM_OUTER) {  // W[:, o:] -= V_J L[o:, J]^T after the outer block J = step of the TRSM is solved
-        const int o = kNB * kOB * (step + 1);
+    if (mode == GEMM_TRSM_OUTER) {  // W[:, o:] -= V_J L[o:, J]^T after the outer block J = step of the TRSM is solved; `ob` 64-blocks wide
+        const int wob = kNB * ob;
+        const int o = wob * (step + 1);
         if (kk <= o) return false;
-        g.A = F.W + (size_t)(o - kNB * kOB) * F.ldw;
+        g.A = F.W + (size_t)(o - wob) * F.ldw;
         g.lda = F.ldw;
-        g.B = F.Sm + o + (size_t)(o - kNB * kOB) * F.lds;
+        g.B = F.Sm + o + (size_t)(o - wob) * F.lds;
         g.ldb = F.lds;
         g.C = F.W + (size_t)o * F.ldw;
         g.ldc = F.ldw;
         g.M = F.n + 1;
         g.N = kk - o;
-        g.K = kNB * kOB;
+        g.K = wob;
         g.lower = false;
         return true;
     }
@@ -1115,7 +1119,7 @@ __global__ void __launch_bounds__(GemmCfg<BM, BN>::kThreads, GemmCfg<BM, BN>::kM
     constexpr int LDA = Cfg::kLdA, LDB = Cfg::kLdB, MT = Cfg::kMT, NT = Cfg::kNT, THREADS = Cfg::kThreads;
     const DevFilter& F = Fs[blockIdx.z];
     GemmProb g;
-    if (!gemm_setup(F, mode & 0xff, step, g)) return;
+    if (!gemm_setup(F, mode & 0xff, step, mode >> 16, g)) return;
     int ti, tj;
     const int tm = (g.M + BM - 1) / BM, tn = (g.N + BN - 1) / BN;
     if (g.lower) {
@@ -1205,29 +1209,47 @@ __global__ void __launch_bounds__(GemmCfg<BM, BN>::kThreads, GemmCfg<BM, BN>::kM
     cp_async_wait<0>();
     const bool syrk = (mode & 0xff) == GEMM_SYRK_P;
     const int xrow = syrk ? F.n : -1;
-    const double* x0 = (mode >> 8) ? F.x_kk : F.x_km1;
-    // epilogue: C -= acc ; lower: only row >= col ; mirror: also store the transposed element
+    const double* x0 = ((mode >> 8) & 0xff) ? F.x_kk : F.x_km1;
+    // epilogue: C -= acc ; lower: only row >= col ; mirror: also store the transposed element.  The C entries of two m8 tile rows (16
+    // per thread) are fetched as one batch before any of them is stored: issued one by one behind the stores of the previous entry
+    // (the compiler cannot move a load of C above a store to C) the 64 dependent round trips cost ~30 us per tile -- as much as the
+    // whole k-loop of a K = 256 update (ncu / event timing: the K = 256 GEMMs ran at 45 % of the rate of the K = 3300 SYRK).
+    constexpr int EB = 2;
+    static_assert(MT % EB == 0, "epilogue batches");
 #pragma unroll
-    for (int mt = 0; mt < MT; mt++) {
-        const int row = m0 + wm0 + mt * 8 + (lane >> 2);
+    for (int mt0 = 0; mt0 < MT; mt0 += EB) {
+        double cv[EB][NT][2];
 #pragma unroll
-        for (int nt = 0; nt < NT; nt++) {
-            const int col = n0 + wn0 + nt * 8 + 2 * (lane & 3);
+        for (int u = 0; u < EB; u++) {
+            const int row = m0 + wm0 + (mt0 + u) * 8 + (lane >> 2);
+#pragma unroll
+            for (int nt = 0; nt < NT; nt++)
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const int cc = n0 + wn0 + nt * 8 + 2 * (lane & 3) + e;
+                    const bool ok = row < g.M && cc < g.N && !(g.lower && row < cc) && row != xrow;
+                    cv[u][nt][e] = ok ? g.C[row + (size_t)cc * g.ldc] : 0.0;
+                }
+        }
+#pragma unroll
+        for (int u = 0; u < EB; u++) {
+            const int row = m0 + wm0 + (mt0 + u) * 8 + (lane >> 2);
             if (row >= g.M) continue;
 #pragma unroll
-            for (int e = 0; e < 2; e++) {
-                const int cc = col + e;
-                if (cc >= g.N) continue;
-                if (g.lower && row < cc) continue;
-                if (row == xrow) {
-                    if (cc < xrow) F.x_kk[cc] = x0[cc] + acc[mt][nt][e];
-                    continue;
+            for (int nt = 0; nt < NT; nt++)
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const int cc = n0 + wn0 + nt * 8 + 2 * (lane & 3) + e;
+                    if (cc >= g.N) continue;
+                    if (g.lower && row < cc) continue;
+                    if (row == xrow) {
+                        if (cc < xrow) F.x_kk[cc] = x0[cc] + acc[mt0 + u][nt][e];
+                        continue;
+                    }
+                    const double v = cv[u][nt][e] - acc[mt0 + u][nt][e];
+                    g.C[row + (size_t)cc * g.ldc] = v;
+                    if (g.mirror && row != cc) g.C[cc + (size_t)row * g.ldc] = v;
                 }
-                double* cp = g.C + row + (size_t)cc * g.ldc;
-                const double v = *cp - acc[mt][nt][e];
-                *cp = v;
-                if (g.mirror && row != cc) g.C[cc + (size_t)row * g.ldc] = v;
-            }
         }
     }
 }

@@ -73,6 +73,7 @@ struct rslam_filter {
     bool have_image = false;
     bool warp_patches = false;  // run pred_patch_fc on the device before the search
     bool upd_ws = false;
+    int trsm_ob = 0;  // outer-block width of the large-k TRSM in 64-column blocks (0: one left-looking launch); RSLAM_TRSM_OB overrides
     int hN = 0, hn = 0;  // max over filters of the uploaded N / n
     bool descr_dirty = false;
     // CUDA-graph replay of the per-frame launch sequence
@@ -249,20 +250,22 @@ int run_update(rslam_filter* f, int which, bool gathered = false, bool defer_jno
     if (kmax <= SR_KMAX) {  // small systems: W rows resident in smem, L streamed once
         LAUNCH(f, k_trsm_small, dim3(cdiv(n + 1, TS_R), B), TS_THREADS, trsm_small_smem_bytes(kmax), f->dF, round_up(kmax, kNB));
     } else {
-        // two-level: the 64-wide blocks of one 256-wide outer block are solved left-looking by k_trsm_ll (a CTA owns its rows), then one
-        // K = 256 GEMM subtracts that outer block's contribution from all remaining columns of W
-        const int nouter = cdiv(nsteps, kOB);
+        // two-level: the 64-wide blocks of one outer block (f->trsm_ob blocks wide) are solved left-looking by k_trsm_ll (a CTA owns its
+        // rows), then one GEMM with K = 64 trsm_ob subtracts that outer block's contribution from all remaining columns of W.
+        // trsm_ob == 0: the whole solve in one left-looking launch.
+        const int ob = f->trsm_ob > 0 ? f->trsm_ob : nsteps;
+        const int nouter = cdiv(nsteps, ob);
         for (int J = 0; J < nouter; J++) {
             if (cdiv(n + 1, 48) * B >= 200) {  // 48-row CTAs, two resident per SM: one CTA's barriers / diagonal step hide behind the other's DMMA stream
-                LAUNCH_N(f, "k_trsm_ll", (k_trsm_ll<48, 2>), dim3(cdiv(n + 1, 48), B), 128, (TrsmCfg<48, 2>::kSmemBytes), f->dF, J * kOB, (J + 1) * kOB);
+                LAUNCH_N(f, "k_trsm_ll", (k_trsm_ll<48, 2>), dim3(cdiv(n + 1, 48), B), 128, (TrsmCfg<48, 2>::kSmemBytes), f->dF, J * ob, (J + 1) * ob);
             } else {
-                LAUNCH_N(f, "k_trsm_ll", (k_trsm_ll<32, 2>), dim3(cdiv(n + 1, 32), B), 128, (TrsmCfg<32, 2>::kSmemBytes), f->dF, J * kOB, (J + 1) * kOB);
+                LAUNCH_N(f, "k_trsm_ll", (k_trsm_ll<32, 2>), dim3(cdiv(n + 1, 32), B), 128, (TrsmCfg<32, 2>::kSmemBytes), f->dF, J * ob, (J + 1) * ob);
             }
-            const int o = kNB * kOB * (J + 1);
+            const int o = kNB * ob * (J + 1);
             if (kmax > o) {
                 const int tm = cdiv(n + 1, 128), tn = cdiv(kmax - o, 64);
                 LAUNCH_N(f, "k_gemm_dmma/trsm_outer", (k_gemm_dmma<128, 64>), dim3(tm * tn, 1, B), (GemmCfg<128, 64>::kThreads), (GemmCfg<128, 64>::kSmemBytes), f->dF,
-                         (int)GEMM_TRSM_OUTER, J);
+                         (int)GEMM_TRSM_OUTER | (ob << 16), J);
             }
         }
     }
@@ -346,6 +349,7 @@ int rslam_create(const rslam_camera* cam, const rslam_params* par, int max_featu
     f->kmax = 2 * max_features;
     f->lds = round_up(f->kmax, 16);
     f->mwords = cdiv(max_features, 32);
+    if (const char* e = getenv("RSLAM_TRSM_OB")) f->trsm_ob = atoi(e);
     f->cam = *cam;
     if (par)
         f->par = *par;

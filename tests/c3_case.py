@@ -57,9 +57,11 @@ def assert_summary_close(got, exp, what, rtol=1e-9):
     d = np.abs(got["PV"] - exp["PV"])
     lim = rtol * exp["absPV"] + atol * np.sqrt(got["x"].size)
     assert (d <= lim).all(), f"{what}: P v: max |d| / bound = {(d / lim).max():.3e}"
+    # state: 1e-9 relative, with an absolute floor of 1e-10 (metres / radians / inverse metres) for entries that are themselves ~0 --
+    # two chained updates of rank ~2000 leave ~2e-11 of absolute difference between a Cholesky-based and an LU-based solve
     a, b = got["x"], exp["x"]
     d = np.abs(a - b)
-    assert (d <= rtol * np.maximum(np.abs(a), np.abs(b)) + 1e-12).all(), f"{what}: x: max |d| = {d.max():.3e} at {int(np.argmax(d))}"
+    assert (d <= rtol * np.maximum(np.abs(a), np.abs(b)) + 1e-10).all(), f"{what}: x: max |d| = {d.max():.3e} at {int(np.argmax(d))}"
 
 
 def run_oracle(quirks, cam, scene, seq, P0, threads=None):

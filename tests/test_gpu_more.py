@@ -284,8 +284,8 @@ def test_patch_warp_matches_oracle_remap():
         po = o.patch_matching(i)
         assert po.std() > 0
         d = np.abs(pg[i].astype(np.float64) - po)
-        # identical sampling except where a map coordinate sits within rounding noise of a 1/32-px quantisation boundary
-        assert (d == 0).mean() > 0.97 and d.max() < 12.0, (i, (d == 0).mean(), d.max())
+        # identical sampling except where a map coordinate sits within rounding noise (1e-13 px) of a 1/32-px quantisation boundary
+        assert (d == 0).mean() > 0.99 and d.max() < 12.0, (i, (d == 0).mean(), d.max())
         same += int((d == 0).all())
         npix += d.size
         neq += int((d == 0).sum())
@@ -294,7 +294,7 @@ def test_patch_warp_matches_oracle_remap():
     print(stats)
     if os.path.isdir("gpurun_out"):
         open("gpurun_out/r02_patch_stats.txt", "a").write(stats + "\n")
-    assert same >= 0.8 * fo["has_h"].sum()
+    assert neq >= npix - 2, stats  # bit-identical pixels (a flip needs a coordinate within ~1e-13 px of a quantisation boundary)
     # build an image that contains the oracle-predicted appearance at a pasted location and search on both sides
     img = synth.background(scene.cam).copy()
     for i in np.flatnonzero(fo["has_h"]):

@@ -14,9 +14,19 @@ from tests import helpers as H
 pytestmark = pytest.mark.gpu
 
 
+def _blank(scene, seq, k, feats):
+    """paint the background over the pasted appearance of some features in frame k: they are predicted but not matched"""
+    bg = synth.background(scene.cam)
+    for i in feats:
+        x, y = seq.z_true[k][i]
+        if x >= 0:
+            seq.images[k][y - 6:y + 7, x - 6:x + 7] = bg[y - 6:y + 7, x - 6:x + 7]
+
+
 def test_deletion_moves_flags_with_the_record():
     scene, x, P = synth.random_spd_state(30, seed=33)
     seq = synth.make_sequence(scene, T=3, seed=35, t0=3)
+    _blank(scene, seq, 0, [3, 7, 11, 19, 22, 27])  # six features without a match in the first frame
     o = H.oracle_from(scene, x, P, prior=False, sparse=False)
     g = H.gpu_from(scene, x, P, prior=False, max_features=34)
     o.frame(seq.images[0], seq.u01[0])
@@ -69,6 +79,7 @@ def test_map_management_measured_count_after_deletion():
     """the whole Map::map_management: `measured` (src/Map.cpp:57-66) decides how many features are initialised"""
     scene, x, P = synth.random_spd_state(20, seed=43)
     seq = synth.make_sequence(scene, T=2, seed=45, t0=3)
+    _blank(scene, seq, 0, [2, 9, 15])
     o = H.oracle_from(scene, x, P, prior=False, sparse=False)
     g = H.gpu_from(scene, x, P, prior=False, max_features=60)
     o.frame(seq.images[0], seq.u01[0])
@@ -136,11 +147,14 @@ def test_rescue_relinearises_a_feature_that_left_the_view():
     # no low-innovation inliers: every match goes through the rescue gate at x_k_k = x2
     o.set_state(x2, P, prior=False)
     g.upload_state(x2, P, prior=False)
-    h_stale = fo["h"][j].copy()
+    ho_stale, hg_stale = fo["h"][j].copy(), g.features()["h"][j].copy()
     o.rescue_hi()
     g.rescue_hi()
     fo, fg = o.features(), g.features()
-    assert fg["has_h"][j] and np.array_equal(fg["h"][j], h_stale) and np.array_equal(fo["h"][j], h_stale)  # h of x_k_km1 stays
+    assert fg["has_h"][j] and fo["has_h"][j] and np.array_equal(fg["h"][j], hg_stale) and np.array_equal(fo["h"][j], ho_stale)  # h of x_k_km1 stays
+    others = np.flatnonzero(fo["has_h"])
+    others = others[others != j]
+    assert not np.array_equal(fg["h"][others], np.rint(fg["h"][others]))  # ... while the visible ones were re-predicted
     assert (fo["hi"] == fg["hi"]).all()
     Hc, Hf = g.H_sparse()
     for i in np.flatnonzero(fo["has_h"]):
