@@ -554,7 +554,14 @@ __global__ void __launch_bounds__(256) k_chol_panel(DevFilter* Fs, int step) {
     double* S = F.Sm;
     const int ld = F.lds;
     const int nr = blockIdx.x == 0 ? 0 : min(kNB, kk - r0);
+#ifdef RSLAM_PHASE_CLOCKS
+    long long tprev = clock64();
+#define PPH(i) do { __syncthreads(); if (blockIdx.x == 1 && threadIdx.x == 0) { const long long now__ = clock64(); F.Jn[16 + (i)] += (double)(now__ - tprev); tprev = now__; } } while (0)
+#else
+#define PPH(i)
+#endif
     panel_load(ps, S, ld, j0, w, r0, nr);
+    PPH(0);
     const int ob0 = kNB * kOB * (step / kOB);  // first column of the outer block
     if (ob0 < j0) {
         // pending update: [D; A] -= [Ld; La] Ld^T over the columns [ob0, j0) already factored in this outer block
@@ -620,7 +627,9 @@ __global__ void __launch_bounds__(256) k_chol_panel(DevFilter* Fs, int step) {
         }
     }
     __syncthreads();
+    PPH(1);
     smem_panel_factor(ps, kNB + nr, w);
+    PPH(2);
     if (blockIdx.x == 0) {
         for (int e = threadIdx.x; e < kNB * kNB; e += blockDim.x) {
             const int i = e % kNB, c = e / kNB;
@@ -632,6 +641,11 @@ __global__ void __launch_bounds__(256) k_chol_panel(DevFilter* Fs, int step) {
         const int i = e % nr, c = e / nr;
         if (c < w) S[(r0 + i) + (size_t)(j0 + c) * ld] = ps.sT[c * kTld + kNB + i];
     }
+    PPH(3);
+#ifdef RSLAM_PHASE_CLOCKS
+    if (threadIdx.x == 0 && blockIdx.x == 1) F.Jn[16 + 4] += 1.0;
+#endif
+#undef PPH
 }
 
 // ---- U4b: explicit inverses of ALL 64 x 64 diagonal blocks of the finished factor, one CTA per block (the TRSM kernel multiplies by

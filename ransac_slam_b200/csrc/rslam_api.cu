@@ -73,7 +73,7 @@ struct rslam_filter {
     bool have_image = false;
     bool warp_patches = false;  // run pred_patch_fc on the device before the search
     bool upd_ws = false;
-    int trsm_ob = 0;  // outer-block width of the large-k TRSM in 64-column blocks (0: one left-looking launch); RSLAM_TRSM_OB overrides
+    int trsm_ob = 16;  // outer-block width of the large-k TRSM in 64-column blocks (0: one left-looking launch); RSLAM_TRSM_OB overrides
     int hN = 0, hn = 0;  // max over filters of the uploaded N / n
     bool descr_dirty = false;
     // CUDA-graph replay of the per-frame launch sequence

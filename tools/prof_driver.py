@@ -30,20 +30,20 @@ def main():
         g.sync()
         print("c2 done", g.launches, g.download_pose()[:3])
     elif wl == "c3":
-        N = 2000
-        cam = synth.scaled_camera(4)
-        scene = synth.make_scene(N=N, seed=1234, cam=cam, margin=30, min_sep=18, assemble_P=False, motion_scale=0.25)
-        seq = synth.make_sequence(scene, T=frames, seed=1235, n_u01=8192)
+        cam, scene, seq = B.make_c3(frames)
         P0 = synth.assemble_P_torch(scene, dev)
-        g = capi.Filter(cam.as9(), N, std_a=0.007 * 0.25, std_alpha=0.007 * 0.25)
+        g = B.new_c3_filter(cam, scene, P0, 0)
         g.set_graph(graph)
-        x0 = torch.from_numpy(scene.x0).to(dev)
-        g.upload_state_device(x0.data_ptr(), P0.data_ptr(), scene.x0.size, scene.x0.size, N)
-        g.upload_patches(scene.templates.astype(np.float64))
         for k in range(frames):
             g.frame(seq.images[k][None], seq.u01[k][None])
         g.sync()
         print("c3 done", g.launches, B.frame_stats(g))
+        if os.environ.get("RSLAM_PHASES"):
+            import ctypes as C
+            out = np.zeros(32)
+            g.L.rslam_debug_scratch(g.h, 0, out.ctypes.data_as(C.c_void_p))
+            n = max(out[20], 1.0)
+            print("k_chol_panel phase cycles per launch (CTA 1): load %.0f update %.0f factor %.0f store %.0f over %d launches" % (out[16] / n, out[17] / n, out[18] / n, out[19] / n, int(n)))
     elif wl == "c4":
         N, H = 5000, 100000
         scene, x, P, z = X.make_c4(dev, N)
@@ -66,7 +66,8 @@ def main():
         Pd = torch.from_numpy(np.ascontiguousarray(scene.P0)).to(dev)
         for b in range(Bl):
             g.upload_state_device(xd.data_ptr(), Pd.data_ptr(), n, n, 100, b=b)
-            g.upload_patches(scene.templates.astype(np.float64), b=b)
+            B.upload_appearance(g, scene, b=b)
+        g.set_patch_warp(True)
         for k in range(frames):
             g.frame(seq.images[k][None].repeat(Bl, 0), seq.u01[k][None].repeat(Bl, 0))
         g.sync()
