@@ -106,6 +106,10 @@ int rslam_download_patches(rslam_filter* f, int b, float* patches, int N);
 int rslam_download_features(rslam_filter* f, int b, double* h, double* S, double* z, uint8_t* flags, int* counters);
 /* structurally non-zero part of H_i: Hc[14N] = d h / d (r,q) (2x7 row-major), Hf[12N] = d h / d y_i (2x6 row-major; 2x3 used for cartesian) */
 int rslam_download_H(rslam_filter* f, int b, double* Hc, double* Hf);
+/* inject a linearisation and inlier flags directly: h[2N], Hc[14N], Hf[12N], z[2N], flags[4N] = {has_h, individually_compatible,
+ * low_innovation_inlier, high_innovation_inlier}; any pointer may be NULL (left as it is).  What ExtendKF::update needs when it is called
+ * with caller-built H, z, h (src/ExtendKF.cpp:597) instead of through ekf_update_li_inliers / ekf_update_hi_inliers. */
+int rslam_upload_linearisation(rslam_filter* f, int b, const double* h, const double* Hc, const double* Hf, const double* z, const uint8_t* flags);
 /* inject matches directly (z[2N], ic[N]) instead of running the active search */
 int rslam_set_matches(rslam_filter* f, int b, const double* z, const uint8_t* ic);
 /* grayscale frame for filter b (host or device).  With share != 0 the same image is used by every filter of the batch. */
@@ -119,6 +123,11 @@ int rslam_ekf_prediction(rslam_filter* f);
 /* Tracking::search_IC_matches (src/Tracking.cpp:32-70): h_i, H_i, S_i at x_k_km1, then ZNCC active search on the
  * image set by rslam_set_image (skipped when no image is set: only h/H/S are produced). */
 int rslam_search_ic_matches(rslam_filter* f);
+/* The two halves of rslam_search_ic_matches on their own (the reference exposes them as Tracking::calculate_derivatives / pred_patch_fc
+ * and Tracking::matching, include/ransac_slam/Tracking.h:30-37): h_i, H_i, S_i (+ the patch warp when enabled) at x_k_km1, and the ZNCC
+ * search on the bound image with the current predictions. */
+int rslam_predict_measurements(rslam_filter* f);
+int rslam_match(rslam_filter* f);
 /* Tracking::ransac_hypotheses (src/Tracking.cpp:352-539).  u01: batch x n_u01 uniform draws in [0,1) (host or device),
  * replacing ExtendKF::rand (src/ExtendKF.cpp:220-235). */
 int rslam_ransac_hypotheses(rslam_filter* f, const double* u01, int n_u01);

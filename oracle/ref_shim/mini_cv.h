@@ -37,6 +37,7 @@ typedef unsigned char uchar;
 #define CV_COVAR_ROWS 8
 #define CV_COVAR_COLS 16
 #define CV_BGR2GRAY 6
+#define CV_GRAY2BGR 8
 
 namespace cv {
 [[noreturn]] inline void shim_fail(const char* what) {
@@ -309,6 +310,14 @@ class FileStorage {
     std::map<std::string, std::string> kv_;
     bool opened_ = false;
 };
+// drawing primitives used only by the reference's image overlay (src/System.cpp:199-227): accepted, nothing is drawn
+struct Size {
+    int width = 0, height = 0;
+    Size() {}
+    Size(double w, double h) : width((int)w), height((int)h) {}
+};
+inline void line(Mat&, Point, Point, const Scalar&, int = 1, int = 8, int = 0) {}
+inline void ellipse(Mat&, Point, Size, double, double, double, const Scalar&, int = 1, int = 8, int = 0) {}
 }  // namespace cv
 typedef cv::Scalar CvScalar;
 inline cv::Scalar cvScalarAll(double v) { return cv::Scalar::all(v); }

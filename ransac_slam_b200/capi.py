@@ -43,7 +43,7 @@ EXPORTS = [
     "rslam_search_ic_matches", "rslam_ransac_hypotheses", "rslam_ransac_result_get", "rslam_update_li", "rslam_rescue_hi", "rslam_update_hi",
     "rslam_frame", "rslam_set_graph", "rslam_profile_enable", "rslam_profile_read", "rslam_download_pose", "rslam_support_sweep", "rslam_sweep_mask",
     "rslam_comm_init", "rslam_comm_unique_id", "rslam_comm_init_rank", "rslam_comm_destroy", "rslam_comm_size", "rslam_comm_local_size",
-    "rslam_support_sweep_multi",
+    "rslam_support_sweep_multi", "rslam_upload_linearisation", "rslam_predict_measurements", "rslam_match",
 ]
 
 _lib = None
@@ -80,8 +80,10 @@ def load():
     L.rslam_download_patches.argtypes = [vp, ci, vp, ci]
     L.rslam_download_H.argtypes = [vp, ci, vp, vp]
     L.rslam_set_matches.argtypes = [vp, ci, vp, vp]
+    L.rslam_upload_linearisation.argtypes = [vp, ci, vp, vp, vp, vp, vp]
     L.rslam_set_image.argtypes = [vp, ci, vp, ci, ci, ci, ci]
-    for n in ("rslam_begin_frame", "rslam_ekf_prediction", "rslam_search_ic_matches", "rslam_update_li", "rslam_rescue_hi", "rslam_update_hi"):
+    for n in ("rslam_begin_frame", "rslam_ekf_prediction", "rslam_search_ic_matches", "rslam_update_li", "rslam_rescue_hi", "rslam_update_hi", "rslam_predict_measurements",
+              "rslam_match"):
         getattr(L, n).argtypes = [vp]
     L.rslam_ransac_hypotheses.argtypes = [vp, vp, ci]
     L.rslam_ransac_result_get.argtypes = [vp, ci, C.POINTER(RansacResult)]

@@ -667,6 +667,37 @@ int rslam_download_H(rslam_filter* f, int b, double* Hc, double* Hf) {
     return RSLAM_OK;
 }
 
+int rslam_upload_linearisation(rslam_filter* f, int b, const double* h, const double* Hc, const double* Hf, const double* z, const uint8_t* flags) {
+    if (!f || b < 0 || b >= f->B) return fail(RSLAM_ERR_INVALID, "rslam_upload_linearisation: bad arguments");
+    CK(cudaSetDevice(f->device));
+    DevFilter& D = f->hF[b];
+    const int N = D.N;
+    if (N == 0) return RSLAM_OK;
+    if (h) CK(cudaMemcpyAsync(D.h, h, sizeof(double) * 2 * N, cudaMemcpyDefault, f->stream));
+    if (Hc) CK(cudaMemcpyAsync(D.Hc, Hc, sizeof(double) * 14 * N, cudaMemcpyDefault, f->stream));
+    if (Hf) CK(cudaMemcpyAsync(D.Hf, Hf, sizeof(double) * 12 * N, cudaMemcpyDefault, f->stream));
+    if (z) CK(cudaMemcpyAsync(D.z, z, sizeof(double) * 2 * N, cudaMemcpyDefault, f->stream));
+    std::vector<unsigned char> a, bb, c, d;
+    if (flags) {
+        a.resize(N);
+        bb.resize(N);
+        c.resize(N);
+        d.resize(N);
+        for (int i = 0; i < N; i++) {
+            a[i] = flags[4 * i] != 0;
+            bb[i] = flags[4 * i + 1] != 0;
+            c[i] = flags[4 * i + 2] != 0;
+            d[i] = flags[4 * i + 3] != 0;
+        }
+        CK(cudaMemcpyAsync(D.has_h, a.data(), N, cudaMemcpyHostToDevice, f->stream));
+        CK(cudaMemcpyAsync(D.ic, bb.data(), N, cudaMemcpyHostToDevice, f->stream));
+        CK(cudaMemcpyAsync(D.li, c.data(), N, cudaMemcpyHostToDevice, f->stream));
+        CK(cudaMemcpyAsync(D.hi, d.data(), N, cudaMemcpyHostToDevice, f->stream));
+    }
+    CK(cudaStreamSynchronize(f->stream));
+    return RSLAM_OK;
+}
+
 int rslam_set_matches(rslam_filter* f, int b, const double* z, const uint8_t* ic) {
     if (!f || b < 0 || b >= f->B || !z || !ic) return fail(RSLAM_ERR_INVALID, "rslam_set_matches: bad arguments");
     CK(cudaSetDevice(f->device));
@@ -741,7 +772,7 @@ int rslam_ekf_prediction(rslam_filter* f) {
     return check_launch();
 }
 
-int rslam_search_ic_matches(rslam_filter* f) {
+int rslam_predict_measurements(rslam_filter* f) {
     if (!f) return fail(RSLAM_ERR_INVALID, "null handle");
     CK(cudaSetDevice(f->device));
     if (f->hN == 0) return RSLAM_OK;
@@ -750,8 +781,23 @@ int rslam_search_ic_matches(rslam_filter* f) {
         LAUNCH(f, k_pred_patch_setup, dim3(cdiv(f->hN, 64), f->B), 64, 0, f->dF, f->camd);
         LAUNCH(f, k_pred_patch, dim3(f->hN, f->B), 192, 0, f->dF, f->camd);
     }
-    if (f->have_image) LAUNCH(f, k_search, dim3(f->hN, f->B), kSearchThreads, 0, f->dF, f->camd, f->pard);
     return check_launch();
+}
+
+int rslam_match(rslam_filter* f) {
+    if (!f) return fail(RSLAM_ERR_INVALID, "null handle");
+    CK(cudaSetDevice(f->device));
+    if (f->hN == 0) return RSLAM_OK;
+    if (!f->have_image) return fail(RSLAM_ERR_INVALID, "rslam_match: no image is bound (rslam_set_image)");
+    LAUNCH(f, k_search, dim3(f->hN, f->B), kSearchThreads, 0, f->dF, f->camd, f->pard);
+    return check_launch();
+}
+
+int rslam_search_ic_matches(rslam_filter* f) {
+    if (!f) return fail(RSLAM_ERR_INVALID, "null handle");
+    int rc = rslam_predict_measurements(f);
+    if (rc || f->hN == 0 || !f->have_image) return rc;
+    return rslam_match(f);
 }
 
 static int set_u01(rslam_filter* f, const double* u01, int n_u01) {

@@ -7,6 +7,8 @@
 #include "ExtendKF.h"
 
 namespace ransac_slam {
+class ExtendKF;
+struct Feature;
 class Map {
   public:
     Map(const int min_fea, ExtendKF* m_ExtendKF);

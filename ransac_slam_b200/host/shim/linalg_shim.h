@@ -1,6 +1,8 @@
 // linalg_shim.h -- the few Eigen / OpenCV types that appear in the reference's class interfaces.
 // With real Eigen / OpenCV installed the genuine headers are used; this image has neither, so minimal stand-ins with the same
-// names, storage order (column-major MatrixXd, row-major 8-bit cv::Mat) and accessors are provided.
+// names, storage order (column-major matrices, row-major 8-bit cv::Mat) and accessors are provided: construction, resize,
+// rows / cols / size, (i) and (i, j) element access, data().  The host classes use nothing else, so the same source builds against
+// either.
 #pragma once
 #include <cstddef>
 #include <cstdint>
@@ -10,43 +12,55 @@
 #include <Eigen/Dense>
 #else
 namespace Eigen {
-class VectorXd {
+const int Dynamic = -1;
+template <class T, int R, int C>
+class Matrix {  // column-major, like Eigen's default; R / C == Dynamic: set at run time
   public:
-    VectorXd() {}
-    explicit VectorXd(int n) : v_(n, 0.0) {}
-    void resize(int n) { v_.assign(n, 0.0); }
-    int rows() const { return (int)v_.size(); }
-    int size() const { return (int)v_.size(); }
-    double& operator()(int i) { return v_[i]; }
-    double operator()(int i) const { return v_[i]; }
-    double& operator[](int i) { return v_[i]; }
-    double operator[](int i) const { return v_[i]; }
-    double* data() { return v_.data(); }
-    const double* data() const { return v_.data(); }
-
-  private:
-    std::vector<double> v_;
-};
-class MatrixXd {  // column-major, like Eigen's default
-  public:
-    MatrixXd() {}
-    MatrixXd(int r, int c) : r_(r), c_(c), v_((size_t)r * c, 0.0) {}
+    Matrix() : r_(R > 0 ? R : 0), c_(C > 0 ? C : 0), v_((size_t)r_ * c_, T(0)) {}
+    explicit Matrix(int n) : r_(C == 1 ? n : (R > 0 ? R : 1)), c_(C == 1 ? 1 : n), v_((size_t)r_ * c_, T(0)) {}
+    Matrix(int r, int c) : r_(r), c_(c), v_((size_t)r * c, T(0)) {}
+    void resize(int n) {
+        if (C == 1) {
+            r_ = n;
+            c_ = 1;
+        } else {
+            r_ = R > 0 ? R : 1;
+            c_ = n;
+        }
+        v_.assign((size_t)r_ * c_, T(0));
+    }
     void resize(int r, int c) {
         r_ = r;
         c_ = c;
-        v_.assign((size_t)r * c, 0.0);
+        v_.assign((size_t)r * c, T(0));
     }
     int rows() const { return r_; }
     int cols() const { return c_; }
-    double& operator()(int i, int j) { return v_[(size_t)i + (size_t)j * r_]; }
-    double operator()(int i, int j) const { return v_[(size_t)i + (size_t)j * r_]; }
-    double* data() { return v_.data(); }
-    const double* data() const { return v_.data(); }
+    int size() const { return r_ * c_; }
+    T& operator()(int i) { return v_[i]; }
+    T operator()(int i) const { return v_[i]; }
+    T& operator[](int i) { return v_[i]; }
+    T operator[](int i) const { return v_[i]; }
+    T& operator()(int i, int j) { return v_[(size_t)i + (size_t)j * r_]; }
+    T operator()(int i, int j) const { return v_[(size_t)i + (size_t)j * r_]; }
+    T* data() { return v_.data(); }
+    const T* data() const { return v_.data(); }
 
   private:
-    int r_ = 0, c_ = 0;
-    std::vector<double> v_;
+    int r_, c_;
+    std::vector<T> v_;
 };
+typedef Matrix<double, Dynamic, Dynamic> MatrixXd;
+typedef Matrix<double, Dynamic, 1> VectorXd;
+typedef Matrix<double, 1, Dynamic> RowVectorXd;
+typedef Matrix<double, 2, 1> Vector2d;
+typedef Matrix<double, 3, 1> Vector3d;
+typedef Matrix<double, 4, 1> Vector4d;
+typedef Matrix<double, 1, 2> RowVector2d;
+typedef Matrix<double, 1, 4> RowVector4d;
+typedef Matrix<double, 2, 2> Matrix2d;
+typedef Matrix<double, 3, 3> Matrix3d;
+typedef Matrix<double, 4, 4> Matrix4d;
 }  // namespace Eigen
 #endif
 

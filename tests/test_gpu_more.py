@@ -307,3 +307,35 @@ def test_patch_warp_matches_oracle_remap():
     f2o, f2g = o.features(), g.features()
     assert f2o["ic"].sum() >= N // 2
     assert (f2o["ic"] == f2g["ic"]).all() and (f2o["z"][f2o["ic"]] == f2g["z"][f2g["ic"]]).all()
+
+
+def test_upload_linearisation_reproduces_the_update_and_stage_entry_points():
+    """rslam_upload_linearisation (what the host ExtendKF::update uses when it is handed caller-built H, z, h) and the two halves of
+    search_IC_matches as separate entry points (Tracking::calculate_derivatives / matching)."""
+    import ctypes as C
+
+    scene, x, P = synth.random_spd_state(40, seed=131)
+    seq = synth.make_sequence(scene, T=1, seed=136, t0=3)
+    a = H.gpu_from(scene, x, P, quirks=0x6)
+    a.set_image(seq.images[0])
+    a.search_ic_matches()
+    a.ransac_hypotheses(seq.u01[0])
+    fa = a.features()
+    Hc, Hf = a.H_sparse()
+    assert fa["li"].sum() >= 5
+    a.update_li()
+    xa, Pa = a.download_state()
+    # second handle: prediction and matching as separate calls, then the linearisation + flags of the first injected instead of RANSAC
+    b = H.gpu_from(scene, x, P, quirks=0x6)
+    b.set_image(seq.images[0])
+    L = b.L
+    assert L.rslam_predict_measurements(b.h) == 0 and L.rslam_match(b.h) == 0
+    fb = b.features()
+    assert (fb["ic"] == fa["ic"]).all() and np.array_equal(fb["z"][fb["ic"]], fa["z"][fa["ic"]]) and np.array_equal(fb["h"], fa["h"])
+    flags = np.stack([fa["has_h"], fa["ic"], fa["li"], np.zeros_like(fa["li"])], axis=1).astype(np.uint8)
+    arrs = [np.ascontiguousarray(v, dtype=np.float64) for v in (fa["h"], Hc, Hf, fa["z"])]
+    rc = L.rslam_upload_linearisation(b.h, 0, *[v.ctypes.data_as(C.c_void_p) for v in arrs], np.ascontiguousarray(flags).ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    b.update_li()
+    xb, Pb = b.download_state()
+    assert np.array_equal(xa, xb) and np.array_equal(Pa, Pb)
