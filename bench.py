@@ -195,8 +195,10 @@ def kernel_work(kernel, launches, N, n, st):
 
 CHOL_KERNELS = ("k_chol_panel", "k_gemm_dmma/chol_outer", "k_chol_trinv", "k_chol_small")
 
-# DRAM bytes (read + write) per launch of the dominant kernels from this round's `ncu --set full` captures (profiles/r02_*.md)
-NCU_TRAFFIC = {"k_gemm_dmma/syrk_P": None, "k_syrk_rows": None}
+# DRAM bytes (read + write) per launch of the dominant kernels from this round's `ncu --set full` captures:
+#   profiles/r02_syrk_c3.md      k_gemm_dmma/syrk_P at N = 2000, k = 3608: 8.54 GB read + 1.15 GB written
+#   profiles/r02_c5_kernels.md   k_syrk_rows at 1024 filters, k = 186: 2.83 GB read + 3.05 GB written (scaled to the filters of the launch)
+NCU_TRAFFIC = {"k_gemm_dmma/syrk_P": 9.70e9, "k_syrk_rows": 5.88e9 / 1024.0}
 
 
 def roofline_table(prof, frames, N, n, st, fp64_peak):
@@ -593,6 +595,7 @@ def bench_c3(args, world, rank, local):
     top = next(k for k in kernels if not k.startswith("cholesky ("))
     roof = dict(kernel=top, **{k: v for k, v in kernels[top].items()})
     roof["traffic"] = NCU_TRAFFIC.get(top)
+    roof["algorithmic_bytes"] = 2.0 * 8.0 * n * (n + 1) / 2 + 8.0 * (n + 1) * 2.0 * st["m_hi"]  # P lower triangle read + written, V read once
     roof["note"] = ("dominant kernel of the step, from the instrumented pass; achieved = algorithmic flops of THIS kernel (covariance downdate P -= V V^T, lower "
                     "triangle: (n+1)^2 k per update) / its time; peak = cuBLAS fp64 GEMM measured live (MEASURED_PEAKS.json has no fp64 figure); "
                     "per-kernel fractions for every kernel of the step are under `kernels`")
@@ -718,7 +721,7 @@ def bench_c5(args, world, rank, local, filters_total=None, steps=None, warmup=No
             row["frac"] *= Bl
     top = next(k for k in kernels if not k.startswith("cholesky ("))
     roof = dict(kernel=top, **kernels[top])
-    roof["traffic"] = NCU_TRAFFIC.get(top)
+    roof["traffic"] = NCU_TRAFFIC[top] * Bl if top == "k_syrk_rows" else NCU_TRAFFIC.get(top)
     # whole batch frame against HBM: every filter's P is read and written once per non-empty update, + the P columns W = P H^T gathers
     ldp = (n + 15) // 16 * 16
     upd = (1 if st["m_li"] > 0 else 0) + (1 if st["m_hi"] > 0 else 0)
