@@ -816,6 +816,20 @@ __global__ void __launch_bounds__(WM * 64) k_trsm_ll(DevFilter* Fs, int jb0, int
         for (int a = 0; a < MT; a++)
 #pragma unroll
             for (int b = 0; b < NT; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+        // this thread's entries of W_j, fetched now: they are needed only after the accumulation (ncu: long-scoreboard 1.56 warps per
+        // issue with the loads placed at the point of use), and nothing in this launch writes block j before its own diagonal step
+        double wpre[MT][NT][2];
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++) {
+            const int row = r0 + wm0 + mt * 8 + (lane >> 2);
+#pragma unroll
+            for (int nt = 0; nt < NT; nt++)
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const int cl = wn0 + nt * 8 + 2 * (lane & 3) + e;
+                    wpre[mt][nt][e] = (row < M && cl < w) ? W[row + (size_t)(c0 + cl) * ldw] : 0.0;
+                }
+        }
         const int nkt = (c0 - kbase) / GBK_T;  // K = 64 (j - jb0)
         auto load_stage = [&](int stage, int kt) {
             const int k0 = kbase + kt * GBK_T;
@@ -874,7 +888,7 @@ __global__ void __launch_bounds__(WM * 64) k_trsm_ll(DevFilter* Fs, int jb0, int
                 for (int e = 0; e < 2; e++) {
                     const int cl = wn0 + nt * 8 + 2 * (lane & 3) + e;
                     double v = 0.0;
-                    if (row < M && cl < w) v = W[row + (size_t)(c0 + cl) * ldw] - acc[mt][nt][e];
+                    if (row < M && cl < w) v = wpre[mt][nt][e] - acc[mt][nt][e];
                     Ts[cl * LDA + rl] = v;
                 }
             }
