@@ -1,0 +1,146 @@
+#!/usr/bin/env python
+"""Configuration C1: the reference's bundled monocular sequence (data/images_sequences, 100 P5 frames 320x240, non-contiguous indices),
+replayed in sorted order through System::TrackRunning's call sequence with the libc draws fed from a seeded queue.
+
+  python tools/c1_replay.py ref   [--out tests/golden/c1_ref_outputs.npz]   reference's own sources (oracle/_ref/libref.so), CPU, here
+  python tools/c1_replay.py gpu                                              rslam_replay_pgm (C++ host classes over the C ABI), GPU box
+Both print one JSON line with frames/s and the per-frame feature / match / inlier counts; `gpu` also compares with the committed reference
+outputs frame by frame.  Frames come from /root/reference when it exists, else from tests/golden/pgm_frames_all.npz."""
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+GOLD = os.path.join(ROOT, "tests", "golden")
+SEQ = "/root/reference/data/images_sequences"
+N_MAP, N_RANSAC = 100, 1000  # draws per frame: 2 per initialisation attempt (<= 50 attempts), 1000 RANSAC draws
+
+
+def read_pgm(path):
+    raw = open(path, "rb").read()
+    tok, pos = [], 0
+    while len(tok) < 4:
+        while raw[pos:pos + 1].isspace():
+            pos += 1
+        if raw[pos:pos + 1] == b"#":
+            pos = raw.index(b"\n", pos) + 1
+            continue
+        end = pos
+        while not raw[end:end + 1].isspace():
+            end += 1
+        tok.append(raw[pos:end])
+        pos = end
+    w, h = int(tok[1]), int(tok[2])
+    return np.frombuffer(raw[pos + 1:pos + 1 + w * h], dtype=np.uint8).reshape(h, w).copy()
+
+
+def load_frames():
+    if os.path.isdir(SEQ):
+        names = sorted(f for f in os.listdir(SEQ) if f.endswith(".pgm"))
+        return np.stack([read_pgm(os.path.join(SEQ, f)) for f in names]), names
+    g = np.load(os.path.join(GOLD, "pgm_frames_all.npz"))
+    return g["frames"], [str(s) for s in g["names"]]
+
+
+def draws_for(n_frames):
+    from oracle import ref_py as R
+
+    rng = np.random.default_rng(20261018)
+    return [R.make_draws(rng, N_MAP + N_RANSAC) for _ in range(n_frames)]
+
+
+def run_ref(out):
+    from oracle import ref_py as R
+
+    frames, names = load_frames()
+    draws = draws_for(len(frames))
+    r = R.ReferenceFilter()
+    rec = []
+    t_total = 0.0
+    stopped = None
+    for k, img in enumerate(frames):
+        r.set_draws(draws[k])
+        t0 = time.perf_counter()
+        r.map_management(img, k + 1)
+        r.ekf_prediction()
+        r.search_ic_matches(img)
+        t_total += time.perf_counter() - t0
+        if int(r.features()["ic"].sum()) == 0:
+            # Tracking::ransac_hypotheses indexes an empty vector when no feature is individually compatible (src/Tracking.cpp:413-415,
+            # SURVEY A.3 Q9): with the sequence's frame gaps that happens here -- the reference's own replay ends (SIGFPE / Eigen assert)
+            stopped = dict(frame=k, name=names[k], reason="no individually compatible match: Tracking::ransac_hypotheses is undefined (Q9)")
+            break
+        t0 = time.perf_counter()
+        r.ransac_hypotheses()
+        r.update_li()
+        r.rescue_hi()
+        r.update_hi()
+        t_total += time.perf_counter() - t0
+        f = r.features()
+        x, _ = r.get_state()
+        rec.append(dict(x13=x[:13].copy(), N=int(r.N), ic=int(f["ic"].sum()), li=int(f["li"].sum()), hi=int(f["hi"].sum()), used=int(r.draws_consumed()),
+                        under=int(r.draws_underflow())))
+    res = dict(impl="reference", workload="C1: bundled sequence (100 frames, sorted order) through the reference's own sources", frames=len(rec),
+               value=len(rec) / t_total, unit="frames/s", seconds=t_total, cores=1, reference_stops=stopped, N=[q["N"] for q in rec], ic=[q["ic"] for q in rec],
+               li=[q["li"] for q in rec], hi=[q["hi"] for q in rec], draws_underflow=sum(q["under"] for q in rec))
+    if out:
+        np.savez_compressed(out, x13=np.stack([q["x13"] for q in rec]), N=np.array(res["N"]), ic=np.array(res["ic"]), li=np.array(res["li"]), hi=np.array(res["hi"]),
+                            draws=np.stack(draws), names=np.array(names))
+    print(json.dumps(res))
+
+
+def run_gpu():
+    from oracle import ref_py as R  # settings template only
+
+    frames, names = load_frames()
+    g = np.load(os.path.join(GOLD, "c1_ref_outputs.npz"))
+    draws = g["draws"]
+    exe = os.path.join(ROOT, "ransac_slam_b200", "lib", "rslam_replay_pgm")
+    with tempfile.TemporaryDirectory() as td:
+        yaml = os.path.join(td, "settings.yaml")
+        open(yaml, "w").write(R.YAML_TEMPLATE.format(**R.BUNDLED_YAML))
+        paths = []
+        with open(os.path.join(td, "draws.bin"), "wb") as d:
+            for k, img in enumerate(frames):
+                p = os.path.join(td, f"f{k:04d}.pgm")
+                with open(p, "wb") as f:
+                    f.write(b"P5\n320 240\n255\n")
+                    f.write(img.tobytes())
+                paths.append(p)
+                d.write(draws[k].astype("<i4").tobytes())
+        out = os.path.join(td, "out.bin")
+        t0 = time.perf_counter()
+        r = subprocess.run([exe, yaml, out, "--draws", os.path.join(td, "draws.bin")] + paths, capture_output=True, text=True, timeout=600)
+        wall = time.perf_counter() - t0
+        assert r.returncode == 0, r.stderr
+        raw = open(out, "rb").read()
+    rec = 13 * 8 + 6 * 4
+    nf = len(raw) // rec
+    agree = 0
+    cnts = []
+    for k in range(nf):
+        x13 = np.frombuffer(raw[k * rec:k * rec + 104], dtype=np.float64)
+        cnt = np.frombuffer(raw[k * rec + 104:(k + 1) * rec], dtype=np.int32)
+        cnts.append([int(v) for v in cnt[:4]])
+        ok = (cnt[0] == g["N"][k] and cnt[1] == g["ic"][k] and cnt[2] == g["li"][k] and cnt[3] == g["hi"][k]
+              and np.allclose(x13, g["x13"][k], rtol=1e-9, atol=1e-10))
+        if ok and agree == k:
+            agree = k + 1
+    return dict(impl="b200", workload="C1: bundled sequence through the C++ host classes (rslam_replay_pgm), incl. process start, CUDA context, file IO",
+                frames=nf, value=nf / wall, unit="frames/s", seconds=wall, frames_in_agreement_with_reference=agree, reference_frames=int(g["N"].size),
+                N=[c[0] for c in cnts], ic=[c[1] for c in cnts], li=[c[2] for c in cnts], hi=[c[3] for c in cnts])
+
+
+if __name__ == "__main__":
+    mode = sys.argv[1] if len(sys.argv) > 1 else "ref"
+    if mode == "ref":
+        out = sys.argv[sys.argv.index("--out") + 1] if "--out" in sys.argv else None
+        run_ref(out)
+    else:
+        print(json.dumps(run_gpu()))
