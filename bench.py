@@ -183,17 +183,18 @@ def kernel_work(kernel, launches, N, n, st):
         return "tensor", sum(float(n + 1) * (n + 1) * k for k in ks)  # lower triangle x 2 flop
     if kernel == "k_trsm_small":
         return "tensor", sum(float(n + 1) * k * k for k in ks)
-    # large k: two-level TRSM -- the left-looking kernel solves inside 256-wide outer blocks, K = 256 GEMMs carry the rest
+    # large k: two-level TRSM -- the left-looking kernel solves inside 1024-wide outer blocks, K = 1024 GEMMs carry the rest
     if kernel == "k_trsm_ll":
-        return "tensor", sum(float(n + 1) * min(256.0 * k, k * k) for k in ks)
+        return "tensor", sum(float(n + 1) * min(1024.0 * k, k * k) for k in ks)
     if kernel == "k_gemm_dmma/trsm_outer":
-        return "tensor", sum(float(n + 1) * max(k * k - 256.0 * k, 0.0) for k in ks)
+        return "tensor", sum(float(n + 1) * max(k * k - 1024.0 * k, 0.0) for k in ks)
     if kernel == "cholesky":  # k_chol_panel + k_gemm_dmma/chol_outer + k_chol_trinv (or the single-CTA k_chol_small)
         return "tensor", sum(k**3 / 3.0 for k in ks)
     return None, None
 
 
 CHOL_KERNELS = ("k_chol_panel", "k_gemm_dmma/chol_outer", "k_chol_trinv", "k_chol_small")
+TRSM_KERNELS = ("k_trsm_ll", "k_gemm_dmma/trsm_outer")
 
 # DRAM bytes (read + write) per launch of the dominant kernels from this round's `ncu --set full` captures:
 #   profiles/r02_syrk_c3.md      k_gemm_dmma/syrk_P at N = 2000, k = 3608: 8.54 GB read + 1.15 GB written
@@ -207,11 +208,15 @@ def roofline_table(prof, frames, N, n, st, fp64_peak):
     tot = sum(v[1] for v in prof.values())
     rows = {}
     chol = [0, 0.0]
+    trsm = [0, 0.0]
     for name, (cnt, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
         row = dict(launches_per_frame=cnt / frames, ms_per_frame=ms / frames, share=ms / tot)
         if name in CHOL_KERNELS:
             chol[0] += cnt
             chol[1] += ms
+        if name in TRSM_KERNELS:
+            trsm[0] += cnt
+            trsm[1] += ms
         bound, amount = kernel_work(name, cnt / frames, N, n, st)
         if bound == "hbm" and ms > 0:
             ach = amount / (ms / frames * 1e-3) / 1e9
@@ -225,6 +230,11 @@ def roofline_table(prof, frames, N, n, st, fp64_peak):
         ach = amount / (chol[1] / frames * 1e-3) / 1e12
         rows["cholesky (all of its kernels)"] = dict(launches_per_frame=chol[0] / frames, ms_per_frame=chol[1] / frames, share=chol[1] / tot, bound="tensor",
                                                      unit="TFLOP/s", achieved=ach, peak=fp64_peak, frac=ach / fp64_peak)
+    if trsm[1] > 0 and len([k for k in prof if k in TRSM_KERNELS]) > 1:
+        amount = sum(float(n + 1) * (2.0 * m) ** 2 for m in (st["m_li"], st["m_hi"]))
+        ach = amount / (trsm[1] / frames * 1e-3) / 1e12
+        rows["triangular solve (all of its kernels)"] = dict(launches_per_frame=trsm[0] / frames, ms_per_frame=trsm[1] / frames, share=trsm[1] / tot, bound="tensor",
+                                                             unit="TFLOP/s", achieved=ach, peak=fp64_peak, frac=ach / fp64_peak)
     return rows
 
 
@@ -592,7 +602,7 @@ def bench_c3(args, world, rank, local):
     st = {k: float(np.mean([s_[k] for s_ in stats])) for k in stats[0]}
     fp64_peak = fp64_gemm_peak()
     kernels = roofline_table(prof, PF, N, n, st, fp64_peak)
-    top = next(k for k in kernels if not k.startswith("cholesky ("))
+    top = next(k for k in kernels if "(all of its kernels)" not in k)
     roof = dict(kernel=top, **{k: v for k, v in kernels[top].items()})
     roof["traffic"] = NCU_TRAFFIC.get(top)
     roof["algorithmic_bytes"] = 2.0 * 8.0 * n * (n + 1) / 2 + 8.0 * (n + 1) * 2.0 * st["m_hi"]  # P lower triangle read + written, V read once
@@ -719,7 +729,7 @@ def bench_c5(args, world, rank, local, filters_total=None, steps=None, warmup=No
         if "achieved" in row:
             row["achieved"] *= Bl
             row["frac"] *= Bl
-    top = next(k for k in kernels if not k.startswith("cholesky ("))
+    top = next(k for k in kernels if "(all of its kernels)" not in k)
     roof = dict(kernel=top, **kernels[top])
     roof["traffic"] = NCU_TRAFFIC[top] * Bl if top == "k_syrk_rows" else NCU_TRAFFIC.get(top)
     # whole batch frame against HBM: every filter's P is read and written once per non-empty update, + the P columns W = P H^T gathers
