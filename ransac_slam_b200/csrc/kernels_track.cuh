@@ -963,15 +963,15 @@ __device__ __forceinline__ bool support_pair_inlier(const DevFilter& F, const Ca
 // (c) 1-point RANSAC (src/Tracking.cpp:352-539)
 // ---------------------------------------------------------------------------------------------------------------
 // c.1 ordered compaction of the individually-compatible list and the matched inverse-depth list (z_id columns, :361-397)
-__device__ __forceinline__ void ransac_compact_cta(DevFilter& F) {  // CTA-collective, 256 threads
-    // flags are 0 / 1: ordered positions from one ballot per warp + the warp totals (three barriers per 256 features instead of the
+__device__ __forceinline__ void ransac_compact_cta(DevFilter& F) {  // CTA-collective, any block size that is a multiple of 32 (<= 1024)
+    // flags are 0 / 1: ordered positions from one ballot per warp + the warp totals (three barriers per block of features instead of the
     // 34 of a shared-memory scan)
-    __shared__ int s_wa[8], s_wb[8], s_wc[8];
+    __shared__ int s_wa[32], s_wb[32], s_wc[32];
     __shared__ int s_base[3];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     if (threadIdx.x == 0) s_base[0] = s_base[1] = s_base[2] = 0;
     __syncthreads();
-    for (int base = 0; base < F.N; base += 256) {
+    for (int base = 0; base < F.N; base += blockDim.x) {
         const int i = base + threadIdx.x;
         bool a = false, b = false, c = false;
         if (i < F.N) {
@@ -1007,7 +1007,7 @@ __device__ __forceinline__ void ransac_compact_cta(DevFilter& F) {  // CTA-colle
         __syncthreads();
         if (threadIdx.x == 0) {
             int ta = 0, tb = 0, tc = 0;
-            for (int w2 = 0; w2 < 8; w2++) {
+            for (int w2 = 0; w2 < nw; w2++) {
                 ta += s_wa[w2];
                 tb += s_wb[w2];
                 tc += s_wc[w2];
@@ -1025,7 +1025,7 @@ __device__ __forceinline__ void ransac_compact_cta(DevFilter& F) {  // CTA-colle
     }
     for (int i = threadIdx.x; i < F.N; i += blockDim.x) F.support[i] = 0;  // accumulated with atomics by k_ransac_support
 }
-__global__ void __launch_bounds__(256) k_ransac_compact(DevFilter* Fs) { ransac_compact_cta(Fs[blockIdx.y]); }
+__global__ void __launch_bounds__(1024) k_ransac_compact(DevFilter* Fs) { ransac_compact_cta(Fs[blockIdx.y]); }
 
 // c.2 one thread per distinct 1-point hypothesis t (match p = ic_list[t]): partial EKF state update restricted to the camera
 //     (src/Tracking.cpp:419-422):  g = S_p^-1 (z_p - h_p);  a = Hc_p^T g;  b = Hf_p^T g;  x_i[0..6] = x[0..6] + P[0..6,nz] [a;b]
@@ -1477,7 +1477,7 @@ __global__ void __launch_bounds__(256) k_sweep_reduce(DevFilter* Fs, const int* 
 //   k_sweep_compact : ordered match lists (k_ransac_compact) + zeroing of the dedupe marks and of the key / pair counter
 //   k_sweep_prep    : blocks [0, nb_hyp) build the hypothesis constants of the distinct hypotheses [t_lo, t_hi) and the row table;
 //                     the remaining blocks mark which distinct hypotheses the id range [h0, h1) references (k_sweep_mark)
-__global__ void __launch_bounds__(256) k_sweep_compact(DevFilter* Fs, int* used, int n_used, unsigned long long* key2) {
+__global__ void __launch_bounds__(1024) k_sweep_compact(DevFilter* Fs, int* used, int n_used, unsigned long long* key2) {
     ransac_compact_cta(Fs[0]);
     for (int i = threadIdx.x; i < n_used; i += blockDim.x) used[i] = 0;
     if (threadIdx.x < 2) key2[threadIdx.x] = 0ull;

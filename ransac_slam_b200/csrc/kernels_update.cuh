@@ -1390,11 +1390,11 @@ __global__ void __launch_bounds__(SR_THREADS, 1) k_syrk_rows(DevFilter* Fs, int 
         }
         const double* as = As + kt * SR_BK * SR_LD;
         const double* bs = Bs + (q % SR_STAGES) * SR_BK * SR_LD;
-        // m8 tiles of this warp that hold at least one valid row (the last tile row of a 613-state filter has 38 of 64), and whether the
-        // warp's 32 x 32 block lies entirely above the diagonal of a diagonal tile: both warp-uniform, both pure padding work otherwise
-        // (ncu: tensor pipe 63.5 % active for 51 % useful -- a fifth of the issued DMMAs produced entries that are never stored)
-        const int mt_live = min(4, max(0, (M - (m0 + wm0) + 7) >> 3));
-        const bool dead = (n0 == m0 && wn0 > wm0) || mt_live == 0;
+        // a warp whose 32 x 32 block lies entirely above the diagonal of a diagonal tile, or entirely below the last state row, only
+        // produces entries that are never stored: it keeps the pipeline protocol (loads, barriers) and skips the arithmetic, which leaves
+        // its scheduler's tensor pipe to the other warp group.  (Predicating single m8 tiles inside the unrolled DMMA stream was tried
+        // and LOST 6 %: the predicate breaks the back-to-back issue of the 16 DMMAs.)
+        const bool dead = (n0 == m0 && wn0 > wm0) || (m0 + wm0 >= M);
         if (!dead) {
 #pragma unroll
             for (int ks = 0; ks < SR_BK / 4; ks++) {
@@ -1405,12 +1405,9 @@ __global__ void __launch_bounds__(SR_THREADS, 1) k_syrk_rows(DevFilter* Fs, int 
 #pragma unroll
                 for (int nt = 0; nt < 4; nt++) bf[nt] = bs[krow * SR_LD + wn0 + nt * 8 + (lane >> 2)];
 #pragma unroll
-                for (int mt = 0; mt < 4; mt++) {
-                    if (mt < mt_live) {
+                for (int mt = 0; mt < 4; mt++)
 #pragma unroll
-                        for (int nt = 0; nt < 4; nt++) dmma8x8x4(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
-                    }
-                }
+                    for (int nt = 0; nt < 4; nt++) dmma8x8x4(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
             }
         }
         if (kt == nkt - 1) {  // epilogue of this tile: P -= acc (lower part, mirrored), row n -> state correction

@@ -299,7 +299,7 @@ int run_ransac_core(rslam_filter* f, bool select, bool gather_li = false) {
     if (N <= 256) {
         LAUNCH(f, k_ransac_compact_hyp, dim3(1, B), 256, 0, f->dF, q1);
     } else {
-        LAUNCH(f, k_ransac_compact, dim3(1, B), 256, 0, f->dF);
+        LAUNCH(f, k_ransac_compact, dim3(1, B), N > 1024 ? 1024 : 256, 0, f->dF);
         LAUNCH(f, k_ransac_hyp, dim3(cdiv(N, 128), B), 128, 0, f->dF, q1);
     }
     if (select) {
@@ -1091,7 +1091,7 @@ static int sweep_local(rslam_filter* f, const int* hyp_match_idx, int n_hyp, int
     const bool dedupe = f->par.dedupe_hypotheses != 0;
     const int tlo = match_begin < N ? match_begin : N, thi = match_end < N ? match_end : N;
     // launch 1: ordered match lists; zeroes the dedupe marks, the key and the pair counter
-    LAUNCH(f, k_sweep_compact, 1, 256, 0, f->dF, f->d_used, f->Nmax, f->d_key);
+    LAUNCH(f, k_sweep_compact, 1, N > 1024 ? 1024 : 256, 0, f->dF, f->d_used, f->Nmax, f->d_key);
     // launch 2: hypothesis constants of the distinct hypotheses this shard can score + the row table + the dedupe marks
     {
         const int nt = dedupe ? (thi - tlo) : N;
