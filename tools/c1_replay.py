@@ -128,7 +128,7 @@ def run_gpu():
         x13 = np.frombuffer(raw[k * rec:k * rec + 104], dtype=np.float64)
         cnt = np.frombuffer(raw[k * rec + 104:(k + 1) * rec], dtype=np.int32)
         cnts.append([int(v) for v in cnt[:4]])
-        ok = (cnt[0] == g["N"][k] and cnt[1] == g["ic"][k] and cnt[2] == g["li"][k] and cnt[3] == g["hi"][k]
+        ok = (k < g["N"].size and cnt[0] == g["N"][k] and cnt[1] == g["ic"][k] and cnt[2] == g["li"][k] and cnt[3] == g["hi"][k]
               and np.allclose(x13, g["x13"][k], rtol=1e-9, atol=1e-10))
         if ok and agree == k:
             agree = k + 1
