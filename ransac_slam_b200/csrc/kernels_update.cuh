@@ -285,11 +285,12 @@ struct PanelSmem {
     double* sRd;
     double* sW;  // [32][kInvLd]
 };
+template <int LD = kTld>
 __device__ __forceinline__ PanelSmem panel_carve(double* base) {
     PanelSmem p;
     p.sT = base;
-    p.sX = reinterpret_cast<double(*)[kNB + 1]>(base + kNB * kTld);
-    p.sRd = base + kNB * kTld + kNB * (kNB + 1);
+    p.sX = reinterpret_cast<double(*)[kNB + 1]>(base + kNB * LD);
+    p.sRd = base + kNB * LD + kNB * (kNB + 1);
     p.sW = p.sRd + kNB;
     return p;
 }
@@ -325,6 +326,7 @@ __device__ __forceinline__ void warp_potrf16(double (&a)[kSB], double (&rd)[kSB]
 // In-place factorisation of the panel in sT: rows 0..63 = diagonal block (lower triangle valid, identity padding beyond w), rows
 // 64..R-1 = the rows below it.  On exit rows 0..63 hold L_jj (lower, zeros above), rows >= 64 hold A L_jj^-T, sRd the reciprocal
 // diagonal.  CTA-collective (256 threads).
+template <int LD = kTld>
 __device__ __forceinline__ void smem_panel_factor(const PanelSmem& ps, int R, int w) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double* sT = ps.sT;
@@ -338,11 +340,11 @@ __device__ __forceinline__ void smem_panel_factor(const PanelSmem& ps, int R, in
             double a[kSB], rd[kSB];
             const int l16 = lane & 15, r = c0 + l16;
 #pragma unroll
-            for (int c = 0; c < kSB; c++) a[c] = (c <= l16) ? sT[(c0 + c) * kTld + r] : 0.0;
+            for (int c = 0; c < kSB; c++) a[c] = (c <= l16) ? sT[(c0 + c) * LD + r] : 0.0;
             warp_potrf16(a, rd);
             if (lane < kSB) {
 #pragma unroll
-                for (int c = 0; c < kSB; c++) sT[(c0 + c) * kTld + r] = (c <= lane) ? a[c] : 0.0;
+                for (int c = 0; c < kSB; c++) sT[(c0 + c) * LD + r] = (c <= lane) ? a[c] : 0.0;
                 double myrd = 1.0;
 #pragma unroll
                 for (int c = 0; c < kSB; c++)
@@ -357,16 +359,16 @@ __device__ __forceinline__ void smem_panel_factor(const PanelSmem& ps, int R, in
             if (i < R) {
                 double a[kSB];
 #pragma unroll
-                for (int c = 0; c < kSB; c++) a[c] = sT[(c0 + c) * kTld + i];
+                for (int c = 0; c < kSB; c++) a[c] = sT[(c0 + c) * LD + i];
 #pragma unroll
                 for (int c = 0; c < kSB; c++) {
                     const double x = a[c] * ps.sRd[c0 + c];
                     a[c] = x;
 #pragma unroll
-                    for (int c2 = c + 1; c2 < kSB; c2++) a[c2] = fma(-x, sT[(c0 + c) * kTld + c0 + c2], a[c2]);
+                    for (int c2 = c + 1; c2 < kSB; c2++) a[c2] = fma(-x, sT[(c0 + c) * LD + c0 + c2], a[c2]);
                 }
 #pragma unroll
-                for (int c = 0; c < kSB; c++) sT[(c0 + c) * kTld + i] = a[c];
+                for (int c = 0; c < kSB; c++) sT[(c0 + c) * LD + i] = a[c];
             }
         }
         __syncthreads();
@@ -380,19 +382,19 @@ __device__ __forceinline__ void smem_panel_factor(const PanelSmem& ps, int R, in
                 double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
 #pragma unroll
                 for (int ks = 0; ks < kSB / 4; ks++) {
-                    const double* kr = sT + (c0 + ks * 4 + (lane & 3)) * kTld + base;
+                    const double* kr = sT + (c0 + ks * 4 + (lane & 3)) * LD + base;
                     const double bf = kr[nt * 8 + (lane >> 2)];
                     dmma8x8x4(c00, c01, kr[mt * 16 + (lane >> 2)], bf);
                     dmma8x8x4(c10, c11, kr[mt * 16 + 8 + (lane >> 2)], bf);
                 }
                 const int i = base + mt * 16 + (lane >> 2), cc = base + nt * 8 + 2 * (lane & 3);
                 if (i < R) {
-                    if (cc <= i) sT[cc * kTld + i] -= c00;
-                    if (cc + 1 <= i) sT[(cc + 1) * kTld + i] -= c01;
+                    if (cc <= i) sT[cc * LD + i] -= c00;
+                    if (cc + 1 <= i) sT[(cc + 1) * LD + i] -= c01;
                 }
                 if (i + 8 < R) {
-                    if (cc <= i + 8) sT[cc * kTld + i + 8] -= c10;
-                    if (cc + 1 <= i + 8) sT[(cc + 1) * kTld + i + 8] -= c11;
+                    if (cc <= i + 8) sT[cc * LD + i + 8] -= c10;
+                    if (cc + 1 <= i + 8) sT[(cc + 1) * LD + i + 8] -= c11;
                 }
             }
             __syncthreads();
@@ -409,6 +411,7 @@ __device__ __forceinline__ void smem_panel_factor(const PanelSmem& ps, int R, in
 //            64 of an unblocked substitution (which cost 11.6 k cycles, a quarter of the single-CTA factorisation).
 //   level 1 / 2: the off-diagonal 16 x 16 and 32 x 32 blocks from two small products each on the fp64 tensor cores.
 // CTA-collective (256 threads).
+template <int LD = kTld>
 __device__ __forceinline__ void smem_trinv64(const PanelSmem& ps) {
     const unsigned fm = 0xffffffffu;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -424,7 +427,7 @@ __device__ __forceinline__ void smem_trinv64(const PanelSmem& ps) {
             if (p == (t & 3)) ps.sX[r0 + t][r0 + cl] = x;
             // rows 4 q + p behind t; entries of rows <= t are already final (or were stored above) and may be clobbered
 #pragma unroll
-            for (int q = t / 4; q < 4; q++) b[q] = fma(-sT[(r0 + t) * kTld + r0 + 4 * q + p], x, b[q]);
+            for (int q = t / 4; q < 4; q++) b[q] = fma(-sT[(r0 + t) * LD + r0 + 4 * q + p], x, b[q]);
         }
         // blocks above the block diagonal are zero
         for (int e = tid; e < 6 * 256; e += 256) {
@@ -442,7 +445,7 @@ __device__ __forceinline__ void smem_trinv64(const PanelSmem& ps) {
 #pragma unroll
         for (int ks = 0; ks < 4; ks++) {  // T = L21 * X11
             const int k = base + ks * 4 + fk;
-            dmma8x8x4(c0, c1, sT[k * kTld + base + 16 + mi * 8 + fr], ps.sX[k][base + ni * 8 + fr]);
+            dmma8x8x4(c0, c1, sT[k * LD + base + 16 + mi * 8 + fr], ps.sX[k][base + ni * 8 + fr]);
         }
         double* T = ps.sW + h * 16 * kInvLd;  // [16][kInvLd] per half
         T[(mi * 8 + fr) * kInvLd + ni * 8 + 2 * fk] = c0;
@@ -464,7 +467,7 @@ __device__ __forceinline__ void smem_trinv64(const PanelSmem& ps) {
 #pragma unroll
         for (int ks = 0; ks < 8; ks++) {  // T = L21 * X11
             const int k = ks * 4 + fk;
-            const double a = sT[k * kTld + 32 + mi * 8 + fr];
+            const double a = sT[k * LD + 32 + mi * 8 + fr];
 #pragma unroll
             for (int u = 0; u < 2; u++) dmma8x8x4(c[u][0], c[u][1], a, ps.sX[k][(nj + u) * 8 + fr]);
         }
@@ -500,6 +503,7 @@ __device__ __forceinline__ void store_linv(const double (*sX)[kNB + 1], double* 
 // Warp `wp` takes columns wp, wp + 8, ...; a lane takes rows lane, lane + 32, ...: no integer divisions, and all of a thread's loads
 // of a column batch are issued before the first store (the element-indexed loop this replaces kept one load in flight per
 // thread and cost ~8.7 k cycles per 64 x 128 panel, a fifth of the single-CTA factorisation).
+template <int LD = kTld>
 __device__ __forceinline__ void panel_load(const PanelSmem& ps, const double* S, int ld, int j0, int w, int r0, int nr) {
     // plain (coherent) loads: k_chol_small re-reads entries of S that its own trailing update has just written.
     // 256 threads: warp wp owns columns wp + 8 cs; all (up to 64) loads of a thread are issued before its first store.
@@ -523,7 +527,7 @@ __device__ __forceinline__ void panel_load(const PanelSmem& ps, const double* S,
     }
 #pragma unroll
     for (int cs = 0; cs < 8; cs++) {
-        double* dst = ps.sT + (wp + 8 * cs) * kTld;
+        double* dst = ps.sT + (wp + 8 * cs) * LD;
         dst[lane] = v[cs][0];
         dst[lane + 32] = v[cs][1];
 #pragma unroll
@@ -650,6 +654,8 @@ __global__ void __launch_bounds__(256) k_chol_panel(DevFilter* Fs, int step) {
 
 // ---- U4b: explicit inverses of ALL 64 x 64 diagonal blocks of the finished factor, one CTA per block (the TRSM kernel multiplies by
 //           them on tensor cores).  Built after the factorisation so that the 63 serial panel steps do not each carry one.
+constexpr int kTrinvLd = 68;  // 64 rows are enough here; == 4 (mod 16) like kTld, so the same access patterns stay conflict free
+constexpr int kTrinvSmemBytes = (kNB * kTrinvLd + kNB * (kNB + 1) + kNB + 32 * kInvLd) * (int)sizeof(double);  // 77 KB: 2 CTAs per SM
 __global__ void __launch_bounds__(256) k_chol_trinv(DevFilter* Fs) {
     DevFilter& F = Fs[blockIdx.y];
     const int kk = F.ctl[CTL_K];
@@ -657,13 +663,13 @@ __global__ void __launch_bounds__(256) k_chol_trinv(DevFilter* Fs) {
     if (j0 >= kk) return;
     const int w = min(kNB, kk - j0);
     extern __shared__ __align__(16) double psm[];
-    const PanelSmem ps = panel_carve(psm);
-    panel_load(ps, F.Sm, F.lds, j0, w, j0, 0);
+    const PanelSmem ps = panel_carve<kTrinvLd>(psm);
+    panel_load<kTrinvLd>(ps, F.Sm, F.lds, j0, w, j0, 0);
     __syncthreads();
-    if (threadIdx.x < kNB) ps.sRd[threadIdx.x] = 1.0 / ps.sT[threadIdx.x * kTld + threadIdx.x];
+    if (threadIdx.x < kNB) ps.sRd[threadIdx.x] = 1.0 / ps.sT[threadIdx.x * kTrinvLd + threadIdx.x];
     // panel_load leaves the strict upper triangle of the block zero and the padding identity: exactly what smem_trinv64 expects
     __syncthreads();
-    smem_trinv64(ps);
+    smem_trinv64<kTrinvLd>(ps);
     store_linv(ps.sX, F.Linv + (size_t)blockIdx.x * kNB * kNB, threadIdx.x, blockDim.x);
 }
 
@@ -692,9 +698,8 @@ __global__ void __launch_bounds__(256) k_chol_small(DevFilter* Fs) {
         PH(0);
         smem_panel_factor(ps, kNB + rem, w);
         PH(1);
-        // inverse of the diagonal block (all warps), then store the panel and run the trailing update on DMMA tiles
-        smem_trinv64(ps);
-        PH(4);
+        // store the panel and run the trailing update on DMMA tiles (the inverses of the diagonal blocks, which the TRSM kernel
+        // multiplies by, are built afterwards by k_chol_trinv for all blocks at once: ~10 k cycles less on this serial chain per panel)
         {
             {
                 const int ln = threadIdx.x & 31, wp = threadIdx.x >> 5;
@@ -740,11 +745,8 @@ __global__ void __launch_bounds__(256) k_chol_small(DevFilter* Fs) {
                         }
             }
         }
-        __syncthreads();
+        __syncthreads();  // the trailing update must have landed before the next panel is loaded; sT is reused
         PH(2);
-        store_linv(ps.sX, F.Linv + (size_t)(j0 / kNB) * kNB * kNB, threadIdx.x, blockDim.x);
-        __syncthreads();  // the trailing update must have landed before the next panel is loaded; sX / sT are reused
-        PH(3);
     }
 #ifdef RSLAM_PHASE_CLOCKS
     if (threadIdx.x == 0)

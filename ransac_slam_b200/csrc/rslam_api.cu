@@ -118,6 +118,18 @@ int dev_alloc(rslam_filter* f, T** p, size_t count, bool zero = true) {
     return 0;
 }
 
+// give back a buffer obtained from dev_alloc (regrown scratch); stream-ordered work that still uses it has been issued on f->stream
+void dev_release(rslam_filter* f, void* p) {
+    if (!p) return;
+    for (size_t i = 0; i < f->allocs.size(); i++)
+        if (f->allocs[i] == p) {
+            f->allocs.erase(f->allocs.begin() + i);
+            break;
+        }
+    cudaStreamSynchronize(f->stream);
+    cudaFree(p);
+}
+
 int push_descr(rslam_filter* f) {
     CK(cudaMemcpyAsync(f->dF, f->hF.data(), sizeof(DevFilter) * f->B, cudaMemcpyHostToDevice, f->stream));
     // hF is pageable: the copy is staged before the call returns, so later host edits are safe
@@ -227,11 +239,13 @@ int run_update(rslam_filter* f, int which, bool gathered = false, bool defer_jno
         if (fork) CK(cudaEventRecord(f->ev_join, f->side));
         LAUNCH_N(f, "k_upd_S", k_upd_S_direct, dim3(cdiv(N * (N + 1) / 2, 8), 1, B), 256, 0, f->dF);
         LAUNCH(f, k_chol_small, dim3(1, B), 256, kCholSmallSmemBytes, f->dF);
+        LAUNCH(f, k_chol_trinv, dim3(nsteps, B), 256, kTrinvSmemBytes, f->dF);
         if (fork) CK(cudaStreamWaitEvent(f->stream, f->ev_join, 0));
     } else if (kmax <= kCholSmallMaxK) {
         LAUNCH(f, k_upd_W, dim3(cdiv(n, 256), cdiv(N, kWChunk), B), 256, 0, f->dF);
         LAUNCH(f, k_upd_S, dim3(cdiv(N, 16), cdiv(N, 16), B), 256, 0, f->dF);
         LAUNCH(f, k_chol_small, dim3(1, B), 256, kCholSmallSmemBytes, f->dF);
+        LAUNCH(f, k_chol_trinv, dim3(nsteps, B), 256, kTrinvSmemBytes, f->dF);
     } else {
         LAUNCH(f, k_upd_W, dim3(cdiv(n, 256), cdiv(N, kWChunk), B), 256, 0, f->dF);
         LAUNCH(f, k_upd_S, dim3(cdiv(N, 16), cdiv(N, 16), B), 256, 0, f->dF);
@@ -245,7 +259,7 @@ int run_update(rslam_filter* f, int which, bool gathered = false, bool defer_jno
                          (int)GEMM_CHOL_OUTER, s / kOB);
             }
         }
-        LAUNCH(f, k_chol_trinv, dim3(nsteps, B), 256, kPanelSmemBytes, f->dF);
+        LAUNCH(f, k_chol_trinv, dim3(nsteps, B), 256, kTrinvSmemBytes, f->dF);
     }
     if (kmax <= SR_KMAX) {  // small systems: W rows resident in smem, L streamed once
         LAUNCH(f, k_trsm_small, dim3(cdiv(n + 1, TS_R), B), TS_THREADS, trsm_small_smem_bytes(kmax), f->dF, round_up(kmax, kNB));
@@ -377,7 +391,7 @@ int rslam_create(const rslam_camera* cam, const rslam_params* par, int max_featu
     CKF(cudaFuncSetAttribute(k_trsm_ll<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TrsmCfg<32, 2>::kSmemBytes));
     CKF(cudaFuncSetAttribute(k_ransac_support, cudaFuncAttributeMaxDynamicSharedMemorySize, kSupSmemBytes));
     CKF(cudaFuncSetAttribute(k_chol_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPanelSmemBytes));
-    CKF(cudaFuncSetAttribute(k_chol_trinv, cudaFuncAttributeMaxDynamicSharedMemorySize, kPanelSmemBytes));
+    CKF(cudaFuncSetAttribute(k_chol_trinv, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrinvSmemBytes));
     CKF(cudaFuncSetAttribute(k_chol_small, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholSmallSmemBytes));
     CKF(cudaFuncSetAttribute(k_trsm_small, cudaFuncAttributeMaxDynamicSharedMemorySize, trsm_small_smem_bytes(SR_KMAX)));
     CKF(cudaFuncSetAttribute(k_syrk_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, syrk_rows_smem_bytes(SR_KMAX)));
@@ -1455,11 +1469,17 @@ int fast_detect(rslam_filter* f, int b, int x0, int y0, int w, int h, int thresh
     if (!D.image) return fail(RSLAM_ERR_INVALID, "FAST: no image is bound to filter %d (rslam_set_image)", b);
     if (x0 < 0 || y0 < 0 || w < 1 || h < 1 || x0 + w > D.img_cols || y0 + h > D.img_rows) return fail(RSLAM_ERR_INVALID, "FAST: window outside the image");
     if ((size_t)w * h > f->fast_cap) {
+        dev_release(f, f->fast_score);
+        f->fast_score = nullptr;
+        f->fast_cap = 0;
         int rc = dev_alloc(f, &f->fast_score, (size_t)w * h);
         if (rc) return rc;
         f->fast_cap = (size_t)w * h;
     }
     if (max_kp > f->fast_xy_cap) {
+        dev_release(f, f->fast_xy);
+        f->fast_xy = nullptr;
+        f->fast_xy_cap = 0;
         int rc = dev_alloc(f, &f->fast_xy, (size_t)2 * max_kp);
         if (rc) return rc;
         f->fast_xy_cap = max_kp;
