@@ -167,6 +167,7 @@ def run_gpu():
     nf = len(raw) // rec
     agree = agree_orc = 0
     cnts = []
+    dx = []
     for k in range(nf):
         x13 = np.frombuffer(raw[k * rec:k * rec + 104], dtype=np.float64)
         cnt = np.frombuffer(raw[k * rec + 104:(k + 1) * rec], dtype=np.int32)
@@ -175,13 +176,14 @@ def run_gpu():
               and np.allclose(x13, g["x13"][k], rtol=1e-9, atol=1e-10))
         if ok and agree == k:
             agree = k + 1
+        dx.append(float(np.abs(x13 - g["orc_x13"][k]).max()))
         oko = (cnt[0] == g["orc_N"][k] and cnt[1] == g["orc_ic"][k] and cnt[2] == g["orc_li"][k] and cnt[3] == g["orc_hi"][k]
                and np.allclose(x13, g["orc_x13"][k], rtol=1e-9, atol=1e-10))
         if oko and agree_orc == k:
             agree_orc = k + 1
     return dict(impl="b200", workload="C1: bundled sequence through the C++ host classes (rslam_replay_pgm), incl. process start, CUDA context, file IO",
                 frames=nf, value=nf / wall, unit="frames/s", seconds=wall, frames_in_agreement_with_reference=agree, reference_frames=int(g["N"].size),
-                frames_before_reference_ub=int(g["defined"]), frames_in_agreement_with_oracle=agree_orc,
+                frames_before_reference_ub=int(g["defined"]), frames_in_agreement_with_oracle=agree_orc, max_abs_dx13_vs_oracle=dx,
                 N=[c[0] for c in cnts], ic=[c[1] for c in cnts], li=[c[2] for c in cnts], hi=[c[3] for c in cnts])
 
 
