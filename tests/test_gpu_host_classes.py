@@ -84,3 +84,87 @@ def test_pgm_replay_through_host_classes_matches_the_reference(tmp_path):
         pre = f"bundled_k{k}_"
         H.assert_x_close(x13, g[pre + "x"][:13], what=f"camera state after frame {k}")
         assert cnt[0] == g[pre + "types"].size and cnt[1] == g[pre + "ic"].sum() and cnt[2] == g[pre + "li"].sum() and cnt[3] == g[pre + "hi"].sum(), (k, cnt)
+
+
+_UPDATE_SRC = r'''
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include "ransac_slam/ExtendKF.h"
+using namespace ransac_slam;
+// reads n, k, x(n), P(n x n col-major), H(k x n col-major), z(k), h(k) as doubles from argv[1]; writes x_k_k (n) and p_k_k (n x n) to argv[2]
+int main(int argc, char** argv) {
+    FILE* f = fopen(argv[1], "rb");
+    double hdr[2];
+    if (fread(hdr, 8, 2, f) != 2) return 2;
+    const int n = (int)hdr[0], k = (int)hdr[1];
+    Eigen::VectorXd x(n), z(k), h(k);
+    Eigen::MatrixXd P(n, n), H(k, n), R(k, k);
+    if (fread(x.data(), 8, n, f) != (size_t)n || fread(P.data(), 8, (size_t)n * n, f) != (size_t)n * n || fread(H.data(), 8, (size_t)k * n, f) != (size_t)k * n ||
+        fread(z.data(), 8, k, f) != (size_t)k || fread(h.data(), 8, k, f) != (size_t)k)
+        return 3;
+    fclose(f);
+    for (int i = 0; i < k; i++) for (int j = 0; j < k; j++) R(i, j) = i == j ? 1.0 : 0.0;
+    CamParam cam;
+    cam.k1 = 0.06333; cam.k2 = 0.01390; cam.nRows = 240; cam.nCols = 320; cam.dx = cam.dy = 0.0112; cam.f = 2.1735;
+    cam.Cx = 1.7945 / 0.0112; cam.Cy = 1.4433 / 0.0112;
+    ExtendKF kf("", &cam, "constant_velocity");
+    const int N = (n - 13) / 6;
+    kf.features_info.resize(N);  // inverse-depth features (the default type)
+    kf.update(x, P, H, R, z, h);
+    if (kf.last_status() != 0) { fprintf(stderr, "update failed: %d %s\n", kf.last_status(), rslam_last_error()); return 4; }
+    // a Jacobian without the measurement structure must be refused, not silently mangled
+    Eigen::MatrixXd Hbad = H;
+    Hbad(0, 8) = 1.0;  // velocity column
+    Eigen::VectorXd xk = kf.x_k_k;
+    kf.update(x, P, Hbad, R, z, h);
+    if (kf.last_status() == 0) return 5;
+    kf.x_k_k = xk;
+    FILE* o = fopen(argv[2], "wb");
+    fwrite(kf.x_k_k.data(), 8, n, o);
+    fwrite(kf.p_k_k.data(), 8, (size_t)n * n, o);
+    fclose(o);
+    return 0;
+}
+'''
+
+
+def test_host_extendkf_update_runs_on_the_device(tmp_path):
+    """ExtendKF::update(x, P, H, R, z, h) of the C++ drop-in class (src/ExtendKF.cpp:597-639): dense caller-built H with the structure of
+    stacked measurement Jacobians goes through rslam_upload_linearisation + the device update; against the numpy restatement."""
+    from oracle import np_oracle as NP
+
+    host = os.path.join(ROOT, "ransac_slam_b200", "host")
+    lib = os.path.join(ROOT, "ransac_slam_b200", "lib")
+    src = tmp_path / "upd.cpp"
+    src.write_text(_UPDATE_SRC)
+    exe = str(tmp_path / "upd")
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    r = subprocess.run([gxx, "-std=c++17", "-O1", "-w", "-I", host, str(src), os.path.join(host, "host_classes.cpp"), "-o", exe, "-L", lib, "-lrslam_b200",
+                        "-Wl,-rpath," + lib], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    # a prior and a linearisation from a real prediction (oracle), measurements for features 1, 4, 5 of 8
+    scene, x, P = synth.random_spd_state(8, seed=141)
+    o = H.oracle_from(scene, x, P, sparse=False)
+    o.search_ic_matches(None)
+    fo = o.features()
+    sel = [1, 4, 5]
+    assert fo["has_h"][sel].all()
+    n = x.size
+    Hd = np.vstack([o.H_dense(i) for i in sel])
+    h = fo["h"][sel].reshape(-1)
+    z = np.rint(h) + np.tile([0.6, -0.4], len(sel))
+    with open(tmp_path / "in.bin", "wb") as f:
+        f.write(np.array([n, len(z)], dtype=np.float64).tobytes())
+        f.write(x.tobytes())
+        f.write(np.asfortranarray(P).tobytes(order="F"))
+        f.write(np.asfortranarray(Hd).tobytes(order="F"))
+        f.write(z.tobytes())
+        f.write(h.tobytes())
+    r = subprocess.run([exe, str(tmp_path / "in.bin"), str(tmp_path / "out.bin")], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, (r.returncode, r.stderr)
+    raw = np.fromfile(tmp_path / "out.bin", dtype=np.float64)
+    xg, Pg = raw[:n], raw[n:].reshape(n, n, order="F")
+    xn, Pn = NP.ekf_update(x, P, Hd, z, h)
+    H.assert_x_close(xg, xn)
+    H.assert_P_close(Pg, Pn)
