@@ -87,8 +87,15 @@ def bench_c2(args, world, rank, local):
     h_u01 = torch.from_numpy(seq.u01).pin_memory()
     img_b, u_b = rows * cols, seq.u01.shape[1] * 8
 
+    T_e = h_images.shape[0]
+
+    def e2e_in(k):
+        k %= T_e
+        return (h_images.data_ptr() + k * img_b, rows, cols, cols), (h_u01.data_ptr() + k * u_b, seq.u01.shape[1])
+
     def e2e_step(k):
-        ge.frame((h_images.data_ptr() + k * img_b, rows, cols, cols), (h_u01.data_ptr() + k * u_b, seq.u01.shape[1]), predict=True)
+        ge.frame(*e2e_in(k), predict=True)
+        ge.prefetch(*e2e_in(k + 1))  # next frame's host->device copy beside this frame's kernels (one copy per frame)
         return ge.download_pose()
 
     for k in range(W):

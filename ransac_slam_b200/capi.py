@@ -41,7 +41,7 @@ EXPORTS = [
     "rslam_launch_count", "rslam_num_features", "rslam_state_dim", "rslam_upload_state", "rslam_download_state", "rslam_upload_patches",
     "rslam_download_features", "rslam_upload_feature_init", "rslam_set_patch_warp", "rslam_download_patches", "rslam_debug_scratch", "rslam_download_H", "rslam_set_matches", "rslam_set_image", "rslam_begin_frame", "rslam_ekf_prediction",
     "rslam_search_ic_matches", "rslam_ransac_hypotheses", "rslam_ransac_result_get", "rslam_update_li", "rslam_rescue_hi", "rslam_update_hi",
-    "rslam_frame", "rslam_set_graph", "rslam_profile_enable", "rslam_profile_read", "rslam_download_pose", "rslam_support_sweep", "rslam_sweep_mask",
+    "rslam_frame", "rslam_prefetch_inputs", "rslam_set_graph", "rslam_profile_enable", "rslam_profile_read", "rslam_download_pose", "rslam_support_sweep", "rslam_sweep_mask",
     "rslam_comm_init", "rslam_comm_unique_id", "rslam_comm_init_rank", "rslam_comm_destroy", "rslam_comm_size", "rslam_comm_local_size",
     "rslam_support_sweep_multi", "rslam_upload_linearisation", "rslam_predict_measurements", "rslam_match",
 ]
@@ -88,6 +88,7 @@ def load():
     L.rslam_ransac_hypotheses.argtypes = [vp, vp, ci]
     L.rslam_ransac_result_get.argtypes = [vp, ci, C.POINTER(RansacResult)]
     L.rslam_frame.argtypes = [vp, vp, ci, ci, ci, ci, vp, ci, ci]
+    L.rslam_prefetch_inputs.argtypes = [vp, vp, ci, ci, ci, ci, vp, ci]
     L.rslam_download_pose.argtypes = [vp, ci, vp]
     L.rslam_set_graph.argtypes = [vp, ci]
     L.rslam_profile_enable.argtypes = [vp, ci]
@@ -274,9 +275,8 @@ class Filter:
     def update_hi(self):
         self._ck(self.L.rslam_update_hi(self.h))
 
-    def frame(self, images, u01, predict=True, share=False):
-        """images: uint8 array [batch, rows, cols] (or [rows, cols] with share) on the host, or (ptr, rows, cols, stride) on the device.
-        u01: float64 [batch, n_u01] on the host, or (ptr, n_u01) on the device."""
+    def _frame_args(self, images, u01):
+        keep = []
         if images is None:
             ip, rows, cols, stride = None, 0, 0, 0
         elif isinstance(images, tuple):
@@ -286,15 +286,29 @@ class Filter:
             rows, cols = img.shape[-2], img.shape[-1]
             stride = cols
             ip = _p(img)
-            self._keep = [img]
+            keep.append(img)
         if isinstance(u01, tuple):
             up, n_u01 = C.c_void_p(u01[0]), u01[1]
         else:
             u = np.ascontiguousarray(u01, dtype=np.float64)
             n_u01 = u.size // self.batch
             up = _p(u)
-            self._keep.append(u)
+            keep.append(u)
+        return ip, rows, cols, stride, up, n_u01, keep
+
+    def frame(self, images, u01, predict=True, share=False):
+        """images: uint8 array [batch, rows, cols] (or [rows, cols] with share) on the host, or (ptr, rows, cols, stride) on the host
+        (e.g. pinned memory) or the device.  u01: float64 [batch, n_u01] on the host, or (ptr, n_u01) on the host / device."""
+        ip, rows, cols, stride, up, n_u01, keep = self._frame_args(images, u01)
+        self._keep = keep
         self._ck(self.L.rslam_frame(self.h, ip, rows, cols, stride, int(share), up, n_u01, 1 if predict else 0))
+
+    def prefetch(self, images, u01, share=False):
+        """Start copying the NEXT frame's host inputs (same forms as frame(); (ptr, ...) tuples of pinned memory for an asynchronous
+        copy) while the current frame computes; the following frame() with the same host buffers uses them without copying."""
+        ip, rows, cols, stride, up, n_u01, keep = self._frame_args(images, u01)
+        self._keep_pf = keep
+        self._ck(self.L.rslam_prefetch_inputs(self.h, ip, rows, cols, stride, int(share), up, n_u01))
 
     # ---- Map management (src/Map.cpp), covariance resident on the device ----
     def map_delete_feature(self, index, b=0):

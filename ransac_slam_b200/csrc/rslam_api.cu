@@ -63,6 +63,18 @@ struct rslam_filter {
     size_t image_cap = 0;
     double* d_u01 = nullptr;
     size_t u01_cap = 0;
+    // second staging set: rslam_prefetch_inputs copies the NEXT frame's host inputs into it on the copy stream while the current
+    // frame computes; the rslam_frame that is handed the same host pointers swaps the two sets instead of copying
+    unsigned char* pf_images = nullptr;
+    size_t pf_image_cap = 0;
+    double* pf_u01 = nullptr;
+    size_t pf_u01_cap = 0;
+    cudaStream_t copy = nullptr;
+    cudaEvent_t ev_staged = nullptr, ev_free_cur = nullptr, ev_free_pf = nullptr;  // copy done; last frame that read the current / the other set done
+    bool staged = false;
+    const void* staged_img = nullptr;
+    const void* staged_u01 = nullptr;
+    long long staged_geom[5] = {0, 0, 0, 0, 0};  // rows, cols, stride, share, n_u01
     int* d_hyp_idx = nullptr;
     size_t hyp_cap = 0;
     int* d_used = nullptr;
@@ -385,6 +397,10 @@ int rslam_create(const rslam_camera* cam, const rslam_params* par, int max_featu
     CKF(cudaStreamCreateWithFlags(&f->side, cudaStreamNonBlocking));
     CKF(cudaEventCreateWithFlags(&f->ev_fork, cudaEventDisableTiming));
     CKF(cudaEventCreateWithFlags(&f->ev_join, cudaEventDisableTiming));
+    CKF(cudaStreamCreateWithFlags(&f->copy, cudaStreamNonBlocking));
+    CKF(cudaEventCreateWithFlags(&f->ev_staged, cudaEventDisableTiming));
+    CKF(cudaEventCreateWithFlags(&f->ev_free_cur, cudaEventDisableTiming));
+    CKF(cudaEventCreateWithFlags(&f->ev_free_pf, cudaEventDisableTiming));
     CKF(cudaFuncSetAttribute(k_gemm_dmma<128, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<128, 64>::kSmemBytes));
     CKF(cudaFuncSetAttribute(k_gemm_dmma<64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<64, 64>::kSmemBytes));
     CKF(cudaFuncSetAttribute(k_trsm_ll<48, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TrsmCfg<48, 2>::kSmemBytes));
@@ -499,6 +515,12 @@ int rslam_destroy(rslam_filter* f) {
     for (void* p : f->allocs) cudaFree(p);
     if (f->d_images) cudaFree(f->d_images);
     if (f->d_u01) cudaFree(f->d_u01);
+    if (f->pf_images) cudaFree(f->pf_images);
+    if (f->pf_u01) cudaFree(f->pf_u01);
+    if (f->ev_staged) cudaEventDestroy(f->ev_staged);
+    if (f->ev_free_cur) cudaEventDestroy(f->ev_free_cur);
+    if (f->ev_free_pf) cudaEventDestroy(f->ev_free_pf);
+    if (f->copy) cudaStreamDestroy(f->copy);
     if (f->d_hyp_idx) cudaFree(f->d_hyp_idx);
     if (f->d_sup_h) cudaFree(f->d_sup_h);
     if (f->ev_fork) cudaEventDestroy(f->ev_fork);
@@ -512,6 +534,7 @@ int rslam_destroy(rslam_filter* f) {
 int rslam_sync(rslam_filter* f) {
     if (!f) return fail(RSLAM_ERR_INVALID, "null handle");
     CK(cudaStreamSynchronize(f->stream));
+    CK(cudaStreamSynchronize(f->copy));  // an outstanding rslam_prefetch_inputs copy
     return RSLAM_OK;
 }
 void* rslam_stream(rslam_filter* f) { return f ? (void*)f->stream : nullptr; }
@@ -945,6 +968,44 @@ static int run_frame_stages(rslam_filter* f, int flags) {
     return 0;
 }
 
+int rslam_prefetch_inputs(rslam_filter* f, const uint8_t* images, int rows, int cols, int stride, int share, const double* u01, int n_u01) {
+    if (!f) return fail(RSLAM_ERR_INVALID, "null handle");
+    if (!u01 || n_u01 <= 0) return fail(RSLAM_ERR_INVALID, "rslam_prefetch_inputs: u01 must hold at least one draw per filter");
+    if (images && (rows <= 0 || cols <= 0 || stride < cols)) return fail(RSLAM_ERR_INVALID, "rslam_prefetch_inputs: bad image geometry");
+    CK(cudaSetDevice(f->device));
+    if ((images && is_device_ptr(images)) || is_device_ptr(u01))
+        return fail(RSLAM_ERR_INVALID, "rslam_prefetch_inputs: inputs already on the device need no staging -- pass them to rslam_frame");
+    const size_t ineed = images ? (size_t)rows * stride * (share ? 1 : f->B) : 0;
+    const size_t uneed = (size_t)n_u01 * f->B;
+    if (ineed > f->pf_image_cap) {
+        if (f->pf_images) CK(cudaFree(f->pf_images));
+        f->pf_images = nullptr;
+        f->pf_image_cap = 0;
+        CK(cudaMalloc((void**)&f->pf_images, ineed));
+        f->pf_image_cap = ineed;
+    }
+    if (uneed > f->pf_u01_cap) {
+        if (f->pf_u01) CK(cudaFree(f->pf_u01));
+        f->pf_u01 = nullptr;
+        f->pf_u01_cap = 0;
+        CK(cudaMalloc((void**)&f->pf_u01, uneed * sizeof(double)));
+        f->pf_u01_cap = uneed;
+    }
+    CK(cudaStreamWaitEvent(f->copy, f->ev_free_pf, 0));  // the last frame that read this set (no-op if there was none)
+    if (images) CK(cudaMemcpyAsync(f->pf_images, images, ineed, cudaMemcpyHostToDevice, f->copy));
+    CK(cudaMemcpyAsync(f->pf_u01, u01, uneed * sizeof(double), cudaMemcpyHostToDevice, f->copy));
+    CK(cudaEventRecord(f->ev_staged, f->copy));
+    f->staged = true;
+    f->staged_img = images;
+    f->staged_u01 = u01;
+    f->staged_geom[0] = rows;
+    f->staged_geom[1] = cols;
+    f->staged_geom[2] = stride;
+    f->staged_geom[3] = share;
+    f->staged_geom[4] = n_u01;
+    return RSLAM_OK;
+}
+
 int rslam_frame(rslam_filter* f, const uint8_t* images, int rows, int cols, int stride, int share, const double* u01, int n_u01, int flags) {
     if (!f) return fail(RSLAM_ERR_INVALID, "null handle");
     if (!u01 || n_u01 <= 0) return fail(RSLAM_ERR_INVALID, "rslam_frame: u01 must hold at least one draw per filter");
@@ -952,12 +1013,30 @@ int rslam_frame(rslam_filter* f, const uint8_t* images, int rows, int cols, int 
     int rc;
     const unsigned char* ibase = nullptr;
     long long iper = 0;
-    if (images) {
-        if (rows <= 0 || cols <= 0 || stride < cols) return fail(RSLAM_ERR_INVALID, "rslam_frame: bad image geometry");
-        if ((rc = resolve_images(f, images, rows, stride, share, &ibase, &iper))) return rc;
-    }
     const double* ubase = nullptr;
-    if ((rc = resolve_u01(f, u01, n_u01, &ubase))) return rc;
+    if (images && (rows <= 0 || cols <= 0 || stride < cols)) return fail(RSLAM_ERR_INVALID, "rslam_frame: bad image geometry");
+    const bool use_staged = f->staged && f->staged_img == (const void*)images && f->staged_u01 == (const void*)u01 && f->staged_geom[4] == n_u01 &&
+                            (!images || (f->staged_geom[0] == rows && f->staged_geom[1] == cols && f->staged_geom[2] == stride && f->staged_geom[3] == share));
+    f->staged = false;
+    if (use_staged) {
+        // the inputs were copied by rslam_prefetch_inputs: make that set the current one
+        if (images) {  // (no image staged: the current one stays bound)
+            std::swap(f->d_images, f->pf_images);
+            std::swap(f->image_cap, f->pf_image_cap);
+        }
+        std::swap(f->d_u01, f->pf_u01);
+        std::swap(f->u01_cap, f->pf_u01_cap);
+        std::swap(f->ev_free_cur, f->ev_free_pf);
+        CK(cudaStreamWaitEvent(f->stream, f->ev_staged, 0));
+        if (images) {
+            ibase = f->d_images;
+            iper = share ? 0 : (long long)rows * stride;
+        }
+        ubase = f->d_u01;
+    } else {
+        if (images && (rc = resolve_images(f, images, rows, stride, share, &ibase, &iper))) return rc;
+        if ((rc = resolve_u01(f, u01, n_u01, &ubase))) return rc;
+    }
     if ((rc = ensure_update_ws(f))) return rc;
     // bind the inputs in the device descriptors -- skipped when nothing changed (host inputs always land in the same staging buffers)
     if (f->descr_dirty || f->bound_img != ibase || f->bound_iper != iper || f->bound_geom[0] != rows || f->bound_geom[1] != cols || f->bound_geom[2] != stride ||
@@ -985,6 +1064,7 @@ int rslam_frame(rslam_filter* f, const uint8_t* images, int rows, int cols, int 
     if (images) f->have_image = true;
     if (!f->graph_enabled || f->prof) {
         if ((rc = run_frame_stages(f, flags))) return rc;
+        CK(cudaEventRecord(f->ev_free_cur, f->stream));
         return check_launch();
     }
     const long long key = ((long long)f->hN << 40) ^ ((long long)f->hn << 16) ^ ((long long)f->B << 4) ^ ((flags & 1) << 1) ^ (f->have_image ? 1 : 0) ^ (f->warp_patches ? 4 : 0);
@@ -1012,6 +1092,7 @@ int rslam_frame(rslam_filter* f, const uint8_t* images, int rows, int cols, int 
         f->graph_key = key;
     }
     CK(cudaGraphLaunch(f->graph_exec, f->stream));
+    CK(cudaEventRecord(f->ev_free_cur, f->stream));
     f->launches += f->graph_nodes;
     return RSLAM_OK;
 }

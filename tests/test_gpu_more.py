@@ -161,6 +161,49 @@ def test_batch_matches_single_and_graph_matches_stream():
         assert (bat.features(b)["hi"] == ref.features()["hi"]).all()
 
 
+def test_prefetched_inputs_give_the_same_frames_as_inline_copies():
+    """rslam_prefetch_inputs (copy stream + second staging set) only changes WHEN the host inputs are copied: trajectories must be bitwise
+    equal to the inline-copy path, also when a staged set is dropped because the next frame is handed other buffers."""
+    import torch
+
+    scene = synth.make_scene(N=30, seed=83)
+    T = 5
+    seq = synth.make_sequence(scene, T=T, seed=84)
+    inline = H.gpu_from(scene, scene.x0, scene.P0, prior=False)
+    for k in range(T):
+        inline.frame(seq.images[k][None], seq.u01[k][None])
+    xi, Pi = inline.download_state()
+    rows, cols = seq.images.shape[1:]
+    himg = torch.from_numpy(seq.images).pin_memory()
+    hu = torch.from_numpy(seq.u01).pin_memory()
+    nu = seq.u01.shape[1]
+
+    def args(k):
+        return (himg.data_ptr() + k * rows * cols, rows, cols, cols), (hu.data_ptr() + k * nu * 8, nu)
+
+    pf = H.gpu_from(scene, scene.x0, scene.P0, prior=False)
+    for k in range(T):
+        pf.frame(*args(k))  # frame 0 copies inline, frames 1.. consume the staged set
+        if k + 1 < T:
+            pf.prefetch(*args(k + 1))
+        if k == 2:
+            pf.prefetch(*args(0))  # staged, then overwritten by the right one: the last prefetch wins
+            pf.prefetch(*args(k + 1))
+    xp, Pp = pf.download_state()
+    assert np.array_equal(xi, xp) and np.array_equal(Pi, Pp)
+    # a staged set that does not match the next frame's buffers is dropped, not used
+    dr = H.gpu_from(scene, scene.x0, scene.P0, prior=False)
+    for k in range(T):
+        dr.prefetch(*args((k + 2) % T))
+        dr.frame(*args(k))
+    xd, Pd = dr.download_state()
+    assert np.array_equal(xi, xd) and np.array_equal(Pi, Pd)
+    # arguments that cannot be staged
+    du = torch.zeros(nu, dtype=torch.float64, device="cuda")
+    with pytest.raises(Exception):
+        pf.prefetch(args(0)[0], (du.data_ptr(), nu))  # device-resident inputs need no staging
+
+
 @pytest.mark.parametrize("q1", [True, False])
 def test_support_sweep_against_numpy(q1):
     scene, x, P = synth.random_spd_state(40, seed=91)
