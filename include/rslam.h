@@ -142,7 +142,7 @@ int rslam_update_hi(rslam_filter* f);
  * images: batch images (or one shared, see rslam_set_image) host or device, may be NULL to keep the current one. */
 int rslam_frame(rslam_filter* f, const uint8_t* images, int rows, int cols, int stride, int share, const double* u01, int n_u01,
                 int flags);
-/* Input prefetch for streaming callers (not in the reference, whose images arrive through a ROS callback, src/System.cpp:72-101):
+/* Input prefetch for streaming callers (not in the reference, whose loop reads an image file and calls TrackRunning on it, examples/Monocular/mono_slam.cpp:47-69):
  * copies the NEXT frame's HOST inputs (same arguments as rslam_frame; pinned memory for a truly asynchronous copy) into a second
  * staging set on the handle's copy stream and returns at once, so the transfer runs beside the frame that is still computing.  The
  * next rslam_frame that is handed the same host pointers and geometry uses the staged set instead of copying; any other call
