@@ -91,6 +91,8 @@ struct rslam_filter {
     // CUDA-graph replay of the per-frame launch sequence
     bool graph_enabled = true;
     bool capturing = false;
+    bool li_conditional = true;  // RSLAM_LI_CONDITIONAL=0 keeps the low-innovation update's launches unconditional in the graph
+    long long cond_nodes = 0;    // launches inside the IF node (not counted as launches: they run only when armed)
     // side stream for work that is independent of the critical path of a single small filter (W = P H^T beside S + Cholesky)
     bool jnorm_pending = false;  // rslam_frame only: the li update's k_upd_jnorm was deferred into the next rescue launch
     bool hi_gathered = false;  // the last rslam_rescue_hi also built the hi inlier list (single-CTA grids)
@@ -318,7 +320,7 @@ int run_update(rslam_filter* f, int which, bool gathered = false, bool defer_jno
     return check_launch();
 }
 
-int run_ransac_core(rslam_filter* f, bool select, bool gather_li = false) {
+int run_ransac_core(rslam_filter* f, bool select, bool gather_li = false, unsigned long long cond = 0ull) {
     const int B = f->B, N = f->hN;
     if (N == 0) return 0;
     const int q1 = (int)((f->par.quirks & RSLAM_Q1_ANGLES_FROM_POSITIONS) != 0);
@@ -331,7 +333,7 @@ int run_ransac_core(rslam_filter* f, bool select, bool gather_li = false) {
     if (select) {
         LAUNCH(f, k_ransac_support, dim3(cdiv(N, SJT), cdiv(N, SHB), B), SUP_THREADS, kSupSmemBytes, f->dF, f->camd, f->pard, (const int*)nullptr, 0, N, 0, N, (const int*)nullptr,
                (int*)nullptr, (unsigned long long*)nullptr);
-        LAUNCH(f, k_ransac_select, dim3(1, B), 256, 0, f->dF, f->pard, gather_li ? 1 : 0);
+        LAUNCH(f, k_ransac_select, dim3(1, B), 256, 0, f->dF, f->pard, gather_li ? 1 : 0, cond);
     }
     return check_launch();
 }
@@ -376,6 +378,7 @@ int rslam_create(const rslam_camera* cam, const rslam_params* par, int max_featu
     f->lds = round_up(f->kmax, 16);
     f->mwords = cdiv(max_features, 32);
     if (const char* e = getenv("RSLAM_TRSM_OB")) f->trsm_ob = atoi(e);
+    if (const char* e = getenv("RSLAM_LI_CONDITIONAL")) f->li_conditional = atoi(e) != 0;
     f->cam = *cam;
     if (par)
         f->par = *par;
@@ -956,10 +959,50 @@ static int run_frame_stages(rslam_filter* f, int flags) {
     }
     if ((rc = rslam_search_ic_matches(f))) return rc;
     if ((rc = ensure_update_ws(f))) return rc;
-    if ((rc = run_ransac_core(f, true, true))) return rc;
+    // Low-innovation update as an IF node of the frame graph: with no low-innovation inlier in any filter (the usual outcome with quirk Q1)
+    // every one of its launches exits at once, but the grids are sized for the map, not for the inlier count -- 0.27 ms per empty
+    // launch of the 4096-filter batch, ~100 empty launches at N = 2000.  k_ransac_select arms the node when any filter has inliers.
+    // Not for one small filter: there the node costs more than the six launches it skips.
+    const bool li_cond = f->capturing && f->li_conditional && ((f->B > 1 && (long long)f->B * f->hN >= 4096) || 2 * f->hN > kCholSmallMaxK);
+    cudaGraph_t cap_graph = nullptr;
+    cudaGraphConditionalHandle cond = 0;
+    cudaStreamCaptureStatus cap_status;
+    if (li_cond) {
+        CK(cudaStreamGetCaptureInfo_v2(f->stream, &cap_status, nullptr, &cap_graph, nullptr, nullptr));
+        CK(cudaGraphConditionalHandleCreate(&cond, cap_graph, 0, cudaGraphCondAssignDefault));
+    }
+    if ((rc = run_ransac_core(f, true, true, (unsigned long long)cond))) return rc;
     // single-CTA rescue kernel: the li update's closing quaternion normalisation rides at its head (one dependent launch less)
     const bool defer = cdiv(f->hN, 128) == 1 && f->hN > 0;
-    if ((rc = run_update(f, 0, true, defer))) return rc;
+    if (li_cond) {
+        const cudaGraphNode_t* deps = nullptr;
+        size_t ndeps = 0;
+        CK(cudaStreamGetCaptureInfo_v2(f->stream, &cap_status, nullptr, &cap_graph, &deps, &ndeps));
+        cudaGraphNodeParams np = {cudaGraphNodeTypeConditional};
+        np.type = cudaGraphNodeTypeConditional;
+        np.conditional.handle = cond;
+        np.conditional.type = cudaGraphCondTypeIf;
+        np.conditional.size = 1;
+        cudaGraphNode_t node = nullptr;
+        CK(cudaGraphAddNode(&node, cap_graph, deps, ndeps, &np));
+        cudaGraph_t body = np.conditional.phGraph_out[0];
+        CK(cudaStreamUpdateCaptureDependencies(f->stream, &node, 1, cudaStreamSetCaptureDependencies));
+        // the update's launches go to the body graph: capture them on the side stream, standing in for the handle's stream
+        CK(cudaStreamBeginCaptureToGraph(f->side, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+        cudaStream_t main_stream = f->stream;
+        f->stream = f->side;
+        const long long before = f->launches;
+        rc = run_update(f, 0, true, defer);
+        f->cond_nodes = f->launches - before;
+        f->stream = main_stream;
+        cudaGraph_t body_out = nullptr;
+        cudaError_t e = cudaStreamEndCapture(f->side, &body_out);
+        if (rc) return rc;
+        if (e != cudaSuccess) return fail(RSLAM_ERR_CUDA, "capture of the conditional update failed: %s", cudaGetErrorString(e));
+    } else {
+        f->cond_nodes = 0;
+        if ((rc = run_update(f, 0, true, defer))) return rc;
+    }
     f->jnorm_pending = defer;
     if ((rc = rslam_rescue_hi(f))) return rc;
     const bool gathered = f->hi_gathered;
@@ -1085,7 +1128,7 @@ int rslam_frame(rslam_filter* f, const uint8_t* images, int rows, int cols, int 
             return rc;
         }
         if (e != cudaSuccess) return fail(RSLAM_ERR_CUDA, "stream capture failed: %s", cudaGetErrorString(e));
-        f->graph_nodes = f->launches - before;
+        f->graph_nodes = f->launches - before - f->cond_nodes;
         f->launches = before;
         CK(cudaGraphInstantiate(&f->graph_exec, graph, 0));
         cudaGraphDestroy(graph);

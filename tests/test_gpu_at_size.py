@@ -19,6 +19,7 @@ import pytest
 from oracle import np_oracle as NP
 from ransac_slam_b200 import synth, sweep
 from tests import c3_case as C3
+from oracle import oracle_py as O
 from tests import helpers as H
 
 pytestmark = pytest.mark.gpu
@@ -230,3 +231,88 @@ def test_c5_64_heterogeneous_filters_vs_singles_and_oracle():
         H.assert_x_close(xb, xo, what=f"filter {b} x")
         H.assert_P_close(Pb, Po, what=f"filter {b} P")
     bat.close()
+
+
+def _with_env(name, value, fn):
+    old = os.environ.get(name)
+    os.environ[name] = value
+    try:
+        return fn()
+    finally:
+        if old is None:
+            del os.environ[name]
+        else:
+            os.environ[name] = old
+
+
+@pytest.mark.parametrize("quirks", [0x7, 0x6])
+def test_li_update_if_node_batch(quirks):
+    """rslam_frame's graph holds the low-innovation update in an IF node for large batches.  Armed by ONE filter of 48 (the others see
+    a blank image: no matches), or by none (quirk Q1 on: no hypothesis gathers support): bitwise the same as unconditional launches."""
+    from ransac_slam_b200 import capi
+
+    B, T, special = 48, 2, 7
+    scenes = [synth.make_scene(N=100, seed=5100 + b) for b in range(B)]
+    seqs = [synth.make_sequence(scenes[b], T=T, seed=5200 + b, u01_seed=60 + b) for b in range(B)]
+    cam9 = scenes[0].cam.as9()
+
+    def run():
+        bat = capi.Filter(cam9, 100, batch=B, quirks=quirks)
+        for b in range(B):
+            bat.upload_state(scenes[b].x0, scenes[b].P0, b=b)
+            bat.upload_patches(scenes[b].templates.astype(np.float64), b=b)
+        for k in range(T):
+            imgs = np.stack([seqs[b].images[k] if b == special else np.zeros_like(seqs[b].images[k]) for b in range(B)])
+            bat.frame(imgs, np.stack([seqs[b].u01[k] for b in range(B)]))
+        out = [bat.download_state(b=b) for b in (special, 3)], [bat.features(b) for b in (special, 3)]
+        bat.close()
+        return out
+
+    (s_on, f_on) = _with_env("RSLAM_LI_CONDITIONAL", "1", run)
+    (s_off, f_off) = _with_env("RSLAM_LI_CONDITIONAL", "0", run)
+    for (xa, Pa), (xb, Pb) in zip(s_on, s_off):
+        assert np.array_equal(xa, xb) and np.array_equal(Pa, Pb)
+    for fa, fb in zip(f_on, f_off):
+        for key in ("ic", "li", "hi"):
+            assert (fa[key] == fb[key]).all()
+    assert f_on[1]["ic"].sum() == 0  # blank image: nothing matched
+    assert f_on[0]["ic"].sum() > 50
+    # li flags are reset at the start of the next frame's search; what the armed node did shows in the state: with Q1 off the special
+    # filter's li update ran (its result is compared bitwise above), and the oracle agrees
+    o = H.oracle_from(scenes[special], scenes[special].x0, scenes[special].P0, prior=False, fast_corr=True, quirks=quirks | O.Q11)
+    for k in range(T):
+        o.frame(seqs[special].images[k], seqs[special].u01[k])
+    xo, Po = o.get_state()
+    H.assert_x_close(s_on[0][0], xo, what="special filter x")
+    H.assert_P_close(s_on[0][1], Po, what="special filter P")
+    if quirks == 0x6:
+        assert o.features()["li"].sum() > 0, "this case must arm the node"
+
+
+@pytest.mark.parametrize("quirks", [0x7, 0x6])
+def test_li_update_if_node_large_map(quirks):
+    """The same at N = 2000 (one filter, large-k path: ~100 launches inside the node): frame() with and without the IF node, bitwise."""
+    from ransac_slam_b200 import capi
+
+    cam, scene, seq, P0 = _c3_inputs()
+
+    def run():
+        f = capi.Filter(cam.as9(), C3.N, quirks=quirks, std_a=0.007 * C3.STD_SCALE, std_alpha=0.007 * C3.STD_SCALE)
+        f.upload_state(scene.x0, P0)
+        f.upload_patches(scene.templates.astype(np.float64))
+        f.frame(seq.images[0][None], seq.u01[0][None])
+        x, P = f.download_state()
+        ft = f.features()
+        s = C3.summarize(x, P)
+        f.close()
+        return x, s, ft
+
+    xa, sa, fa = _with_env("RSLAM_LI_CONDITIONAL", "1", run)
+    xb, sb, fb = _with_env("RSLAM_LI_CONDITIONAL", "0", run)
+    assert np.array_equal(xa, xb)
+    for k in sa:
+        assert np.array_equal(np.asarray(sa[k]), np.asarray(sb[k])), k
+    for key in ("ic", "li", "hi"):
+        assert (fa[key] == fb[key]).all()
+    if quirks == 0x6:
+        assert fa["li"].sum() > 800
