@@ -1331,7 +1331,10 @@ __global__ void __launch_bounds__(SR_THREADS, 1) k_syrk_rows(DevFilter* Fs, int 
     const int wm0 = (gw & 1) * 32, wn0 = (gw >> 1) * 32;  // warp grid 2 x 2 inside the group, warp tile 32 x 32
     const int m0 = ti * SR_BM;
     const int nkt = (kk + SR_BK - 1) / SR_BK;
-    const int ntile = (tj1 - tj0 - grp + 1) / 2;  // this group's tiles: tj0 + grp, tj0 + grp + 2, ...
+    // the segment's tiles are dealt alternately to the two groups; an odd last tile is SPLIT between them by columns (group g takes columns
+    // 32 g .. 32 g + 31 with 32 x 16 warp tiles) instead of leaving one group idle for a whole tile
+    const int nfull = (tj1 - tj0) >> 1, ntile = nfull + ((tj1 - tj0) & 1);
+    auto tile_col = [&](int tile) { return tile < nfull ? tj0 + grp + 2 * tile : tj1 - 1; };
     const int total = ntile * nkt;
     const double* x0 = which ? F.x_kk : F.x_km1;
 
@@ -1344,7 +1347,7 @@ __global__ void __launch_bounds__(SR_THREADS, 1) k_syrk_rows(DevFilter* Fs, int 
     }
     auto load_B = [&](int q) {
         const int tile = q / nkt, kt = q - tile * nkt;
-        const int n0 = (tj0 + grp + 2 * tile) * SR_BM, k0 = kt * SR_BK;
+        const int n0 = tile_col(tile) * SR_BM, k0 = kt * SR_BK;
         double* bs = Bs + (q % SR_STAGES) * SR_BK * SR_LD;
 #pragma unroll
         for (int it = 0; it < SR_BK * (SR_BM / 2) / 128; it++) {
@@ -1366,7 +1369,10 @@ __global__ void __launch_bounds__(SR_THREADS, 1) k_syrk_rows(DevFilter* Fs, int 
     double acc[4][4][2], cpre[4][4][2];
     for (int q = 0; q < total; q++) {
         const int tile = q / nkt, kt = q - tile * nkt;
-        const int n0 = (tj0 + grp + 2 * tile) * SR_BM;
+        const int n0 = tile_col(tile) * SR_BM;
+        const bool half = tile >= nfull;
+        const int wn = half ? grp * 32 + (gw >> 1) * 16 : wn0;  // first column of this warp's block inside the tile
+        const int ntl = half ? 2 : 4;                          // m8n8 tiles across
         if (kt == 0) {
 #pragma unroll
             for (int a = 0; a < 4; a++)
@@ -1376,8 +1382,8 @@ __global__ void __launch_bounds__(SR_THREADS, 1) k_syrk_rows(DevFilter* Fs, int 
                     const int row = m0 + wm0 + a * 8 + (lane >> 2);
 #pragma unroll
                     for (int e = 0; e < 2; e++) {
-                        const int cc = n0 + wn0 + b * 8 + 2 * (lane & 3) + e;
-                        cpre[a][b][e] = (row < n && cc <= row) ? P[row + (size_t)cc * ldp] : 0.0;
+                        const int cc = n0 + wn + b * 8 + 2 * (lane & 3) + e;
+                        cpre[a][b][e] = (b < ntl && row < n && cc <= row) ? P[row + (size_t)cc * ldp] : 0.0;
                     }
                 }
         }
@@ -1396,8 +1402,8 @@ __global__ void __launch_bounds__(SR_THREADS, 1) k_syrk_rows(DevFilter* Fs, int 
         // produces entries that are never stored: it keeps the pipeline protocol (loads, barriers) and skips the arithmetic, which leaves
         // its scheduler's tensor pipe to the other warp group.  (Predicating single m8 tiles inside the unrolled DMMA stream was tried
         // and LOST 6 %: the predicate breaks the back-to-back issue of the 16 DMMAs.)
-        const bool dead = (n0 == m0 && wn0 > wm0) || (m0 + wm0 >= M);
-        if (!dead) {
+        const bool dead = (n0 == m0 && wn > wm0 + 31) || (m0 + wm0 >= M);
+        if (!dead && !half) {
 #pragma unroll
             for (int ks = 0; ks < SR_BK / 4; ks++) {
                 const int krow = ks * 4 + (lane & 3);
@@ -1411,6 +1417,20 @@ __global__ void __launch_bounds__(SR_THREADS, 1) k_syrk_rows(DevFilter* Fs, int 
 #pragma unroll
                     for (int nt = 0; nt < 4; nt++) dmma8x8x4(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
             }
+        } else if (!dead) {
+#pragma unroll
+            for (int ks = 0; ks < SR_BK / 4; ks++) {
+                const int krow = ks * 4 + (lane & 3);
+                double af[4], bf[2];
+#pragma unroll
+                for (int mt = 0; mt < 4; mt++) af[mt] = as[krow * SR_LD + wm0 + mt * 8 + (lane >> 2)];
+#pragma unroll
+                for (int nt = 0; nt < 2; nt++) bf[nt] = bs[krow * SR_LD + wn + nt * 8 + (lane >> 2)];
+#pragma unroll
+                for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+                    for (int nt = 0; nt < 2; nt++) dmma8x8x4(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+            }
         }
         if (kt == nkt - 1) {  // epilogue of this tile: P -= acc (lower part, mirrored), row n -> state correction
 #pragma unroll
@@ -1421,8 +1441,8 @@ __global__ void __launch_bounds__(SR_THREADS, 1) k_syrk_rows(DevFilter* Fs, int 
                 for (int nt = 0; nt < 4; nt++)
 #pragma unroll
                     for (int e = 0; e < 2; e++) {
-                        const int cc = n0 + wn0 + nt * 8 + 2 * (lane & 3) + e;
-                        if (cc > row || cc >= n) continue;
+                        const int cc = n0 + wn + nt * 8 + 2 * (lane & 3) + e;
+                        if (nt >= ntl || cc > row || cc >= n) continue;
                         if (row == n) {
                             F.x_kk[cc] = x0[cc] + acc[mt][nt][e];
                             continue;
