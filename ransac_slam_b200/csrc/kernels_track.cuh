@@ -1323,8 +1323,8 @@ __device__ __forceinline__ void gather_inliers(DevFilter& F, int which, int* s_s
 //     then write-back of the winner's low_innovation_inlier flags.  One CTA per filter; warp 0 walks the draws 32 at a time:
 //     a chunk without a new record (support > best so far) only has to be checked against the current budget n_hyp, so the
 //     scalar loop body runs only for the (rare) record-setting hypotheses.
-// cond != 0 (rslam_frame's graph, large batches / large maps): the low-innovation update that follows sits in an IF node of the graph;
-// any filter that has low-innovation inliers arms it, otherwise its ~100 launches (every CTA of which would exit at once) are skipped
+// cond != 0 (rslam_frame's graph, large batches): the low-innovation update that follows sits in an IF node of the graph;
+// any filter that has low-innovation inliers arms it, otherwise its launches (every CTA of which would exit at once) are skipped
 __global__ void __launch_bounds__(256) k_ransac_select(DevFilter* Fs, ParDev par, int gather_li, unsigned long long cond) {
     DevFilter& F = Fs[blockIdx.y];
     __shared__ int s_state[8];  // 1 max, 2 n_hyp, 3 winner i, 5 hyp_run, 6 status

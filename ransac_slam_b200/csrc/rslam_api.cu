@@ -959,11 +959,12 @@ static int run_frame_stages(rslam_filter* f, int flags) {
     }
     if ((rc = rslam_search_ic_matches(f))) return rc;
     if ((rc = ensure_update_ws(f))) return rc;
-    // Low-innovation update as an IF node of the frame graph: with no low-innovation inlier in any filter (the usual outcome with quirk Q1)
-    // every one of its launches exits at once, but the grids are sized for the map, not for the inlier count -- 0.27 ms per empty
-    // launch of the 4096-filter batch, ~100 empty launches at N = 2000.  k_ransac_select arms the node when any filter has inliers.
-    // Not for one small filter: there the node costs more than the six launches it skips.
-    const bool li_cond = f->capturing && f->li_conditional && ((f->B > 1 && (long long)f->B * f->hN >= 4096) || 2 * f->hN > kCholSmallMaxK);
+    // Low-innovation update as an IF node of the frame graph, for large batches: with no low-innovation inlier in any filter (the usual
+    // outcome with quirk Q1) every one of its launches exits at once, but the grids are sized for the maps, not for the inlier counts --
+    // 0.27 ms per empty launch of the 4096-filter batch.  k_ransac_select arms the node when any filter has inliers.  Not for a single
+    // filter: one small filter pays more for the node than for the six launches it skips, and at N = 2000 the ~90 empty launches cost
+    // 0.03 ms of 25 -- and ncu cannot profile the kernel nodes of a graph that holds a conditional node.
+    const bool li_cond = f->capturing && f->li_conditional && f->B > 1 && (long long)f->B * f->hN >= 4096;
     cudaGraph_t cap_graph = nullptr;
     cudaGraphConditionalHandle cond = 0;
     cudaStreamCaptureStatus cap_status;

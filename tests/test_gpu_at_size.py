@@ -287,32 +287,3 @@ def test_li_update_if_node_batch(quirks):
     H.assert_P_close(s_on[0][1], Po, what="special filter P")
     if quirks == 0x6:
         assert o.features()["li"].sum() > 0, "this case must arm the node"
-
-
-@pytest.mark.parametrize("quirks", [0x7, 0x6])
-def test_li_update_if_node_large_map(quirks):
-    """The same at N = 2000 (one filter, large-k path: ~100 launches inside the node): frame() with and without the IF node, bitwise."""
-    from ransac_slam_b200 import capi
-
-    cam, scene, seq, P0 = _c3_inputs()
-
-    def run():
-        f = capi.Filter(cam.as9(), C3.N, quirks=quirks, std_a=0.007 * C3.STD_SCALE, std_alpha=0.007 * C3.STD_SCALE)
-        f.upload_state(scene.x0, P0)
-        f.upload_patches(scene.templates.astype(np.float64))
-        f.frame(seq.images[0][None], seq.u01[0][None])
-        x, P = f.download_state()
-        ft = f.features()
-        s = C3.summarize(x, P)
-        f.close()
-        return x, s, ft
-
-    xa, sa, fa = _with_env("RSLAM_LI_CONDITIONAL", "1", run)
-    xb, sb, fb = _with_env("RSLAM_LI_CONDITIONAL", "0", run)
-    assert np.array_equal(xa, xb)
-    for k in sa:
-        assert np.array_equal(np.asarray(sa[k]), np.asarray(sb[k])), k
-    for key in ("ic", "li", "hi"):
-        assert (fa[key] == fb[key]).all()
-    if quirks == 0x6:
-        assert fa["li"].sum() > 800
