@@ -675,12 +675,23 @@ __global__ void __launch_bounds__(256) k_chol_trinv(DevFilter* Fs) {
 
 // ---- U4s: whole Cholesky (+ inverses of the diagonal blocks) in ONE CTA for small systems (k <= 256): the launch-latency
 //           path of the 100-feature configuration.
-__global__ void __launch_bounds__(256) k_chol_small(DevFilter* Fs) {
+// LD: panel row capacity (k-major leading dimension, == 4 mod 16); MINB: CTAs per SM asked of the compiler.  <kTld, 1> serves any k <= 256;
+// <212, 2> (k <= 200: the 100-feature filters) fits two CTAs per SM -- 109 KB of shared memory each, no scratch for the inverse (that is
+// k_chol_trinv's) -- so that one filter's serial column chain runs beside another's.
+constexpr int kCholSmallLd2 = 212;
+constexpr int kCholSmall2SmemBytes = (kNB * kCholSmallLd2 + kNB) * (int)sizeof(double);
+template <int LD, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_chol_small(DevFilter* Fs) {
     DevFilter& F = Fs[blockIdx.y];
     const int kk = F.ctl[CTL_K];
     if (kk <= 0) return;
     extern __shared__ __align__(16) double psm[];
-    const PanelSmem ps = panel_carve(psm);
+    PanelSmem ps = panel_carve<LD>(psm);
+    if (LD != kTld) {  // compact carve-up: panel + reciprocal diagonal only
+        ps.sRd = psm + kNB * LD;
+        ps.sX = nullptr;
+        ps.sW = nullptr;
+    }
     double* S = F.Sm;
     const int ld = F.lds;
 #ifdef RSLAM_PHASE_CLOCKS
@@ -693,10 +704,10 @@ __global__ void __launch_bounds__(256) k_chol_small(DevFilter* Fs) {
     for (int j0 = 0; j0 < kk; j0 += kNB) {
         const int w = min(kNB, kk - j0);
         const int rem = max(0, kk - (j0 + kNB));
-        panel_load(ps, S, ld, j0, w, j0 + kNB, rem);
+        panel_load<LD>(ps, S, ld, j0, w, j0 + kNB, rem);
         __syncthreads();
         PH(0);
-        smem_panel_factor(ps, kNB + rem, w);
+        smem_panel_factor<LD>(ps, kNB + rem, w);
         PH(1);
         // store the panel and run the trailing update on DMMA tiles (the inverses of the diagonal blocks, which the TRSM kernel
         // multiplies by, are built afterwards by k_chol_trinv for all blocks at once: ~10 k cycles less on this serial chain per panel)
@@ -705,7 +716,7 @@ __global__ void __launch_bounds__(256) k_chol_small(DevFilter* Fs) {
                 const int ln = threadIdx.x & 31, wp = threadIdx.x >> 5;
                 for (int c = wp; c < w; c += 8) {  // warp per column, lanes down the rows: coalesced, no divisions
                     double* col = S + (size_t)(j0 + c) * ld + j0;
-                    const double* src = ps.sT + c * kTld;
+                    const double* src = ps.sT + c * LD;
                     for (int i = ln; i < w; i += 32) col[i] = src[i];
                     for (int i = ln; i < rem; i += 32) col[kNB + i] = src[kNB + i];
                 }
@@ -723,7 +734,7 @@ __global__ void __launch_bounds__(256) k_chol_small(DevFilter* Fs) {
                     for (int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
 #pragma unroll 4
                 for (int ks = 0; ks < kNB / 4; ks++) {
-                    const double* kr = ps.sT + (ks * 4 + (lane & 3)) * kTld + kNB;
+                    const double* kr = ps.sT + (ks * 4 + (lane & 3)) * LD + kNB;
                     double af[2], bf[4];
 #pragma unroll
                     for (int a = 0; a < 2; a++) af[a] = kr[mt * 16 + a * 8 + (lane >> 2)];

@@ -85,6 +85,7 @@ struct rslam_filter {
     bool have_image = false;
     bool warp_patches = false;  // run pred_patch_fc on the device before the search
     bool upd_ws = false;
+    bool chol2 = true;  // batches of small filters: k_chol_small with two CTAs per SM (RSLAM_CHOL2=0: one)
     int trsm_ob = 16;  // outer-block width of the large-k TRSM in 64-column blocks (0: one left-looking launch); RSLAM_TRSM_OB overrides
     int hN = 0, hn = 0;  // max over filters of the uploaded N / n
     bool descr_dirty = false;
@@ -252,13 +253,17 @@ int run_update(rslam_filter* f, int which, bool gathered = false, bool defer_jno
         LAUNCH_ON(f, ws, "k_upd_W", k_upd_W, dim3(cdiv(n, 256), cdiv(N, kWChunk), B), 256, 0, f->dF);
         if (fork) CK(cudaEventRecord(f->ev_join, f->side));
         LAUNCH_N(f, "k_upd_S", k_upd_S_direct, dim3(cdiv(N * (N + 1) / 2, 8), 1, B), 256, 0, f->dF);
-        LAUNCH(f, k_chol_small, dim3(1, B), 256, kCholSmallSmemBytes, f->dF);
+        LAUNCH_N(f, "k_chol_small", (k_chol_small<kTld, 1>), dim3(1, B), 256, kCholSmallSmemBytes, f->dF);
         LAUNCH(f, k_chol_trinv, dim3(nsteps, B), 256, kTrinvSmemBytes, f->dF);
         if (fork) CK(cudaStreamWaitEvent(f->stream, f->ev_join, 0));
     } else if (kmax <= kCholSmallMaxK) {
         LAUNCH(f, k_upd_W, dim3(cdiv(n, 256), cdiv(N, kWChunk), B), 256, 0, f->dF);
         LAUNCH(f, k_upd_S, dim3(cdiv(N, 16), cdiv(N, 16), B), 256, 0, f->dF);
-        LAUNCH(f, k_chol_small, dim3(1, B), 256, kCholSmallSmemBytes, f->dF);
+        if (f->chol2 && kmax + kNB <= kCholSmallLd2 + kNB && kmax <= 200 && B >= 2 * 148) {  // two CTAs per SM
+            LAUNCH_N(f, "k_chol_small", (k_chol_small<kCholSmallLd2, 2>), dim3(1, B), 256, kCholSmall2SmemBytes, f->dF);
+        } else {
+            LAUNCH_N(f, "k_chol_small", (k_chol_small<kTld, 1>), dim3(1, B), 256, kCholSmallSmemBytes, f->dF);
+        }
         LAUNCH(f, k_chol_trinv, dim3(nsteps, B), 256, kTrinvSmemBytes, f->dF);
     } else {
         LAUNCH(f, k_upd_W, dim3(cdiv(n, 256), cdiv(N, kWChunk), B), 256, 0, f->dF);
@@ -378,6 +383,7 @@ int rslam_create(const rslam_camera* cam, const rslam_params* par, int max_featu
     f->lds = round_up(f->kmax, 16);
     f->mwords = cdiv(max_features, 32);
     if (const char* e = getenv("RSLAM_TRSM_OB")) f->trsm_ob = atoi(e);
+    if (const char* e = getenv("RSLAM_CHOL2")) f->chol2 = atoi(e) != 0;
     if (const char* e = getenv("RSLAM_LI_CONDITIONAL")) f->li_conditional = atoi(e) != 0;
     f->cam = *cam;
     if (par)
@@ -411,7 +417,8 @@ int rslam_create(const rslam_camera* cam, const rslam_params* par, int max_featu
     CKF(cudaFuncSetAttribute(k_ransac_support, cudaFuncAttributeMaxDynamicSharedMemorySize, kSupSmemBytes));
     CKF(cudaFuncSetAttribute(k_chol_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPanelSmemBytes));
     CKF(cudaFuncSetAttribute(k_chol_trinv, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrinvSmemBytes));
-    CKF(cudaFuncSetAttribute(k_chol_small, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholSmallSmemBytes));
+    CKF(cudaFuncSetAttribute(k_chol_small<kTld, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholSmallSmemBytes));
+    CKF(cudaFuncSetAttribute(k_chol_small<kCholSmallLd2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholSmall2SmemBytes));
     CKF(cudaFuncSetAttribute(k_trsm_small, cudaFuncAttributeMaxDynamicSharedMemorySize, trsm_small_smem_bytes(SR_KMAX)));
     CKF(cudaFuncSetAttribute(k_syrk_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, syrk_rows_smem_bytes(SR_KMAX)));
 

@@ -287,3 +287,44 @@ def test_li_update_if_node_batch(quirks):
     H.assert_P_close(s_on[0][1], Po, what="special filter P")
     if quirks == 0x6:
         assert o.features()["li"].sum() > 0, "this case must arm the node"
+
+
+def test_batch_of_300_small_filters_two_cholesky_ctas_per_sm():
+    """Batches of >= 296 filters with k <= 200 factorise S with the compact k_chol_small (two CTAs per SM, panel rows capped at 212):
+    members must equal the same filters stepped in a batch of two (the one-CTA-per-SM kernel) bit for bit, and the oracle to 1e-9."""
+    from ransac_slam_b200 import capi
+
+    B, T, NS = 300, 2, 6
+    scenes = [synth.make_scene(N=30 + 10 * s, seed=6100 + s) for s in range(NS)]  # 30 .. 80 features: one to three panels
+    seqs = [synth.make_sequence(scenes[s], T=T, seed=6200 + s, u01_seed=70 + s) for s in range(NS)]
+    cam9 = scenes[0].cam.as9()
+    bat = capi.Filter(cam9, 100, batch=B)
+    for b in range(B):
+        s = b % NS
+        bat.upload_state(scenes[s].x0, scenes[s].P0, b=b)
+        bat.upload_patches(scenes[s].templates.astype(np.float64), b=b)
+    for k in range(T):
+        bat.frame(np.stack([seqs[b % NS].images[k] for b in range(B)]), np.stack([seqs[b % NS].u01[k] for b in range(B)]))
+    n_hi = 0
+    for s in range(NS):
+        one = capi.Filter(cam9, 100, batch=2)
+        for bb in range(2):
+            one.upload_state(scenes[s].x0, scenes[s].P0, b=bb)
+            one.upload_patches(scenes[s].templates.astype(np.float64), b=bb)
+        for k in range(T):
+            one.frame(np.repeat(seqs[s].images[k][None], 2, 0), np.repeat(seqs[s].u01[k][None], 2, 0))
+        xo, Po = one.download_state(b=0)
+        for b in (s, s + NS * 17, s + NS * 49):
+            xb, Pb = bat.download_state(b=b)
+            assert np.array_equal(xb, xo) and np.array_equal(Pb, Po), (s, b)
+        n_hi += int(one.features(0)["hi"].sum())
+        one.close()
+    assert n_hi > 20 * NS
+    o = H.oracle_from(scenes[5], scenes[5].x0, scenes[5].P0, prior=False, fast_corr=True)
+    for k in range(T):
+        o.frame(seqs[5].images[k], seqs[5].u01[k])
+    xo, Po = o.get_state()
+    xb, Pb = bat.download_state(b=5)
+    H.assert_x_close(xb, xo, what="member 5 x")
+    H.assert_P_close(Pb, Po, what="member 5 P")
+    bat.close()
