@@ -640,7 +640,7 @@ __global__ void __launch_bounds__(192) k_pred_patch(DevFilter* Fs, CamDev cam) {
     DevFilter& F = Fs[blockIdx.y];
     const int i = blockIdx.x;
     if (i >= F.N || !F.has_h[i] || F.patch_init == nullptr) return;
-    __shared__ unsigned char sp[41 * 41 + 3];
+    __shared__ unsigned int spw[(41 * 41 + 3) / 4 + 2];
     const int tid = threadIdx.x;
     float* out = F.patch + (size_t)i * kPatchPix;
     const double* geo = F.pp_geom + (size_t)i * kPPGeom;
@@ -649,9 +649,17 @@ __global__ void __launch_bounds__(192) k_pred_patch(DevFilter* Fs, CamDev cam) {
         if (tid < kPatchPix) out[tid] = 0.f;
         return;
     }
-    {   // 41 x 41 bytes; every feature's block starts 1681 i bytes into the array: bytes up to the first 4-byte boundary, words, tail
+    // 41 x 41 bytes; a feature's block starts 1681 i bytes into the array, i.e. at any byte alignment: the aligned words that cover it are
+    // copied (three loads per thread instead of nine byte loads) and the patch is addressed at the same misalignment in shared memory
+    // (the array is allocated with 4 spare bytes)
+    const unsigned char* sp;
+    {
         const unsigned char* src = F.patch_init + (size_t)i * 1681;
-        for (int e = tid; e < 41 * 41; e += blockDim.x) sp[e] = src[e];
+        const int mis = (int)((size_t)src & 3);
+        const unsigned int* wsrc = reinterpret_cast<const unsigned int*>(src - mis);
+        const int nwords = (mis + 41 * 41 + 3) >> 2;
+        for (int e = tid; e < nwords; e += blockDim.x) spw[e] = wsrc[e];
+        sp = reinterpret_cast<const unsigned char*>(spw) + mis;
     }
     const double* ip = F.init_pose + (size_t)i * 14;
     const double uvf0 = ip[12], uvf1 = ip[13];

@@ -443,7 +443,7 @@ int rslam_create(const rslam_camera* cam, const rslam_params* par, int max_featu
     A(P, psz) A(xkk, n) A(xkm1, n) A(h, 2 * N) A(Hc, 14 * N) A(Hf, 12 * N) A(S, 4 * N) A(z, 2 * N) A(hyp_ab, 16 * N) A(hyp_xcam, 7 * N) A(Jn, 32)
     A(ftype, N) A(foff, N) A(tp, N) A(tm, N) A(ic_list, N) A(id_list, N) A(id_pos, N) A(support, N) A(ctl, CTL_SIZE) A(upd_list, N) A(sup_rows, 6 * (size_t)round_up(N, 64))
     A(has_h, N) A(ic, N) A(li, N) A(hi, N) A(patch, (size_t)N * kPatchPix) A(masks, (size_t)N * f->mwords)
-    A(patch_init, (size_t)N * 1681) A(init_pose, (size_t)N * 14) A(pp_geom, (size_t)N * 12) A(last_id, N)
+    A(patch_init, (size_t)N * 1681 + 4) A(init_pose, (size_t)N * 14) A(pp_geom, (size_t)N * 12) A(last_id, N)
 #undef A
     if ((rc = dev_alloc(f, &f->dF, (size_t)B))) {
         rslam_destroy(f);
