@@ -947,7 +947,7 @@ __global__ void __launch_bounds__(WM * 64) k_trsm_ll(DevFilter* Fs, int jb0, int
 // configuration).  Here the CTA's 32 rows of W are loaded ONCE into shared memory and turned into V in place; the only streamed
 // operand is L (off-diagonal blocks, then the inverse of the diagonal block), through a 4-stage cp.async ring flattened over the
 // whole (column block, k-chunk) sequence, so every load is issued several chunks before it is needed.
-constexpr int TS_R = 32, TS_THREADS = 128, TS_LDA = TS_R + 4, TS_LDB = kNB + 4, TS_STAGES = 4, TS_BK = 16;
+constexpr int TS_R = 32, TS_THREADS = 128, TS_LDA = TS_R + 4, TS_LDB = kNB + 4, TS_STAGES = 2, TS_BK = 32, TS_CPB = kNB / TS_BK;  // chunks per 64-column block
 inline int trsm_small_smem_bytes(int kmax) { return (((kmax + kNB - 1) / kNB * kNB) * TS_LDA + TS_STAGES * TS_BK * TS_LDB) * (int)sizeof(double); }
 
 __global__ void __launch_bounds__(TS_THREADS, 2) k_trsm_small(DevFilter* Fs, int krows) {
@@ -966,7 +966,7 @@ __global__ void __launch_bounds__(TS_THREADS, 2) k_trsm_small(DevFilter* Fs, int
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm0 = (warp & 1) * 16, wn0 = (warp >> 1) * 32;  // warp grid 2 x 2, warp tile 16 x 32
     const int nb = (kk + kNB - 1) / kNB;
-    const int total = 2 * nb * (nb + 1);  // sum_j (4 j + 4) chunks
+    const int total = TS_CPB * nb * (nb + 1) / 2;  // sum_j (CPB j + CPB) chunks
 
     for (int ch = tid; ch < nb * kNB * (TS_R / 2); ch += TS_THREADS) {
         const int kc = ch / (TS_R / 2), r2 = ch % (TS_R / 2);
@@ -978,7 +978,7 @@ __global__ void __launch_bounds__(TS_THREADS, 2) k_trsm_small(DevFilter* Fs, int
     auto load_next = [&](int stage) {
         double* bs = Bs + stage * TS_BK * TS_LDB;
         const int c0 = lj * kNB;
-        if (lc < 4 * lj) {  // off-diagonal: Bs[k][col] = L[c0 + col, 16 lc + k]
+        if (lc < TS_CPB * lj) {  // off-diagonal: Bs[k][col] = L[c0 + col, 16 lc + k]
             const int k0 = lc * TS_BK;
 #pragma unroll
             for (int it = 0; it < TS_BK * (kNB / 2) / TS_THREADS; it++) {
@@ -989,7 +989,7 @@ __global__ void __launch_bounds__(TS_THREADS, 2) k_trsm_small(DevFilter* Fs, int
                 cp_async16(&bs[kc * TS_LDB + 2 * r2], v ? (Sm + row + (size_t)(k0 + kc) * lds) : Sm, v);
             }
         } else {  // diagonal: Bs[k][col] = inv(L_jj)[col, 16 d + k]
-            const int d = lc - 4 * lj;
+            const int d = lc - TS_CPB * lj;
             const double* Li = F.Linv + (size_t)lj * kNB * kNB + (size_t)d * TS_BK * kNB;
 #pragma unroll
             for (int it = 0; it < TS_BK * (kNB / 2) / TS_THREADS; it++) {
@@ -998,7 +998,7 @@ __global__ void __launch_bounds__(TS_THREADS, 2) k_trsm_small(DevFilter* Fs, int
                 cp_async16(&bs[kc * TS_LDB + 2 * r2], Li + 2 * r2 + (size_t)kc * kNB, true);
             }
         }
-        if (++lc == 4 * lj + 4) {
+        if (++lc == TS_CPB * lj + TS_CPB) {
             lc = 0;
             lj++;
         }
@@ -1012,7 +1012,7 @@ __global__ void __launch_bounds__(TS_THREADS, 2) k_trsm_small(DevFilter* Fs, int
     int j = 0, c = 0;
     for (int q = 0; q < total; q++) {
         const int c0 = j * kNB;
-        if (c == 0 || c == 4 * j) {
+        if (c == 0 || c == TS_CPB * j) {
 #pragma unroll
             for (int a = 0; a < 2; a++)
 #pragma unroll
@@ -1025,8 +1025,8 @@ __global__ void __launch_bounds__(TS_THREADS, 2) k_trsm_small(DevFilter* Fs, int
             if (nq < total) load_next(nq % TS_STAGES);
             cp_async_commit();
         }
-        const bool diag = c >= 4 * j;
-        const double* as = Vs + (diag ? (c0 + (c - 4 * j) * TS_BK) : c * TS_BK) * TS_LDA;
+        const bool diag = c >= TS_CPB * j;
+        const double* as = Vs + (diag ? (c0 + (c - TS_CPB * j) * TS_BK) : c * TS_BK) * TS_LDA;
         const double* bs = Bs + (q % TS_STAGES) * TS_BK * TS_LDB;
 #pragma unroll
         for (int ks = 0; ks < TS_BK / 4; ks++) {
@@ -1041,7 +1041,7 @@ __global__ void __launch_bounds__(TS_THREADS, 2) k_trsm_small(DevFilter* Fs, int
 #pragma unroll
                 for (int nt = 0; nt < 4; nt++) dmma8x8x4(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
         }
-        if (!diag && c == 4 * j - 1) {
+        if (!diag && c == TS_CPB * j - 1) {
             // T = W_j - acc, in place (each thread touches only its own elements; the accumulation never reads rows >= c0)
 #pragma unroll
             for (int mt = 0; mt < 2; mt++)
@@ -1052,7 +1052,7 @@ __global__ void __launch_bounds__(TS_THREADS, 2) k_trsm_small(DevFilter* Fs, int
                         const int rl = wm0 + mt * 8 + (lane >> 2), cl = wn0 + nt * 8 + 2 * (lane & 3) + e;
                         Vs[(c0 + cl) * TS_LDA + rl] -= acc[mt][nt][e];
                     }
-        } else if (diag && c == 4 * j + 3) {
+        } else if (diag && c == TS_CPB * j + TS_CPB - 1) {
             // V_j = T inv(L_jj)^T : everybody must be done reading T before it is overwritten
             __syncthreads();
             const int w = min(kNB, kk - c0);
@@ -1070,7 +1070,7 @@ __global__ void __launch_bounds__(TS_THREADS, 2) k_trsm_small(DevFilter* Fs, int
                     }
             }
         }
-        if (++c == 4 * j + 4) {
+        if (++c == TS_CPB * j + TS_CPB) {
             c = 0;
             j++;
         }
