@@ -1310,9 +1310,9 @@ __global__ void __launch_bounds__(GemmCfg<BM, BN>::kThreads, GemmCfg<BM, BN>::kM
 // seg_len = 1 gives one CTA per tile (single filter: maximum parallelism, minimum latency); seg_len = tiles-per-row gives one CTA
 // per tile row (large batches: minimum traffic).  Same row-n convention as k_gemm_dmma: row n of V V^T is the state correction.
 #ifndef RSLAM_SR_STAGES
-#define RSLAM_SR_STAGES 4
+#define RSLAM_SR_STAGES 2
 #endif
-constexpr int SR_BM = 64, SR_THREADS = 256, SR_LD = SR_BM + 4, SR_STAGES = RSLAM_SR_STAGES, SR_BK = 16, SR_KMAX = 256;
+constexpr int SR_BM = 64, SR_THREADS = 256, SR_LD = SR_BM + 4, SR_STAGES = RSLAM_SR_STAGES, SR_BK = 32, SR_KMAX = 256;
 inline int syrk_rows_smem_bytes(int kmax) { return (((kmax + SR_BK - 1) / SR_BK * SR_BK) * SR_LD + 2 * SR_STAGES * SR_BK * SR_LD) * (int)sizeof(double); }
 
 __device__ __forceinline__ void group_barrier(int g) { asm volatile("bar.sync %0, 128;\n" ::"r"(1 + g) : "memory"); }
