@@ -94,6 +94,7 @@ enum CtlSlot {
     CTL_NHYP = 8,
     CTL_WINNER = 9,   // winning hypothesis index in the u01 sequence
     CTL_WINNER_T = 10,// winning distinct hypothesis (index into ic_list)
+    CTL_JN_DONE = 11, // k_upd_jnorm_wide: CTAs that have finished (reset to 0 by the last one)
     CTL_SIZE = 16
 };
 

@@ -1546,5 +1546,74 @@ __device__ __forceinline__ void upd_jnorm_cta(DevFilter& F, const ParDev& par) {
 }
 __global__ void __launch_bounds__(256) k_upd_jnorm(DevFilter* Fs, ParDev par) { upd_jnorm_cta(Fs[blockIdx.y], par); }
 
+// The same for large maps: one CTA over 12013 columns of 4 strided rows is a 125 us latency chain (N = 2000); here CTA b takes columns
+// [256 b, 256 b + 256), every CTA forms Jn from the un-normalised quaternion, and the CTA that finishes LAST (a counter in the control
+// block) writes the normalised quaternion back -- nobody can read it after that.  CTA 0 also does the 4 x 4 block.
+__global__ void __launch_bounds__(256) k_upd_jnorm_wide(DevFilter* Fs, ParDev par) {
+    DevFilter& F = Fs[blockIdx.y];
+    if (F.ctl[CTL_K] <= 0) return;
+    __shared__ double sJ[16], sB[16], sT[16];
+    __shared__ int s_last;
+    const int ld = F.ldp;
+    double* P = F.P;
+    const double r = F.x_kk[3], x = F.x_kk[4], y = F.x_kk[5], z = F.x_kk[6];
+    const double s = r * r + x * x + y * y + z * z;
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    const bool mine = c < F.n && !(c >= 3 && c < 7);
+    double v[4];
+#pragma unroll
+    for (int l = 0; l < 4; l++) v[l] = mine ? P[(3 + l) + (size_t)c * ld] : 0.0;
+    if (threadIdx.x == 0) {
+        const double scale = (par.quirks & RSLAM_Q4_JNORM_INT_EXPONENT) ? 1.0 / s : 1.0 / (s * sqrt(s));
+        const double tv[16] = {x * x + y * y + z * z, -r * x, -r * y, -r * z, -x * r, r * r + y * y + z * z, -x * y, -x * z,
+                               -y * r, -y * x, r * r + x * x + z * z, -y * z, -z * r, -z * x, -z * y, r * r + x * x + y * y};
+        for (int e = 0; e < 16; e++) sJ[e] = scale * tv[e];
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 16) sB[threadIdx.x] = P[(3 + threadIdx.x / 4) + (size_t)(3 + threadIdx.x % 4) * ld];
+    __syncthreads();
+    if (blockIdx.x == 0) {
+        if (threadIdx.x < 16) {  // (Jn * B)
+            const int i = threadIdx.x / 4, j = threadIdx.x % 4;
+            double t = 0;
+            for (int l = 0; l < 4; l++) t += sJ[i * 4 + l] * sB[l * 4 + j];
+            sT[threadIdx.x] = t;
+        }
+        __syncthreads();
+        if (threadIdx.x < 16) {  // (Jn * B) * Jn^T
+            const int i = threadIdx.x / 4, j = threadIdx.x % 4;
+            double t = 0;
+            for (int l = 0; l < 4; l++) t += sT[i * 4 + l] * sJ[j * 4 + l];
+            if (i >= j) {
+                P[(3 + i) + (size_t)(3 + j) * ld] = t;
+                P[(3 + j) + (size_t)(3 + i) * ld] = t;
+            }
+        }
+    }
+    if (mine) {
+        double o[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) o[i] = sJ[i * 4] * v[0] + sJ[i * 4 + 1] * v[1] + sJ[i * 4 + 2] * v[2] + sJ[i * 4 + 3] * v[3];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            P[(3 + i) + (size_t)c * ld] = o[i];
+            P[c + (size_t)(3 + i) * ld] = o[i];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(&F.ctl[CTL_JN_DONE], 1) == (int)gridDim.x - 1;
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {  // every CTA has read the un-normalised quaternion
+        const double nrm = sqrt(s);
+        F.x_kk[3] = r / nrm;
+        F.x_kk[4] = x / nrm;
+        F.x_kk[5] = y / nrm;
+        F.x_kk[6] = z / nrm;
+        F.ctl[CTL_JN_DONE] = 0;
+    }
+}
+
 
 }  // namespace rslam

@@ -321,7 +321,13 @@ int run_update(rslam_filter* f, int which, bool gathered = false, bool defer_jno
             LAUNCH_N(f, "k_gemm_dmma/syrk_P", (k_gemm_dmma<64, 64>), dim3(ts * (ts + 1) / 2, 1, B), (GemmCfg<64, 64>::kThreads), (GemmCfg<64, 64>::kSmemBytes), f->dF, smode, 0);
         }
     }
-    if (!defer_jnorm) LAUNCH(f, k_upd_jnorm, dim3(1, B), 256, 0, f->dF, f->pard);  // deferred: fused into the head of the rescue kernel
+    if (!defer_jnorm) {  // deferred: fused into the head of the rescue kernel
+        if (n >= 4096) {
+            LAUNCH_N(f, "k_upd_jnorm", k_upd_jnorm_wide, dim3(cdiv(n, 256), B), 256, 0, f->dF, f->pard);
+        } else {
+            LAUNCH(f, k_upd_jnorm, dim3(1, B), 256, 0, f->dF, f->pard);
+        }
+    }
     return check_launch();
 }
 
