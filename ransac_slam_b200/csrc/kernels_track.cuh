@@ -1336,17 +1336,20 @@ __device__ __forceinline__ void gather_inliers(DevFilter& F, int which, int* s_s
 __global__ void __launch_bounds__(256) k_ransac_select(DevFilter* Fs, ParDev par, int gather_li, unsigned long long cond) {
     DevFilter& F = Fs[blockIdx.y];
     __shared__ int s_state[8];  // 1 max, 2 n_hyp, 3 winner i, 5 hyp_run, 6 status
-    __shared__ int s_sup[2048];
+    constexpr int kResolved = 8192;  // draws resolved to supports up front
+    __shared__ int s_sup[kResolved];
     const int nIC = F.ctl[CTL_NIC];
     const int n_u01 = F.n_u01;
     const double* u01 = F.u01;
     const int* support = F.support;
-    // the first 2048 draws are resolved to supports by the whole CTA up front (parallel, latency paid once)
-    {   // 8 draws per thread (256 threads): all uniforms first, then all supports -- two round trips instead of sixteen
+    // the first min(n_u01, 8192) draws are resolved to supports by the whole CTA up front (parallel, latency paid once per batch of 2048:
+    // beyond that the warp below pays two dependent round trips per 32 draws -- 86 us of this kernel's 90 at N = 2000, 4800 hypotheses)
+    for (int b0 = 0; b0 < kResolved && (b0 == 0 || b0 < n_u01); b0 += 2048) {
+        // 8 draws per thread (256 threads): all uniforms first, then all supports -- two round trips instead of sixteen
         double u[8];
 #pragma unroll
         for (int k = 0; k < 8; k++) {
-            const int i = threadIdx.x + k * 256;
+            const int i = b0 + threadIdx.x + k * 256;
             u[k] = (i < n_u01 && nIC > 0) ? u01[i] : -1.0;
         }
         int sv[8];
@@ -1359,7 +1362,7 @@ __global__ void __launch_bounds__(256) k_ransac_select(DevFilter* Fs, ParDev par
             }
         }
 #pragma unroll
-        for (int k = 0; k < 8; k++) s_sup[threadIdx.x + k * 256] = sv[k];
+        for (int k = 0; k < 8; k++) s_sup[b0 + threadIdx.x + k * 256] = sv[k];
     }
     __syncthreads();
     if (threadIdx.x < 32) {
@@ -1373,7 +1376,7 @@ __global__ void __launch_bounds__(256) k_ransac_select(DevFilter* Fs, ParDev par
         for (int base = 0; !done; base += 32) {
             const int i = base + lane;
             int s = -1;
-            if (i < 2048) {
+            if (i < kResolved && i < ((n_u01 + 2047) & ~2047)) {
                 s = s_sup[i];
             } else if (i < n_u01) {
                 const int pos = (int)floor(u01[i] * (double)nIC);
