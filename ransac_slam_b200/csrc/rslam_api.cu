@@ -86,6 +86,7 @@ struct rslam_filter {
     bool warp_patches = false;  // run pred_patch_fc on the device before the search
     bool upd_ws = false;
     bool chol2 = true;  // batches of small filters: k_chol_small with two CTAs per SM (RSLAM_CHOL2=0: one)
+    bool chol_outer_small = true;  // 64 x 64 tiles for the K = 256 trailing updates of the Cholesky (RSLAM_CHOL_OUTER_SMALL=0: 128 x 64)
     int trsm_ob = 16;  // outer-block width of the large-k TRSM in 64-column blocks (0: one left-looking launch); RSLAM_TRSM_OB overrides
     int hN = 0, hn = 0;  // max over filters of the uploaded N / n
     bool descr_dirty = false;
@@ -273,9 +274,16 @@ int run_update(rslam_filter* f, int which, bool gathered = false, bool defer_jno
             const int o = kNB * (s + 1);
             if (kmax <= o) break;
             if ((s + 1) % kOB == 0) {  // end of a 256-wide outer block: everything beyond it gets one K = 256 update
-                const int tm = cdiv(kmax - o, 128);
-                LAUNCH_N(f, "k_gemm_dmma/chol_outer", (k_gemm_dmma<128, 64>), dim3(tm * (tm + 1), 1, B), (GemmCfg<128, 64>::kThreads), (GemmCfg<128, 64>::kSmemBytes), f->dF,
-                         (int)GEMM_CHOL_OUTER, s / kOB);
+                // the trailing matrix of a K = 256 update is a few hundred 128 x 64 tiles -- one to three waves of 296 slots, the last one mostly
+                // empty; 64 x 64 tiles (three CTAs per SM, 444 slots, half the work each) waste less of the machine on these sizes
+                const int tm = cdiv(kmax - o, 128), ts = cdiv(kmax - o, 64);
+                if (f->chol_outer_small && (long long)ts * (ts + 1) / 2 * B <= 8 * 444) {
+                    LAUNCH_N(f, "k_gemm_dmma/chol_outer", (k_gemm_dmma<64, 64>), dim3(ts * (ts + 1) / 2, 1, B), (GemmCfg<64, 64>::kThreads), (GemmCfg<64, 64>::kSmemBytes), f->dF,
+                             (int)GEMM_CHOL_OUTER, s / kOB);
+                } else {
+                    LAUNCH_N(f, "k_gemm_dmma/chol_outer", (k_gemm_dmma<128, 64>), dim3(tm * (tm + 1), 1, B), (GemmCfg<128, 64>::kThreads), (GemmCfg<128, 64>::kSmemBytes), f->dF,
+                             (int)GEMM_CHOL_OUTER, s / kOB);
+                }
             }
         }
         LAUNCH(f, k_chol_trinv, dim3(nsteps, B), 256, kTrinvSmemBytes, f->dF);
@@ -389,6 +397,7 @@ int rslam_create(const rslam_camera* cam, const rslam_params* par, int max_featu
     f->lds = round_up(f->kmax, 16);
     f->mwords = cdiv(max_features, 32);
     if (const char* e = getenv("RSLAM_TRSM_OB")) f->trsm_ob = atoi(e);
+    if (const char* e = getenv("RSLAM_CHOL_OUTER_SMALL")) f->chol_outer_small = atoi(e) != 0;
     if (const char* e = getenv("RSLAM_CHOL2")) f->chol2 = atoi(e) != 0;
     if (const char* e = getenv("RSLAM_LI_CONDITIONAL")) f->li_conditional = atoi(e) != 0;
     f->cam = *cam;
