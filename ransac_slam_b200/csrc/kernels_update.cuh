@@ -945,8 +945,8 @@ __global__ void __launch_bounds__(WM * 64) k_trsm_ll(DevFilter* Fs, int jb0, int
 // ---- U5s: TRSM for SMALL innovation dimension (k <= 256).  The left-looking kernel above re-reads its own V rows from L2 for every
 // column block and waits on each of those round trips (26 % tensor-pipe utilisation, long-scoreboard bound, on the batched
 // configuration).  Here the CTA's 32 rows of W are loaded ONCE into shared memory and turned into V in place; the only streamed
-// operand is L (off-diagonal blocks, then the inverse of the diagonal block), through a 4-stage cp.async ring flattened over the
-// whole (column block, k-chunk) sequence, so every load is issued several chunks before it is needed.
+// operand is L (off-diagonal blocks, then the inverse of the diagonal block), through a two-stage cp.async ring of 32-deep k-chunks (the same bytes as
+// four stages of 16, half the chunk barriers) flattened over the whole (column block, k-chunk) sequence, so the next chunk is always in flight.
 constexpr int TS_R = 32, TS_THREADS = 128, TS_LDA = TS_R + 4, TS_LDB = kNB + 4, TS_STAGES = 2, TS_BK = 32, TS_CPB = kNB / TS_BK;  // chunks per 64-column block
 inline int trsm_small_smem_bytes(int kmax) { return (((kmax + kNB - 1) / kNB * kNB) * TS_LDA + TS_STAGES * TS_BK * TS_LDB) * (int)sizeof(double); }
 
@@ -1301,7 +1301,7 @@ __global__ void __launch_bounds__(GemmCfg<BM, BN>::kThreads, GemmCfg<BM, BN>::kM
 // 4096-filter batch.  Here a CTA owns a SEGMENT of one 64-row tile row of P:
 //   * its 64 x K block of V (the A operand) is loaded once and stays in shared memory for all tiles of the segment,
 //   * the tiles of the segment are dealt alternately to TWO independent warp groups (4 warps each, one warp per SM sub-partition,
-//     warp tile 32 x 32); each group streams its B operand through its own 4-stage cp.async ring, FLATTENED over
+//     warp tile 32 x 32); each group streams its B operand through its own two-stage cp.async ring of 32-deep k-chunks, FLATTENED over
 //     (tile, k-chunk) so that the pipeline never drains, and synchronises on its own named barrier -- the groups drift apart, and
 //     one group's barrier / fragment-load bubbles are covered by the other group's DMMA stream (what two co-resident CTAs would
 //     do, without paying for the resident A twice),
