@@ -1,5 +1,5 @@
 """A fixed slice of tools/fuzz_parity.py: random small scenes (map sizes 1 .. 70, every combination of the quirk switches), three frames
-each through rslam_frame, against the CPU oracle (dense and sparse mode alternate): match / inlier sets, RANSAC replay counters bit for
+each through rslam_frame (every third case with the patch warp on), against the CPU oracle (dense and sparse mode alternate): match / inlier sets, RANSAC replay counters bit for
 bit, x and P to 1e-9, P exactly symmetric."""
 import os
 import sys

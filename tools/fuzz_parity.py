@@ -12,7 +12,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from oracle import oracle_py as O  # noqa: E402
-from ransac_slam_b200 import synth  # noqa: E402
+from ransac_slam_b200 import capi, synth  # noqa: E402
 from tests import helpers as H  # noqa: E402
 
 QUIRKS = (0x7, 0x6, 0x5, 0x3, 0x0)  # C-ABI masks: Q1 | Q4 | Q6 in every useful combination
@@ -21,15 +21,27 @@ QUIRKS = (0x7, 0x6, 0x5, 0x3, 0x0)  # C-ABI masks: Q1 | Q4 | Q6 in every useful 
 def case_params(case):
     rng = np.random.default_rng(90000 + case)
     N = int(rng.choice([1, 2, 3, 5, 8, 13, 16, 17, 31, 32, 33, 47, 64, 65, 70]))
-    return dict(N=N, quirks=int(rng.choice(QUIRKS)), seed=int(rng.integers(1, 1 << 30)), T=3)
+    # every third case runs with the patch warp (Tracking::pred_patch_fc) on both sides: smooth 41 x 41 appearances, the 13 x 13 predicted
+    # patches warped from them by the device and by the oracle instead of uploaded
+    return dict(N=N, quirks=int(rng.choice(QUIRKS)), seed=int(rng.integers(1, 1 << 30)), T=3, warp=(case % 3 == 2))
 
 
 def run_case(case, verbose=False):
     p = case_params(case)
-    scene = synth.make_scene(N=p["N"], seed=p["seed"])
+    scene = synth.make_scene(N=p["N"], seed=p["seed"], texture="smooth" if p["warp"] else "noise")
     seq = synth.make_sequence(scene, T=p["T"], seed=p["seed"] + 1, u01_seed=p["seed"] + 2)
-    o = H.oracle_from(scene, scene.x0, scene.P0, prior=False, sparse=bool(case & 1), quirks=p["quirks"] | O.Q11)
-    g = H.gpu_from(scene, scene.x0, scene.P0, prior=False, quirks=p["quirks"])
+    if p["warp"]:
+        o = O.OracleFilter(scene.cam.as9(), std_z=scene.std_z, quirks=p["quirks"] | O.Q11, sparse=bool(case & 1), fast_corr=True, warp_patches=True)
+        for i in range(scene.N):
+            o.add_feature(0, scene.init_patches[i], None, scene.x0[:3], np.eye(3), scene.uv0[i])
+        o.set_state(scene.x0, scene.P0, prior=False)
+        g = capi.Filter(scene.cam.as9(), scene.N, quirks=p["quirks"], std_z=scene.std_z)
+        g.upload_state(scene.x0, scene.P0, prior=False)
+        g.upload_feature_init(scene.init_patches, np.tile(scene.x0[:3], (scene.N, 1)), np.tile(np.eye(3).reshape(1, 9), (scene.N, 1)), scene.uv0)
+        g.set_patch_warp(True)
+    else:
+        o = H.oracle_from(scene, scene.x0, scene.P0, prior=False, sparse=bool(case & 1), quirks=p["quirks"] | O.Q11)
+        g = H.gpu_from(scene, scene.x0, scene.P0, prior=False, quirks=p["quirks"])
     stats = dict(ic=0, li=0, hi=0)
     for k in range(p["T"]):
         rc_o, ro = o.frame(seq.images[k], seq.u01[k])
