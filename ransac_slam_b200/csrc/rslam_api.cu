@@ -240,6 +240,8 @@ int run_update(rslam_filter* f, int which, bool gathered = false, bool defer_jno
     if (N == 0) return 0;
     const int kmax = 2 * N;
     const int nsteps = cdiv(kmax, kNB);
+    // k_upd_W is a thread per state row: 128-thread CTAs when they leave fewer idle rows (n = 613: 640 threads instead of 768)
+    const int wbs = round_up(n, 128) < round_up(n, 256) ? 128 : 256;
     if (!gathered) LAUNCH(f, k_upd_gather, dim3(1, B), 256, 0, f->dF, which);
     if (kmax <= kCholSmallMaxK && B == 1) {
         // latency path of one small filter: S comes straight from P, so W = P H^T (needed only by the TRSM) runs on the side stream
@@ -251,14 +253,14 @@ int run_update(rslam_filter* f, int which, bool gathered = false, bool defer_jno
             CK(cudaEventRecord(f->ev_fork, f->stream));
             CK(cudaStreamWaitEvent(f->side, f->ev_fork, 0));
         }
-        LAUNCH_ON(f, ws, "k_upd_W", k_upd_W, dim3(cdiv(n, 256), cdiv(N, kWChunk), B), 256, 0, f->dF);
+        LAUNCH_ON(f, ws, "k_upd_W", k_upd_W, dim3(cdiv(n, wbs), cdiv(N, kWChunk), B), wbs, 0, f->dF);
         if (fork) CK(cudaEventRecord(f->ev_join, f->side));
         LAUNCH_N(f, "k_upd_S", k_upd_S_direct, dim3(cdiv(N * (N + 1) / 2, 8), 1, B), 256, 0, f->dF);
         LAUNCH_N(f, "k_chol_small", (k_chol_small<kTld, 1>), dim3(1, B), 256, kCholSmallSmemBytes, f->dF);
         LAUNCH(f, k_chol_trinv, dim3(nsteps, B), 256, kTrinvSmemBytes, f->dF);
         if (fork) CK(cudaStreamWaitEvent(f->stream, f->ev_join, 0));
     } else if (kmax <= kCholSmallMaxK) {
-        LAUNCH(f, k_upd_W, dim3(cdiv(n, 256), cdiv(N, kWChunk), B), 256, 0, f->dF);
+        LAUNCH(f, k_upd_W, dim3(cdiv(n, wbs), cdiv(N, kWChunk), B), wbs, 0, f->dF);
         LAUNCH(f, k_upd_S, dim3(cdiv(N, 16), cdiv(N, 16), B), 256, 0, f->dF);
         if (f->chol2 && kmax + kNB <= kCholSmallLd2 + kNB && kmax <= 200 && B >= 2 * 148) {  // two CTAs per SM
             LAUNCH_N(f, "k_chol_small", (k_chol_small<kCholSmallLd2, 2>), dim3(1, B), 256, kCholSmall2SmemBytes, f->dF);
@@ -267,7 +269,7 @@ int run_update(rslam_filter* f, int which, bool gathered = false, bool defer_jno
         }
         LAUNCH(f, k_chol_trinv, dim3(nsteps, B), 256, kTrinvSmemBytes, f->dF);
     } else {
-        LAUNCH(f, k_upd_W, dim3(cdiv(n, 256), cdiv(N, kWChunk), B), 256, 0, f->dF);
+        LAUNCH(f, k_upd_W, dim3(cdiv(n, wbs), cdiv(N, kWChunk), B), wbs, 0, f->dF);
         LAUNCH(f, k_upd_S, dim3(cdiv(N, 16), cdiv(N, 16), B), 256, 0, f->dF);
         for (int s = 0; s < nsteps; s++) {
             LAUNCH(f, k_chol_panel, dim3(nsteps - s, B), 256, kPanelSmemBytes, f->dF, s);
