@@ -20,7 +20,10 @@ QUIRKS = (0x7, 0x6, 0x5, 0x3, 0x0)  # C-ABI masks: Q1 | Q4 | Q6 in every useful 
 
 def case_params(case):
     rng = np.random.default_rng(90000 + case)
-    N = int(rng.choice([1, 2, 3, 5, 8, 13, 16, 17, 31, 32, 33, 47, 64, 65, 70]))
+    if case >= 10000:  # larger maps: the multi-CTA rescue (N > 128), the two RANSAC set-up paths (N <= 256 / N > 256), four-panel Cholesky
+        N = int(rng.choice([100, 128, 129, 200, 256, 257, 300]))
+    else:
+        N = int(rng.choice([1, 2, 3, 5, 8, 13, 16, 17, 31, 32, 33, 47, 64, 65, 70]))
     # every third case runs with the patch warp (Tracking::pred_patch_fc) on both sides: smooth 41 x 41 appearances, the 13 x 13 predicted
     # patches warped from them by the device and by the oracle instead of uploaded
     return dict(N=N, quirks=int(rng.choice(QUIRKS)), seed=int(rng.integers(1, 1 << 30)), T=3, warp=(case % 3 == 2))
